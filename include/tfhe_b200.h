@@ -1,0 +1,140 @@
+/* tfhe_b200.h -- C ABI of the B200-native batched TFHE/FHEW bootstrapping engine (libtfhe_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of eric070021/TFHE-GPU (paths below are relative to
+ * /root/reference/src/binfhe).  Every entry point replaces one reference operator; the reference-side
+ * binding (a ~150-line C++ shim defining lbcrypto::GPUFFTBootstrap::* / GPULWEOperation::*) is
+ * tfhe_gpu_b200/adapter/binfhe_b200_shim.cpp and is described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative tfhe_b200_status; tfhe_b200_last_error() gives the
+ *     message (the reference prints and std::exit()s instead: lib/bootstrapping.cu:28-37)
+ *   - all integers are little-endian uint64_t, exactly the memory image of OpenFHE's NativeInteger /
+ *     NativeVector (&v[0]), so the shim can pass OpenFHE buffers without conversion
+ *   - an LWE ciphertext of dimension m is (m+1) words: a[0..m-1], b; batches are dense row-major
+ *   - `space` says whether ciphertext / LUT / matrix pointers are host memory (TFHE_B200_HOST; copied through
+ *     pinned staging inside the call) or device memory on the handle's first GPU (TFHE_B200_DEVICE)
+ *   - calls are synchronous (like the reference: lib/bootstrapping.cu:1642-1646) and re-entrant per handle
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with TFHE_B200_ENODEV
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tfhe_b200_status {
+    TFHE_B200_OK      = 0,
+    TFHE_B200_EINVAL  = -1, /* bad argument (OPENFHE_THROW(openfhe_error / config_error) in the reference)      */
+    TFHE_B200_ENODEV  = -2, /* no usable CUDA device                                                             */
+    TFHE_B200_ECUDA   = -3, /* CUDA runtime error, message has the details                                       */
+    TFHE_B200_ENOTSUP = -4, /* parameter combination the engine has no kernel for (reference: exit(1))           */
+    TFHE_B200_ENOMEM  = -5
+} tfhe_b200_status;
+
+enum { TFHE_B200_HOST = 0, TFHE_B200_DEVICE = 1 };
+enum { TFHE_B200_METHOD_AP = 1, TFHE_B200_METHOD_GINX = 2 };            /* include/binfhe-constants.h:94-98 */
+/* include/binfhe-constants.h:101 */
+enum { TFHE_B200_OR = 0, TFHE_B200_AND, TFHE_B200_NOR, TFHE_B200_NAND, TFHE_B200_XOR_FAST, TFHE_B200_XNOR_FAST,
+       TFHE_B200_XOR, TFHE_B200_XNOR };
+
+/* Flattened BinFHECryptoParams (replaces the reference's params_CUDA[10], lib/bootstrapping.cu:917-929). */
+typedef struct tfhe_b200_params {
+    uint32_t n, N;                 /* LWE dimension, ring dimension                                            */
+    uint64_t q, Q, qKS;            /* LWE modulus, RLWE/RGSW prime modulus, key-switch modulus                 */
+    uint32_t baseKS, dKS;          /* key-switch base and digit count ceil(log qKS / log baseKS)               */
+    uint32_t baseG, digitsG, numDigitsToThrow;
+    uint32_t baseR, digitsR;       /* AP/DM refresh base and digit count (0 for GINX)                          */
+    uint32_t method;               /* TFHE_B200_METHOD_*                                                       */
+    uint32_t reserved;
+    uint64_t psi;                  /* primitive 2N-th root of unity the BK polynomials were transformed with
+                                      (ILNativeParams::GetRootOfUnity(); the engine uses the same bit-reversed
+                                      evaluation order as core/include/math/hal/intnat/transformnat-impl.h)   */
+    uint64_t beta;                 /* BinFHEContext::GetBeta(), include/binfhecontext.h:348                    */
+} tfhe_b200_params;
+
+typedef struct tfhe_b200_handle tfhe_b200_handle;
+
+/* Per-call phase timings in milliseconds (CUDA events), filled when stats != NULL.  Replaces the commented-out
+ * std::chrono blocks of the reference (lib/bootstrapping.cu:1610,1678-1680,1829-1831,1918-1920). */
+typedef struct tfhe_b200_stats {
+    float h2d_ms, prep_ms, blind_rotate_ms, keyswitch_ms, d2h_ms, total_ms;
+    uint32_t bootstraps;           /* number of blind rotations per input performed by the call                */
+    uint32_t kernel_launches;      /* kernels launched by the call on all GPUs                                 */
+} tfhe_b200_stats;
+
+/* --------------------------------------------------------------------------------------------------------
+ * Lifetime.  Replaces GPUFFTBootstrap::GPUSetup/GPUClean (include/bootstrapping.cuh:104-109,
+ * lib/bootstrapping.cu:725-1110) and GPULWEOperation::GPUSetup/GPUClean (include/lwe-operation.cuh:57-62).
+ *
+ *   bk : bootstrapping key in the reference's own element order, EVALUATION format, one u64 per coefficient
+ *        GINX: [key(2)][i(n)][l(d)][j(2)][N], d = 2*(digitsG-numDigitsToThrow)   == (*BSkey)[0][key][i]->[l][j]
+ *        AP  : [i(n)][a0(baseR)][k(digitsR)][l(d)][j(2)][N], d = 2*digitsG       == (*BSkey)[i][a0][k]->[l][j]
+ *   ksk: [i(N)][a0(baseKS)][j(dKS)][n+1]  (A row, then B)  == the flattening of lib/bootstrapping.cu:961-975
+ *   key_space: TFHE_B200_HOST or TFHE_B200_DEVICE (device = already broadcast to this process's GPU, e.g. by NCCL)
+ *   num_gpus : GPUs driven by THIS process (0 = all visible), devices first_device .. first_device+num_gpus-1;
+ *              keys are uploaded once and replicated peer-to-peer, the batch is split evenly, no collectives
+ * -------------------------------------------------------------------------------------------------------- */
+int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* bk, size_t bk_words, const uint64_t* ksk,
+                    size_t ksk_words, int key_space, int first_device, int num_gpus, tfhe_b200_handle** out);
+int tfhe_b200_clean(tfhe_b200_handle* h);
+const char* tfhe_b200_last_error(void);
+int tfhe_b200_num_gpus(const tfhe_b200_handle* h);
+/* expected key sizes for a parameter set (words) */
+size_t tfhe_b200_bk_words(const tfhe_b200_params* params);
+size_t tfhe_b200_ksk_words(const tfhe_b200_params* params);
+/* name of the blind-rotation kernel variant the handle dispatches to ("cggi_u32_ntt32", "generic_u64", ...) */
+const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h);
+/* tuning knob: force the generic kernel (used by tests to cross-check the two implementations) */
+int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value);
+
+/* --------------------------------------------------------------------------------------------------------
+ * Operator-level entry points (what the reference's host code calls).
+ * -------------------------------------------------------------------------------------------------------- */
+/* GPUFFTBootstrap::EvalAcc_CUDA (include/bootstrapping.cuh:111-124, lib/bootstrapping.cu:1139-1853).
+ * a: [batch][n] mask, modulus ct_mod; acc: [batch][2][N] in COEFFICIENT format on entry and exit; on exit the
+ * a-polynomial is already transposed (a(X) -> a(X^-1)), exactly as the reference kernel leaves it. */
+int tfhe_b200_eval_acc(tfhe_b200_handle* h, int batch, const uint64_t* a, uint64_t ct_mod, uint64_t* acc, int space,
+                       tfhe_b200_stats* stats);
+/* GPUFFTBootstrap::MKMSwitch_CUDA (include/bootstrapping.cuh:126-136, lib/bootstrapping.cu:73-118,1855-1935):
+ * ModSwitch Q->qKS, KeySwitch, ModSwitch qKS->fmod.  in: [batch][N+1] mod Q, out: [batch][n+1] mod fmod. */
+int tfhe_b200_mkmswitch(tfhe_b200_handle* h, int batch, const uint64_t* in, uint64_t fmod, uint64_t* out, int space,
+                        tfhe_b200_stats* stats);
+/* GPULWEOperation::CiphertextMulMatrix_CUDA (include/lwe-operation.cuh:49-50, lib/lwe-operation.cu:50-141):
+ * out[i] = sum_k ct[k] * matrix[k][i] mod modulus.  ct: [in][n+1], matrix: [in][out_cols] row-major int64,
+ * out: [out_cols][n+1].  Exact integer arithmetic (the reference uses FP64 and is exact only below 2^53). */
+int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, const uint64_t* ct, const int64_t* matrix,
+                         uint64_t modulus, uint64_t* out, int space, tfhe_b200_stats* stats);
+
+/* --------------------------------------------------------------------------------------------------------
+ * Fused batched API: one call == one BinFHEContext batched method (lib/binfhecontext.cpp:319-347 ->
+ * lib/binfhe-base-scheme.cpp:598-1277).  Ciphertexts stay on the device between the bootstraps of a call.
+ * -------------------------------------------------------------------------------------------------------- */
+/* BinFHEContext::EvalBinGate(gate, vector, vector); ct modulus = ct_mod (normally q). */
+int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch, const uint64_t* ct1, const uint64_t* ct2,
+                            uint64_t ct_mod, uint64_t* out, int space, tfhe_b200_stats* stats);
+/* BinFHEScheme::BootstrapFunc(vector) (lib/binfhe-base-scheme.cpp:1194-1211, 1260-1277): table[x] = f(x, ct_mod,
+ * fmod) for x < ct_mod; per_ct != 0 => one table per ciphertext ([batch][ct_mod]).  Output modulus fmod. */
+int tfhe_b200_bootstrap_func(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod,
+                             const uint64_t* table, int per_ct, uint64_t fmod, uint64_t* out, int space,
+                             tfhe_b200_stats* stats);
+/* BinFHEContext::EvalFunc(vector, LUT) / (vector, LUT_vec): lut has ct_mod entries (per_ct: [batch][ct_mod]). */
+int tfhe_b200_eval_func(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod, const uint64_t* lut,
+                        size_t lut_len, int per_ct, uint64_t* out, int space, tfhe_b200_stats* stats);
+/* BinFHEContext::EvalFloor(vector, roundbits) */
+int tfhe_b200_eval_floor(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod, uint32_t roundbits,
+                         uint64_t* out, int space, tfhe_b200_stats* stats);
+/* BinFHEContext::EvalSign(vector): output modulus q */
+int tfhe_b200_eval_sign(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod, uint64_t* out,
+                        int space, tfhe_b200_stats* stats);
+/* BinFHEContext::EvalDecomp(vector): out [batch][max_digits][n+1]; returns the digit count (>0) or a negative
+ * status; out_mods[k] (host memory) receives the modulus of digit k. */
+int tfhe_b200_eval_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod, int max_digits,
+                          uint64_t* out, uint64_t* out_mods, int space, tfhe_b200_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFHE_B200_H */

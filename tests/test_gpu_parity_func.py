@@ -1,0 +1,128 @@
+"""GPU parity: EvalFunc / EvalFloor / EvalSign / EvalDecomp / CiphertextMulMatrix through the C ABI vs the oracle.
+
+Cases mirror the reference's UnitTestFunc.cpp (x^3 mod p LUT over all inputs, floor around p/2, sign and digit
+decomposition of large-precision inputs) and examples/GEMM.cpp, at the bit level and through the batched API.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _lut_cube(q, p):
+    return np.array([((x // (q // p)) ** 3 % p) * (q // p) for x in range(q)], dtype=np.uint64)
+
+
+@pytest.mark.parametrize("name", ["toy_func12", "toy_func12_throw1"])
+def test_eval_func_arbitrary_lut(keyset, name):
+    ks = keyset(name)
+    q = ks.p.q
+    p = q // (2 * ks.p.beta)
+    lut = _lut_cube(q, p)
+    msgs = [i % p for i in range(2 * p)]
+    ct = ks.port.encrypt_batch(ks.sk, msgs, p, q, 11)
+    want = ks.port.eval_func(ks.bk, ks.ksk, ct, q, lut)
+    got = ks.gpu().EvalFunc(ct, lut)
+    assert np.array_equal(got, want)
+    assert ks.gpu().last_stats.bootstraps == 2
+    if name == "toy_func12":
+        assert ks.port.decrypt_batch(ks.sk, got, q, p) == [m ** 3 % p for m in msgs]
+
+
+def test_eval_func_negacyclic_and_periodic(keyset):
+    ks = keyset("toy_func12")
+    q = ks.p.q
+    p = q // (2 * ks.p.beta)
+    ct = ks.port.encrypt_batch(ks.sk, list(range(p)), p, q, 12)
+    neg = np.array([(x % (q // 2)) + 1 for x in range(q)], dtype=np.uint64)
+    neg[q // 2:] = q - neg[: q // 2]
+    per = np.array([((x % (q // 2)) * 5) % q for x in range(q)], dtype=np.uint64)
+    for lut, nboot in ((neg, 1), (per, 2)):
+        want = ks.port.eval_func(ks.bk, ks.ksk, ct, q, lut)
+        got = ks.gpu().EvalFunc(ct, lut)
+        assert np.array_equal(got, want)
+        assert ks.gpu().last_stats.bootstraps == nboot
+
+
+def test_eval_func_lut_vec(keyset):
+    """EvalFunc(vector, LUT_vec): one LUT per ciphertext (binfhe-base-scheme.cpp:791-924)."""
+    ks = keyset("toy_func12")
+    q = ks.p.q
+    p = q // (2 * ks.p.beta)
+    msgs = list(range(p))
+    ct = ks.port.encrypt_batch(ks.sk, msgs, p, q, 13)
+    luts = np.stack([np.array([(((x // (q // p)) * (k + 1) + k) % p) * (q // p) for x in range(q)], dtype=np.uint64)
+                     for k in range(len(msgs))])
+    want = ks.port.eval_func(ks.bk, ks.ksk, ct, q, luts)
+    got = ks.gpu().EvalFunc(ct, luts)
+    assert np.array_equal(got, want)
+    assert ks.port.decrypt_batch(ks.sk, got, q, p) == [(m * (k + 1) + k) % p for k, m in enumerate(msgs)]
+
+
+def test_eval_func_small_ring_logq11(keyset):
+    """logQ = 11: N=1024, 27-bit Q, baseG=32 (12 digit polynomials), q = 2N (negacyclic / periodic LUTs only)."""
+    ks = keyset("toy_func11")
+    q = ks.p.q
+    p = q // (2 * ks.p.beta)
+    ct = ks.port.encrypt_batch(ks.sk, list(range(p)), p, q, 14)
+    per = np.array([((x // (q // p)) % (p // 2)) * (q // p) for x in range(q)], dtype=np.uint64)
+    per[q // 2:] = per[: q // 2]
+    want = ks.port.eval_func(ks.bk, ks.ksk, ct, q, per)
+    got = ks.gpu().EvalFunc(ct, per)
+    assert np.array_equal(got, want)
+
+
+def _big_inputs(ks, logQ, count):
+    Qin = 1 << logQ
+    q = ks.p.q
+    P = Qin // q * (q // (2 * ks.p.beta))
+    msgs = [P // 2 + i - 3 for i in range(count)]
+    return Qin, P, msgs, ks.port.encrypt_batch(ks.sk, msgs, P, Qin, 15)
+
+
+def test_eval_floor(keyset):
+    ks = keyset("toy_sign17")
+    Qin, P, msgs, ct = _big_inputs(ks, 17, 8)
+    want = ks.port.eval_floor(ks.bk, ks.ksk, ct, Qin)
+    got = ks.gpu().EvalFloor(ct, Qin)
+    assert np.array_equal(got, want)
+    assert ks.gpu().last_stats.bootstraps == 2
+
+
+def test_eval_sign(keyset):
+    ks = keyset("toy_sign17")
+    Qin, P, msgs, ct = _big_inputs(ks, 17, 8)
+    want = ks.port.eval_sign(ks.bk, ks.ksk, ct, Qin)
+    got = ks.gpu().EvalSign(ct, Qin)
+    assert np.array_equal(got, want)
+    assert ks.gpu().last_stats.bootstraps == 5           # logQ=17: 2 floors (4) + final
+    assert ks.port.decrypt_batch(ks.sk, got, ks.p.q, 2) == [int(m >= P // 2) for m in msgs]
+
+
+def test_eval_decomp(keyset):
+    ks = keyset("toy_sign17")
+    Qin, P, msgs, ct = _big_inputs(ks, 17, 8)
+    want, wmods = ks.port.eval_decomp(ks.bk, ks.ksk, ct, Qin)
+    got, gmods = ks.gpu().EvalDecomp(ct, Qin)
+    assert gmods == wmods == [4096, 4096, 512]
+    assert np.array_equal(got, want)
+    assert ks.gpu().last_stats.bootstraps == 4
+
+
+def test_ciphertext_mul_matrix(keyset, rng):
+    """examples/GEMM.cpp: random ciphertexts x matrix with entries < 64, element-wise vs the exact CPU product."""
+    ks = keyset("toy_func12")
+    n, qKS = ks.p.n, ks.p.qKS
+    ct = rng.integers(0, qKS, (48, n + 1), dtype=np.uint64)
+    M = rng.integers(0, 64, (48, 40), dtype=np.int64)
+    want = ks.port.mul_matrix(ct, M, qKS)
+    got = ks.gpu().CiphertextMulMatrix(ct, M, qKS)
+    assert np.array_equal(got, want)
+    # independent check with Python big integers
+    ref = (ct.astype(object).T @ M.astype(object)) % int(qKS)
+    assert np.array_equal(got.astype(object), ref.T)
+    # negative entries: Euclidean residue (the reference's FP64 path is undefined there, lwe-operation.cu:123)
+    M2 = rng.integers(-64, 64, (48, 5), dtype=np.int64)
+    got2 = ks.gpu().CiphertextMulMatrix(ct, M2, qKS)
+    ref2 = (ct.astype(object).T @ M2.astype(object)) % int(qKS)
+    assert np.array_equal(got2.astype(object), ref2.T)

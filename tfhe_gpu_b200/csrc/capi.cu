@@ -1,0 +1,1175 @@
+// C ABI of libtfhe_b200.so (see include/tfhe_b200.h) and the host-side orchestration of the batched operations.
+//
+// The control flow of every batched method re-expresses the reference's host code
+// (binfhe-base-scheme.cpp:598-1277) as a sequence of device kernels over device-resident ciphertext batches:
+// nothing returns to the host between the bootstraps of one call (the reference round-trips through
+// std::vector<LWECiphertext> twice per bootstrap, bootstrapping.cu:1616-1667,1877-1905).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.cuh"
+
+using namespace tfhe_b200;
+
+static thread_local std::string g_err;
+
+#define CUDA_TRY(x)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e__ = (x);                                                                             \
+        if (e__ != cudaSuccess) {                                                                          \
+            char buf__[512];                                                                               \
+            snprintf(buf__, sizeof(buf__), "%s:%d: %s failed: %s", __FILE__, __LINE__, #x,                 \
+                     cudaGetErrorString(e__));                                                             \
+            g_err = buf__;                                                                                 \
+            return TFHE_B200_ECUDA;                                                                        \
+        }                                                                                                  \
+    } while (0)
+
+#define FAIL(code, msg)  \
+    do {                 \
+        g_err = (msg);   \
+        return (code);   \
+    } while (0)
+
+namespace {
+
+struct Arena {
+    unsigned char* base = nullptr;
+    size_t cap = 0, off = 0;
+};
+
+struct Dev {
+    int id = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    // key material / tables
+    void* bk_generic = nullptr;
+    u32* bk_cggi32 = nullptr;
+    void* tw_fwd = nullptr;
+    void* tw_inv = nullptr;
+    void* psi_pow = nullptr;
+    u32* twA = nullptr;
+    u32* twB = nullptr;
+    void* ksk = nullptr;
+    Arena ws;
+};
+
+}  // namespace
+
+struct tfhe_b200_handle {
+    tfhe_b200_params p;
+    bool is64 = false;
+    bool have_cggi32 = false;
+    int force_generic = 0;
+    int group = 0;  // ciphertexts per CTA of the cggi32 kernel (0 = default)
+    u32 logN = 0, d = 0, gBits = 0;
+    ModCtx<u32> m32;
+    ModCtx<u64> m64;
+    int ksk_bytes = 8;
+    u32 row_stride = 0;
+    size_t bk_words = 0, ksk_words = 0;
+    std::vector<Dev> devs;
+    std::string variant;
+    std::mutex mu;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------------------
+static size_t bk_words_of(const tfhe_b200_params* p) {
+    size_t N = p->N, n = p->n;
+    if (p->method == TFHE_B200_METHOD_GINX)
+        return 2 * n * (size_t)(2 * (p->digitsG - p->numDigitsToThrow)) * 2 * N;
+    return n * (size_t)p->baseR * p->digitsR * (size_t)(2 * p->digitsG) * 2 * N;
+}
+static size_t ksk_words_of(const tfhe_b200_params* p) {
+    return (size_t)p->N * p->baseKS * p->dKS * (p->n + 1);
+}
+
+static int arena_reserve(Dev& d, size_t bytes) {
+    if (bytes <= d.ws.cap) {
+        d.ws.off = 0;
+        return 0;
+    }
+    CUDA_TRY(cudaSetDevice(d.id));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    if (d.ws.base)
+        CUDA_TRY(cudaFree(d.ws.base));
+    d.ws.base = nullptr;
+    d.ws.cap = 0;
+    size_t cap = bytes + (bytes >> 3) + (1 << 20);
+    CUDA_TRY(cudaMalloc((void**)&d.ws.base, cap));
+    d.ws.cap = cap;
+    d.ws.off = 0;
+    return 0;
+}
+template <typename T>
+static T* arena_take(Dev& d, size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (d.ws.off + bytes > d.ws.cap)
+        return nullptr;
+    T* p = reinterpret_cast<T*>(d.ws.base + d.ws.off);
+    d.ws.off += bytes;
+    return p;
+}
+
+static u32 bitrev32(u32 x, u32 bits) {
+    u32 r = 0;
+    for (u32 i = 0; i < bits; i++) {
+        r = (r << 1) | (x & 1);
+        x >>= 1;
+    }
+    return r;
+}
+
+// shard [start, start+count) of the batch owned by device k of nd
+static void shard_of(int batch, int nd, int k, int* start, int* count) {
+    int base = batch / nd, rem = batch % nd;
+    *start = k * base + (k < rem ? k : rem);
+    *count = base + (k < rem ? 1 : 0);
+}
+
+static int copy_in(Dev& d, Dev& d0, void* dst, const void* src, size_t bytes, int space) {
+    if (!bytes)
+        return 0;
+    if (space == TFHE_B200_HOST)
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.stream));
+    else if (d.id == d0.id)
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, d.stream));
+    else
+        CUDA_TRY(cudaMemcpyPeerAsync(dst, d.id, src, d0.id, bytes, d.stream));
+    return 0;
+}
+static int copy_out(Dev& d, Dev& d0, void* dst, const void* src, size_t bytes, int space) {
+    if (!bytes)
+        return 0;
+    if (space == TFHE_B200_HOST)
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d.stream));
+    else if (d.id == d0.id)
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, d.stream));
+    else
+        CUDA_TRY(cudaMemcpyPeerAsync(dst, d0.id, src, d.id, bytes, d.stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// setup
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static int build_tables(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M) {
+    const tfhe_b200_params& p = h->p;
+    const u64 Q = p.Q, N = p.N;
+    std::vector<T> fw(N), iv(N), pp(2 * N);
+    u64 psi = p.psi % Q, psii = h_powmod(psi, Q - 2, Q);
+    u64 x = 1, xi = 1;
+    for (u64 k = 0; k < N; k++) {
+        u32 r = bitrev32((u32)k, h->logN);
+        fw[r] = to_mont<T>(x, M);
+        iv[r] = to_mont<T>(xi, M);
+        x = h_mulmod(x, psi, Q);
+        xi = h_mulmod(xi, psii, Q);
+    }
+    x = 1;
+    for (u64 k = 0; k < 2 * N; k++) {
+        pp[k] = to_mont<T>(x, M);
+        x = h_mulmod(x, psi, Q);
+    }
+    CUDA_TRY(cudaMalloc(&d.tw_fwd, N * sizeof(T)));
+    CUDA_TRY(cudaMalloc(&d.tw_inv, N * sizeof(T)));
+    CUDA_TRY(cudaMalloc(&d.psi_pow, 2 * N * sizeof(T)));
+    CUDA_TRY(cudaMemcpy(d.tw_fwd, fw.data(), N * sizeof(T), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.tw_inv, iv.data(), N * sizeof(T), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d.psi_pow, pp.data(), 2 * N * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// upload + re-encode the keys on device 0
+template <typename T>
+static int encode_keys(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M, const u64* bk, const u64* ksk, int key_space) {
+    const tfhe_b200_params& p = h->p;
+    const u64 Q = p.Q;
+    u64 ninv = h_powmod(p.N, Q - 2, Q);
+    u64 R = (u64)M.oneM;
+    T ninvM2 = (T)h_mulmod(h_mulmod(ninv, R, Q), R, Q);  // N^-1 * R^2: mont_mul(x, .) = x * N^-1 * R
+    const size_t stage_words = (size_t)4 << 20;           // 32 MiB staging for host-resident keys
+    u64* stage = nullptr;
+    if (key_space == TFHE_B200_HOST)
+        CUDA_TRY(cudaMalloc((void**)&stage, stage_words * sizeof(u64)));
+
+    // ---- bootstrapping key, generic layout (same element order as the source) ----
+    const bool need_generic = true;
+    if (need_generic) {
+        CUDA_TRY(cudaMalloc(&d.bk_generic, h->bk_words * sizeof(T)));
+        if (key_space == TFHE_B200_DEVICE)
+            CUDA_TRY(launch_bk_convert_generic<T>((T*)d.bk_generic, bk, h->bk_words, M, ninvM2, d.stream));
+        else {
+            for (size_t off = 0; off < h->bk_words; off += stage_words) {
+                size_t cnt = h->bk_words - off < stage_words ? h->bk_words - off : stage_words;
+                CUDA_TRY(cudaMemcpyAsync(stage, bk + off, cnt * sizeof(u64), cudaMemcpyHostToDevice, d.stream));
+                CUDA_TRY(launch_bk_convert_generic<T>((T*)d.bk_generic + off, stage, cnt, M, ninvM2, d.stream));
+                CUDA_TRY(cudaStreamSynchronize(d.stream));
+            }
+        }
+    }
+    // ---- key switching key: narrowest word, 16-byte padded rows ----
+    {
+        const size_t rows = (size_t)p.N * p.baseKS * p.dKS;
+        const u32 words = p.n + 1;
+        CUDA_TRY(cudaMalloc(&d.ksk, rows * h->row_stride * h->ksk_bytes));
+        if (key_space == TFHE_B200_DEVICE)
+            CUDA_TRY(launch_ksk_convert(d.ksk, h->ksk_bytes, h->row_stride, ksk, rows, words, d.stream));
+        else {
+            const size_t rows_per = stage_words / words;
+            for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
+                size_t cnt = rows - r0 < rows_per ? rows - r0 : rows_per;
+                CUDA_TRY(cudaMemcpyAsync(stage, ksk + r0 * words, cnt * words * sizeof(u64), cudaMemcpyHostToDevice,
+                                         d.stream));
+                CUDA_TRY(launch_ksk_convert((unsigned char*)d.ksk + r0 * h->row_stride * h->ksk_bytes, h->ksk_bytes,
+                                            h->row_stride, stage, cnt, words, d.stream));
+                CUDA_TRY(cudaStreamSynchronize(d.stream));
+            }
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    if (stage)
+        CUDA_TRY(cudaFree(stage));
+    return 0;
+}
+
+// the specialised 32-bit CGGI layout is derived on the device from the (already Montgomery-encoded) generic copy
+__global__ void bk_relayout_cggi32_kernel(u32* dst, const u32* src, u32 n, u32 d, u32 N) {
+    const size_t total = (size_t)n * N * 2 * d * 2;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;  // destination [i][k][key][l][j]
+        u32 j = r % 2; r /= 2;
+        u32 l = r % d; r /= d;
+        u32 key = r % 2; r /= 2;
+        u32 k = r % N; r /= N;
+        u32 i = (u32)r;
+        dst[idx] = src[((((size_t)key * n + i) * d + l) * 2 + j) * N + k];
+    }
+}
+
+extern "C" size_t tfhe_b200_bk_words(const tfhe_b200_params* p) {
+    return p ? bk_words_of(p) : 0;
+}
+extern "C" size_t tfhe_b200_ksk_words(const tfhe_b200_params* p) {
+    return p ? ksk_words_of(p) : 0;
+}
+extern "C" const char* tfhe_b200_last_error(void) {
+    return g_err.c_str();
+}
+extern "C" int tfhe_b200_num_gpus(const tfhe_b200_handle* h) {
+    return h ? (int)h->devs.size() : 0;
+}
+extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
+    if (!h)
+        return "";
+    return (h->have_cggi32 && !h->force_generic) ? "cggi_u32_ntt32" : h->variant.c_str();
+}
+extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value) {
+    if (!h || !key)
+        FAIL(TFHE_B200_EINVAL, "set_option: null argument");
+    std::string k(key);
+    if (k == "force_generic")
+        h->force_generic = (int)value;
+    else if (k == "group")
+        h->group = (int)value;
+    else
+        FAIL(TFHE_B200_EINVAL, "set_option: unknown key " + k);
+    return 0;
+}
+
+static int free_dev(Dev& d) {
+    cudaSetDevice(d.id);
+    if (d.stream)
+        cudaStreamSynchronize(d.stream);
+    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.twA, d.twB, d.ksk, d.ws.base};
+    for (void* p : ptrs)
+        if (p)
+            cudaFree(p);
+    for (auto& e : d.ev)
+        if (e)
+            cudaEventDestroy(e);
+    if (d.stream)
+        cudaStreamDestroy(d.stream);
+    d = Dev();
+    return 0;
+}
+
+extern "C" int tfhe_b200_clean(tfhe_b200_handle* h) {
+    if (!h)
+        return 0;  // GPUClean without GPUSetup is a no-op
+    for (auto& d : h->devs)
+        free_dev(d);
+    delete h;
+    return 0;
+}
+
+extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* bk, size_t bk_words, const uint64_t* ksk,
+                               size_t ksk_words, int key_space, int first_device, int num_gpus,
+                               tfhe_b200_handle** out) {
+    if (!params || !bk || !ksk || !out)
+        FAIL(TFHE_B200_EINVAL, "setup: null argument (the reference throws 'Need to call BTKeyGen before calling GPUSetup')");
+    const tfhe_b200_params& p = *params;
+    if (p.N < 16 || (p.N & (p.N - 1)) || p.N > 4096)
+        FAIL(TFHE_B200_ENOTSUP, "setup: ring dimension N must be a power of two in [16, 4096]");
+    if (p.method != TFHE_B200_METHOD_GINX && p.method != TFHE_B200_METHOD_AP)
+        FAIL(TFHE_B200_EINVAL, "setup: method must be AP (1) or GINX (2)");
+    if (p.Q >= (1ULL << 62) || !(p.Q & 1))
+        FAIL(TFHE_B200_ENOTSUP, "setup: Q must be an odd prime below 2^62");
+    if ((p.Q - 1) % (2ULL * p.N) != 0 || h_powmod(p.psi, p.N, p.Q) != p.Q - 1)
+        FAIL(TFHE_B200_EINVAL, "setup: psi is not a primitive 2N-th root of unity mod Q");
+    if (p.baseG == 0 || (p.baseG & (p.baseG - 1)) || p.digitsG <= p.numDigitsToThrow)
+        FAIL(TFHE_B200_EINVAL, "setup: gadget base must be a power of two and leave at least one digit");
+    if (p.baseKS < 2 || p.dKS == 0 || p.qKS == 0 || p.n == 0)
+        FAIL(TFHE_B200_EINVAL, "setup: bad key-switch parameters");
+    if (p.method == TFHE_B200_METHOD_AP && (p.baseR < 2 || p.digitsR == 0))
+        FAIL(TFHE_B200_EINVAL, "setup: bad refresh base for AP");
+    if (bk_words != bk_words_of(&p) || ksk_words != ksk_words_of(&p))
+        FAIL(TFHE_B200_EINVAL, "setup: key sizes do not match the parameter set");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        FAIL(TFHE_B200_ENODEV, std::string("setup: no CUDA device available (") + cudaGetErrorString(ce) +
+                                   "); this engine has no CPU fallback");
+    if (first_device < 0 || first_device >= ndev)
+        FAIL(TFHE_B200_EINVAL, "setup: first_device out of range");
+    if (num_gpus <= 0 || first_device + num_gpus > ndev)
+        num_gpus = ndev - first_device;
+
+    auto* h = new tfhe_b200_handle();
+    h->p = p;
+    h->is64 = p.Q >= (1ULL << 31);
+    while ((1u << h->logN) < p.N)
+        h->logN++;
+    h->d = (p.method == TFHE_B200_METHOD_GINX) ? 2 * (p.digitsG - p.numDigitsToThrow) : 2 * p.digitsG;
+    h->gBits = (u32)std::log2((double)p.baseG);
+    h->bk_words = bk_words;
+    h->ksk_words = ksk_words;
+    h->ksk_bytes = p.qKS <= (1ULL << 16) ? 2 : (p.qKS <= (1ULL << 32) ? 4 : 8);
+    {
+        u32 vw = 16 / h->ksk_bytes;
+        h->row_stride = (p.n + 1 + vw - 1) / vw * vw;
+    }
+    if (h->is64)
+        h->m64 = make_modctx<u64>(p.Q);
+    else
+        h->m32 = make_modctx<u32>(p.Q);
+    h->have_cggi32 = !h->is64 && cggi32_supported(p);
+    h->variant = h->is64 ? "generic_u64" : "generic_u32";
+    if (p.method == TFHE_B200_METHOD_AP)
+        h->variant += "_dm";
+
+    h->devs.resize(num_gpus);
+    int rc = 0;
+    for (int k = 0; k < num_gpus && rc == 0; k++) {
+        Dev& d = h->devs[k];
+        d.id = first_device + k;
+        auto init = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(d.id));
+            cudaDeviceProp prop;
+            CUDA_TRY(cudaGetDeviceProperties(&prop, d.id));
+            d.sm_count = prop.multiProcessorCount;
+            CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+            for (auto& e : d.ev)
+                CUDA_TRY(cudaEventCreate(&e));
+            int r = h->is64 ? build_tables<u64>(h, d, h->m64) : build_tables<u32>(h, d, h->m32);
+            if (r)
+                return r;
+            if (h->have_cggi32) {
+                std::vector<u32> twA, twB;
+                cggi32_build_tables(p, twA, twB);
+                CUDA_TRY(cudaMalloc((void**)&d.twA, twA.size() * 4));
+                CUDA_TRY(cudaMalloc((void**)&d.twB, twB.size() * 4));
+                CUDA_TRY(cudaMemcpy(d.twA, twA.data(), twA.size() * 4, cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(d.twB, twB.data(), twB.size() * 4, cudaMemcpyHostToDevice));
+            }
+            return 0;
+        };
+        rc = init();
+    }
+    // keys: upload + encode on device 0, then replicate peer-to-peer (the reference re-copies from the host to
+    // every GPU, bootstrapping.cu:1007-1069)
+    if (rc == 0) {
+        Dev& d0 = h->devs[0];
+        auto enc = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(d0.id));
+            int r = h->is64 ? encode_keys<u64>(h, d0, h->m64, bk, ksk, key_space)
+                            : encode_keys<u32>(h, d0, h->m32, bk, ksk, key_space);
+            if (r)
+                return r;
+            if (h->have_cggi32) {
+                CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi32, h->bk_words * 4));
+                bk_relayout_cggi32_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi32, (const u32*)d0.bk_generic, p.n,
+                                                                          h->d, p.N);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaStreamSynchronize(d0.stream));
+            }
+            const size_t tsz = h->is64 ? 8 : 4;
+            const size_t ksk_bytes_total = (size_t)p.N * p.baseKS * p.dKS * h->row_stride * h->ksk_bytes;
+            for (size_t k = 1; k < h->devs.size(); k++) {
+                Dev& d = h->devs[k];
+                CUDA_TRY(cudaSetDevice(d.id));
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, d.id, d0.id);
+                if (can) {
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(d0.id, 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                        CUDA_TRY(pe);
+                    cudaGetLastError();
+                }
+                CUDA_TRY(cudaMalloc(&d.bk_generic, h->bk_words * tsz));
+                CUDA_TRY(cudaMemcpyPeerAsync(d.bk_generic, d.id, d0.bk_generic, d0.id, h->bk_words * tsz, d.stream));
+                if (h->have_cggi32) {
+                    CUDA_TRY(cudaMalloc((void**)&d.bk_cggi32, h->bk_words * 4));
+                    CUDA_TRY(cudaMemcpyPeerAsync(d.bk_cggi32, d.id, d0.bk_cggi32, d0.id, h->bk_words * 4, d.stream));
+                }
+                CUDA_TRY(cudaMalloc(&d.ksk, ksk_bytes_total));
+                CUDA_TRY(cudaMemcpyPeerAsync(d.ksk, d.id, d0.ksk, d0.id, ksk_bytes_total, d.stream));
+            }
+            for (auto& d : h->devs) {
+                CUDA_TRY(cudaSetDevice(d.id));
+                CUDA_TRY(cudaStreamSynchronize(d.stream));
+            }
+            return 0;
+        };
+        rc = enc();
+    }
+    if (rc) {
+        std::string keep = g_err;
+        for (auto& d : h->devs)
+            free_dev(d);
+        delete h;
+        g_err = keep;
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device-level building blocks (all asynchronous on d.stream)
+// ---------------------------------------------------------------------------------------------------------
+struct AccDesc {
+    int mode = ACC_GATE;
+    u64 gate_q1 = 0;
+    const u64* table = nullptr;  // device
+    u64 fmod = 0;
+    u64* acc_io = nullptr;
+    int write_acc = 0;
+    u64 ext_add_b = 0;
+};
+
+static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u64 ct_mod, const AccDesc& a, u64* ext,
+                        int* launches) {
+    const tfhe_b200_params& p = h->p;
+    BRCommon c;
+    memset(&c, 0, sizeof(c));
+    c.N = p.N; c.logN = h->logN; c.n = p.n; c.d = h->d;
+    c.gBits = h->gBits; c.numThrow = (p.method == TFHE_B200_METHOD_GINX) ? p.numDigitsToThrow : 0;
+    c.digitsKept = h->d / 2;
+    c.method = p.method; c.baseR = p.baseR; c.digitsR = p.digitsR; c.q_lwe = p.q;
+    c.batch = batch; c.ct = ct; c.ct_mod = ct_mod;
+    c.acc_init = a.mode; c.gate_q1 = a.gate_q1; c.Q8 = p.Q / 8 + 1;
+    c.scale = a.fmod ? p.Q / a.fmod : 0;
+    c.table = a.table; c.acc_io = a.acc_io; c.write_acc = a.write_acc;
+    c.ext = ext; c.ext_add_b = a.ext_add_b;
+    if (batch <= 0)
+        return 0;
+    if (h->have_cggi32 && !h->force_generic) {
+        CGGI32Tables t;
+        t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = d.twA; t.twB = d.twB;
+        CUDA_TRY(launch_br_cggi32(c, t, d.stream, d.sm_count, h->group));
+    }
+    else if (h->is64) {
+        BRTables<u64> t;
+        t.mod = h->m64; t.tw_fwd = (const u64*)d.tw_fwd; t.tw_inv = (const u64*)d.tw_inv;
+        t.psi_pow = (const u64*)d.psi_pow; t.bk = (const u64*)d.bk_generic;
+        CUDA_TRY(launch_br_generic<u64>(c, t, d.stream, d.sm_count));
+    }
+    else {
+        BRTables<u32> t;
+        t.mod = h->m32; t.tw_fwd = (const u32*)d.tw_fwd; t.tw_inv = (const u32*)d.tw_inv;
+        t.psi_pow = (const u32*)d.psi_pow; t.bk = (const u32*)d.bk_generic;
+        CUDA_TRY(launch_br_generic<u32>(c, t, d.stream, d.sm_count));
+    }
+    if (launches)
+        (*launches)++;
+    return 0;
+}
+
+static int mkmswitch_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* ext, u64 fmod, u64* out, int* launches) {
+    const tfhe_b200_params& p = h->p;
+    KSArgs a;
+    a.N = p.N; a.n = p.n; a.baseKS = p.baseKS; a.dKS = p.dKS; a.row_stride = h->row_stride;
+    a.Q = p.Q; a.qKS = p.qKS; a.fmod = fmod; a.batch = batch; a.ext = ext; a.out = out;
+    a.ksk = d.ksk; a.ksk_bytes = h->ksk_bytes;
+    CUDA_TRY(launch_mkmswitch(a, d.stream));
+    if (launches)
+        (*launches)++;
+    return 0;
+}
+
+// One bootstrap = blind rotation + extraction + MS/KS/MS.  `ext` is scratch of batch*(N+1) words.
+static int bootstrap_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u64 ct_mod, const AccDesc& a, u64 fmod,
+                         u64* ext, u64* out, int* launches, cudaEvent_t ev_mid = nullptr) {
+    int rc = blind_rotate(h, d, batch, ct, ct_mod, a, ext, launches);
+    if (rc)
+        return rc;
+    if (ev_mid)
+        CUDA_TRY(cudaEventRecord(ev_mid, d.stream));
+    return mkmswitch_dev(h, d, batch, ext, fmod, out, launches);
+}
+
+#define AFFINE(out, x, y, sx, sy, dbl, cb, m, m2)                                                         \
+    do {                                                                                                  \
+        CUDA_TRY(launch_lwe_affine(out, x, y, sx, sy, dbl, cb, m, m2, batch, W, d.stream));               \
+        if (launches)                                                                                     \
+            (*launches)++;                                                                                \
+    } while (0)
+
+// upload a host-built table to the device arena
+static int put_table(Dev& d, const std::vector<u64>& t, u64** out) {
+    u64* p = arena_take<u64>(d, t.size());
+    if (!p)
+        FAIL(TFHE_B200_ENOMEM, "workspace too small for LUT");
+    CUDA_TRY(cudaMemcpyAsync(p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, d.stream));
+    // the host vector may die before the async copy runs when it is pageable: make it synchronous
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    *out = p;
+    return 0;
+}
+
+// binfhe-base-scheme.cpp:598-677
+static int gate_dev(tfhe_b200_handle* h, Dev& d, int gate, int batch, const u64* c1, const u64* c2, u64 q, u64* out,
+                    u64* tmp /* 4*batch*W */, u64* ext, int* launches, int* nboot) {
+    const tfhe_b200_params& p = h->p;
+    const u32 W = p.n + 1;
+    const size_t S = (size_t)batch * W;
+    static const u64 mult[6] = {5, 7, 1, 3, 5, 1};  // rgsw-cryptoparameters.h:130-137
+    if (gate == TFHE_B200_XOR || gate == TFHE_B200_XNOR) {
+        u64 *n1 = tmp, *n2 = tmp + S, *a1 = tmp + 2 * S, *a2 = tmp + 3 * S;
+        AFFINE(n1, c1, nullptr, -1, 0, 0, q >> 2, q, 0);  // EvalNOT
+        AFFINE(n2, c2, nullptr, -1, 0, 0, q >> 2, q, 0);
+        // the recursive calls need their own prepared-ct scratch: reuse `out` for it
+        int rc = gate_dev(h, d, TFHE_B200_AND, batch, c1, n2, q, a1, out, ext, launches, nboot);
+        if (rc) return rc;
+        rc = gate_dev(h, d, TFHE_B200_AND, batch, n1, c2, q, a2, out, ext, launches, nboot);
+        if (rc) return rc;
+        // OR(a1, a2): prepared ct goes to n1 (free now)
+        AFFINE(n1, a1, a2, 1, 1, 0, 0, q, 0);
+        AccDesc a;
+        a.mode = ACC_GATE; a.gate_q1 = mult[TFHE_B200_OR] * (p.q >> 3); a.ext_add_b = p.Q / 8 + 1;
+        rc = bootstrap_dev(h, d, batch, n1, q, a, q, ext, out, launches);
+        if (rc) return rc;
+        (*nboot)++;
+        if (gate == TFHE_B200_XNOR) {
+            AFFINE(n1, out, nullptr, -1, 0, 0, q >> 2, q, 0);
+            CUDA_TRY(cudaMemcpyAsync(out, n1, S * 8, cudaMemcpyDeviceToDevice, d.stream));
+        }
+        return 0;
+    }
+    u64* prep = tmp;
+    if (gate == TFHE_B200_XOR_FAST || gate == TFHE_B200_XNOR_FAST)
+        AFFINE(prep, c1, c2, 1, -1, 1, 0, q, 0);  // 2*(ct1 - ct2)
+    else
+        AFFINE(prep, c1, c2, 1, 1, 0, 0, q, 0);   // ct1 + ct2
+    AccDesc a;
+    a.mode = ACC_GATE; a.gate_q1 = mult[gate] * (p.q >> 3); a.ext_add_b = p.Q / 8 + 1;
+    int rc = bootstrap_dev(h, d, batch, prep, q, a, q, ext, out, launches, d.ev[2]);
+    (*nboot)++;
+    return rc;
+}
+
+// binfhe-base-scheme.cpp:926-987.  in/out may alias.  tmp: 2*batch*W words.
+static int floor_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* in, u64 mod, u32 roundbits, u64* out, u64* tmp,
+                     u64* ext, u64* tab /* device, >= q words */, int* launches, int* nboot) {
+    const tfhe_b200_params& p = h->p;
+    const u32 W = p.n + 1;
+    const size_t S = (size_t)batch * W;
+    const u64 beta = p.beta;
+    const u64 q = roundbits == 0 ? p.q : beta * 2 * (1ULL << roundbits);
+    u64 *cq = tmp, *r = tmp + S;
+    std::vector<u64> f(q);
+    AFFINE(out, in, nullptr, 1, 0, 0, beta, mod, 0);   // ct1 = ct + beta
+    AFFINE(cq, out, nullptr, 1, 0, 0, 0, mod, q);      // ct1Modq
+    for (u64 x = 0; x < q; x++)
+        f[x] = (x < q / 2) ? mod - q / 4 : q / 4;
+    CUDA_TRY(cudaMemcpyAsync(tab, f.data(), q * 8, cudaMemcpyHostToDevice, d.stream));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    AccDesc a;
+    a.mode = ACC_TABLE; a.table = tab; a.fmod = mod;
+    int rc = bootstrap_dev(h, d, batch, cq, q, a, mod, ext, r, launches);
+    if (rc) return rc;
+    (*nboot)++;
+    AFFINE(out, out, r, 1, -1, 0, 0, mod, 0);          // ct1 -= ct2
+    AFFINE(cq, out, nullptr, 1, 0, 0, 0, mod, q);      // ct2Modq
+    for (u64 x = 0; x < q; x++) {
+        if (x < q / 4)
+            f[x] = mod - q / 2 - x;
+        else if (x < 3 * q / 4)
+            f[x] = x;
+        else
+            f[x] = mod + q / 2 - x;
+    }
+    CUDA_TRY(cudaStreamSynchronize(d.stream));  // previous bootstrap still reads `tab`
+    CUDA_TRY(cudaMemcpyAsync(tab, f.data(), q * 8, cudaMemcpyHostToDevice, d.stream));
+    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    rc = bootstrap_dev(h, d, batch, cq, q, a, mod, ext, r, launches);
+    if (rc) return rc;
+    (*nboot)++;
+    AFFINE(out, out, r, 1, -1, 0, 0, mod, 0);          // ct1 -= ct3
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sharded execution driver
+// ---------------------------------------------------------------------------------------------------------
+struct CallCtx {
+    tfhe_b200_handle* h;
+    tfhe_b200_stats* stats;
+    int launches = 0;
+    int nboot = 0;
+};
+
+template <typename F>
+static int run_sharded(tfhe_b200_handle* h, int batch, tfhe_b200_stats* stats, F body) {
+    std::lock_guard<std::mutex> lock(h->mu);
+    const int nd = (int)h->devs.size();
+    int launches = 0, nboot = 0;
+    int rc = 0;
+    for (int k = 0; k < nd && rc == 0; k++) {
+        Dev& d = h->devs[k];
+        int start, count;
+        shard_of(batch, nd, k, &start, &count);
+        auto run = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(d.id));
+            if (k == 0)
+                CUDA_TRY(cudaEventRecord(d.ev[0], d.stream));
+            int nb = 0;
+            int r = body(d, start, count, &launches, &nb);
+            if (k == 0)
+                nboot = nb;
+            if (r)
+                return r;
+            if (k == 0)
+                CUDA_TRY(cudaEventRecord(d.ev[5], d.stream));
+            return 0;
+        };
+        rc = run();
+    }
+    for (int k = 0; k < nd; k++) {
+        Dev& d = h->devs[k];
+        cudaSetDevice(d.id);
+        cudaError_t e = cudaStreamSynchronize(d.stream);
+        if (e != cudaSuccess && rc == 0) {
+            g_err = std::string("stream sync failed: ") + cudaGetErrorString(e);
+            rc = TFHE_B200_ECUDA;
+        }
+    }
+    if (rc == 0 && stats) {
+        memset(stats, 0, sizeof(*stats));
+        Dev& d0 = h->devs[0];
+        cudaSetDevice(d0.id);
+        float t = 0;
+        if (cudaEventElapsedTime(&t, d0.ev[0], d0.ev[5]) == cudaSuccess)
+            stats->total_ms = t;
+        if (cudaEventElapsedTime(&t, d0.ev[0], d0.ev[1]) == cudaSuccess)
+            stats->h2d_ms = t;
+        if (cudaEventElapsedTime(&t, d0.ev[1], d0.ev[2]) == cudaSuccess)
+            stats->blind_rotate_ms = t;
+        if (cudaEventElapsedTime(&t, d0.ev[2], d0.ev[3]) == cudaSuccess)
+            stats->keyswitch_ms = t;
+        if (cudaEventElapsedTime(&t, d0.ev[4], d0.ev[5]) == cudaSuccess)
+            stats->d2h_ms = t;
+        cudaGetLastError();
+        stats->bootstraps = (uint32_t)nboot;
+        stats->kernel_launches = (uint32_t)launches;
+    }
+    return rc;
+}
+
+static int check_call(tfhe_b200_handle* h, int batch, const void* a, const void* b, const char* what) {
+    if (!h)
+        FAIL(TFHE_B200_EINVAL, std::string(what) + ": GPUSetup has not been called");
+    if (batch <= 0)
+        FAIL(TFHE_B200_EINVAL, std::string("ERROR: ") + what + ": input vector is empty");
+    if (!a || !b)
+        FAIL(TFHE_B200_EINVAL, std::string(what) + ": null pointer");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// operator-level entry points
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int tfhe_b200_eval_acc(tfhe_b200_handle* h, int batch, const uint64_t* a, uint64_t ct_mod, uint64_t* acc,
+                                  int space, tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, a, acc, "EvalAcc");
+    if (rc) return rc;
+    const tfhe_b200_params& p = h->p;
+    if (ct_mod == 0 || (2ULL * p.N) % ct_mod)
+        FAIL(TFHE_B200_EINVAL, "EvalAcc: ciphertext modulus must divide 2N");
+    Dev& d0 = h->devs[0];
+    return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
+        const u32 n = p.n, W = n + 1, N = p.N;
+        size_t need = (size_t)count * (W + 2 * N) * 8 + 4096;
+        int r = arena_reserve(d, need);
+        if (r) return r;
+        u64* ct = arena_take<u64>(d, (size_t)count * W);
+        u64* ac = arena_take<u64>(d, (size_t)count * 2 * N);
+        // the operator passes only the mask; b is unused because the accumulator is explicit
+        CUDA_TRY(cudaMemsetAsync(ct, 0, (size_t)count * W * 8, d.stream));
+        if (space == TFHE_B200_HOST)
+            CUDA_TRY(cudaMemcpy2DAsync(ct, W * 8, a + (size_t)start * n, n * 8, n * 8, count, cudaMemcpyHostToDevice,
+                                       d.stream));
+        else if (d.id == d0.id)
+            CUDA_TRY(cudaMemcpy2DAsync(ct, W * 8, a + (size_t)start * n, n * 8, n * 8, count,
+                                       cudaMemcpyDeviceToDevice, d.stream));
+        else {
+            u64* tmpa = arena_take<u64>(d, (size_t)count * n);
+            if (!tmpa) FAIL(TFHE_B200_ENOMEM, "workspace");
+            CUDA_TRY(cudaMemcpyPeerAsync(tmpa, d.id, a + (size_t)start * n, d0.id, (size_t)count * n * 8, d.stream));
+            CUDA_TRY(cudaMemcpy2DAsync(ct, W * 8, tmpa, n * 8, n * 8, count, cudaMemcpyDeviceToDevice, d.stream));
+        }
+        r = copy_in(d, d0, ac, acc + (size_t)start * 2 * N, (size_t)count * 2 * N * 8, space);
+        if (r) return r;
+        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        AccDesc ad;
+        ad.mode = ACC_EXPLICIT; ad.acc_io = ac; ad.write_acc = 1;
+        r = blind_rotate(h, d, count, ct, ct_mod, ad, nullptr, launches);
+        if (r) return r;
+        (*nboot) = 1;
+        if (d.id == d0.id) {
+            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        }
+        return copy_out(d, d0, acc + (size_t)start * 2 * N, ac, (size_t)count * 2 * N * 8, space);
+    });
+}
+
+extern "C" int tfhe_b200_mkmswitch(tfhe_b200_handle* h, int batch, const uint64_t* in, uint64_t fmod, uint64_t* out,
+                                   int space, tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, in, out, "MKMSwitch");
+    if (rc) return rc;
+    if (fmod == 0)
+        FAIL(TFHE_B200_EINVAL, "MKMSwitch: fmod must be non-zero");
+    const tfhe_b200_params& p = h->p;
+    Dev& d0 = h->devs[0];
+    return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
+        const u32 W = p.n + 1, N = p.N;
+        int r = arena_reserve(d, (size_t)count * (W + N + 1) * 8 + 4096);
+        if (r) return r;
+        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
+        u64* o = arena_take<u64>(d, (size_t)count * W);
+        r = copy_in(d, d0, ext, in + (size_t)start * (N + 1), (size_t)count * (N + 1) * 8, space);
+        if (r) return r;
+        if (d.id == d0.id) {
+            CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+        }
+        r = mkmswitch_dev(h, d, count, ext, fmod, o, launches);
+        if (r) return r;
+        (void)nboot;
+        if (d.id == d0.id) {
+            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        }
+        return copy_out(d, d0, out + (size_t)start * W, o, (size_t)count * W * 8, space);
+    });
+}
+
+extern "C" int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, const uint64_t* ct, const int64_t* matrix,
+                                    uint64_t modulus, uint64_t* out, int space, tfhe_b200_stats* stats) {
+    if (!h)
+        FAIL(TFHE_B200_EINVAL, "CiphertextMulMatrix: GPUSetup has not been called");
+    if (in <= 0 || !ct)
+        FAIL(TFHE_B200_EINVAL, "Input ciphertexts are empty.");
+    if (out_cols <= 0 || !matrix)
+        FAIL(TFHE_B200_EINVAL, "Input matrix is empty.");
+    if (!out || modulus == 0 || modulus >= (1ULL << 63))
+        FAIL(TFHE_B200_EINVAL, "CiphertextMulMatrix: bad output pointer or modulus");
+    const tfhe_b200_params& p = h->p;
+    // like the reference (lwe-operation.cu:91) this runs on the first GPU only: the operand is tiny
+    std::lock_guard<std::mutex> lock(h->mu);
+    Dev& d = h->devs[0];
+    const u32 W = p.n + 1;
+    auto run = [&]() -> int {
+        CUDA_TRY(cudaSetDevice(d.id));
+        int r = arena_reserve(d, ((size_t)in * W + (size_t)in * out_cols + (size_t)out_cols * W) * 8 + 4096);
+        if (r) return r;
+        u64* dct = arena_take<u64>(d, (size_t)in * W);
+        i64* dM = arena_take<i64>(d, (size_t)in * out_cols);
+        u64* dout = arena_take<u64>(d, (size_t)out_cols * W);
+        CUDA_TRY(cudaEventRecord(d.ev[0], d.stream));
+        r = copy_in(d, d, dct, ct, (size_t)in * W * 8, space);
+        if (r) return r;
+        r = copy_in(d, d, dM, matrix, (size_t)in * out_cols * 8, space);
+        if (r) return r;
+        CUDA_TRY(launch_mul_matrix(dout, dct, dM, in, out_cols, W, modulus, d.stream));
+        r = copy_out(d, d, out, dout, (size_t)out_cols * W * 8, space);
+        if (r) return r;
+        CUDA_TRY(cudaEventRecord(d.ev[5], d.stream));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        if (stats) {
+            memset(stats, 0, sizeof(*stats));
+            cudaEventElapsedTime(&stats->total_ms, d.ev[0], d.ev[5]);
+            stats->kernel_launches = 1;
+        }
+        return 0;
+    };
+    return run();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused batched API
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch, const uint64_t* ct1,
+                                       const uint64_t* ct2, uint64_t ct_mod, uint64_t* out, int space,
+                                       tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, ct1, ct2, "EvalBinGate");
+    if (rc) return rc;
+    if (!out)
+        FAIL(TFHE_B200_EINVAL, "EvalBinGate: null output");
+    if (gate < 0 || gate > TFHE_B200_XNOR)
+        FAIL(TFHE_B200_EINVAL, "EvalBinGate: unknown gate");
+    if (ct1 == ct2)
+        FAIL(TFHE_B200_EINVAL, "Input ciphertexts should be independant");
+    const tfhe_b200_params& p = h->p;
+    if (ct_mod == 0 || (2ULL * p.N) % ct_mod)
+        FAIL(TFHE_B200_EINVAL, "EvalBinGate: ciphertext modulus must divide 2N");
+    Dev& d0 = h->devs[0];
+    return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
+        const u32 W = p.n + 1, N = p.N;
+        const size_t S = (size_t)count * W;
+        int r = arena_reserve(d, (7 * S + (size_t)count * (N + 1)) * 8 + 8192);
+        if (r) return r;
+        u64* c1 = arena_take<u64>(d, S);
+        u64* c2 = arena_take<u64>(d, S);
+        u64* o = arena_take<u64>(d, S);
+        u64* tmp = arena_take<u64>(d, 4 * S);
+        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
+        r = copy_in(d, d0, c1, ct1 + (size_t)start * W, S * 8, space);
+        if (r) return r;
+        r = copy_in(d, d0, c2, ct2 + (size_t)start * W, S * 8, space);
+        if (r) return r;
+        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        r = gate_dev(h, d, gate, count, c1, c2, ct_mod, o, tmp, ext, launches, nboot);
+        if (r) return r;
+        if (d.id == d0.id) {
+            if (gate == TFHE_B200_XOR || gate == TFHE_B200_XNOR)
+                CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        }
+        return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
+    });
+}
+
+extern "C" int tfhe_b200_bootstrap_func(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod,
+                                        const uint64_t* table, int per_ct, uint64_t fmod, uint64_t* out, int space,
+                                        tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, ct, table, "BootstrapFunc");
+    if (rc) return rc;
+    const tfhe_b200_params& p = h->p;
+    if (!out || fmod == 0 || ct_mod == 0 || (2ULL * p.N) % ct_mod)
+        FAIL(TFHE_B200_EINVAL, "BootstrapFunc: bad modulus or null output");
+    Dev& d0 = h->devs[0];
+    return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
+        const u32 W = p.n + 1, N = p.N;
+        const size_t S = (size_t)count * W;
+        size_t tabw = per_ct ? (size_t)count * ct_mod : ct_mod;
+        int r = arena_reserve(d, (2 * S + (size_t)count * (N + 1) + tabw) * 8 + 8192);
+        if (r) return r;
+        u64* c = arena_take<u64>(d, S);
+        u64* o = arena_take<u64>(d, S);
+        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
+        u64* tab = arena_take<u64>(d, tabw);
+        r = copy_in(d, d0, c, ct + (size_t)start * W, S * 8, space);
+        if (r) return r;
+        r = copy_in(d, d0, tab, table + (per_ct ? (size_t)start * ct_mod : 0), tabw * 8, space);
+        if (r) return r;
+        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        AccDesc a;
+        a.mode = per_ct ? ACC_TABLE_PER : ACC_TABLE; a.table = tab; a.fmod = fmod;
+        r = bootstrap_dev(h, d, count, c, ct_mod, a, fmod, ext, o, launches, d.ev[2]);
+        if (r) return r;
+        (*nboot) = 1;
+        if (d.id == d0.id) {
+            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        }
+        return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
+    });
+}
+
+// binfhe-base-scheme.cpp:162-186
+static int check_input_function(const std::vector<u64>& lut, u64 mod) {
+    size_t len = lut.size();
+    int ret = 0;
+    if (lut[0] == mod - lut[len / 2]) {
+        for (size_t i = 1; i < len / 2; i++)
+            if (lut[i] != mod - lut[len / 2 + i]) { ret = 2; break; }
+    }
+    else if (lut[0] == lut[len / 2]) {
+        ret = 1;
+        for (size_t i = 1; i < len / 2; i++)
+            if (lut[i] != lut[len / 2 + i]) { ret = 2; break; }
+    }
+    else
+        ret = 2;
+    return ret;
+}
+
+extern "C" int tfhe_b200_eval_func(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod,
+                                   const uint64_t* lut, size_t lut_len, int per_ct, uint64_t* out, int space,
+                                   tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, ct, lut, "EvalFunc");
+    if (rc) return rc;
+    const tfhe_b200_params& p = h->p;
+    const u64 q = ct_mod;
+    if (!out || q == 0 || lut_len != q || (2ULL * p.N) % q)
+        FAIL(TFHE_B200_EINVAL, "EvalFunc: LUT length must equal the ciphertext modulus, which must divide 2N");
+    // classification uses the first LUT only, as the reference does (binfhe-base-scheme.cpp:816)
+    std::vector<u64> lut0(lut_len);
+    if (space == TFHE_B200_HOST)
+        memcpy(lut0.data(), lut, lut_len * 8);
+    else {
+        CUDA_TRY(cudaSetDevice(h->devs[0].id));
+        CUDA_TRY(cudaMemcpy(lut0.data(), lut, lut_len * 8, cudaMemcpyDeviceToHost));
+    }
+    const int prop = check_input_function(lut0, q);
+    if (prop == 2 && q > p.N)
+        FAIL(TFHE_B200_ENOTSUP,
+             "ERROR: ciphertext modulus q needs to be <= ring dimension for arbitrary function evaluation");
+    const u64 beta = p.beta;
+    Dev& d0 = h->devs[0];
+    return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
+        const int batch = count;  // for AFFINE
+        const u32 W = p.n + 1, N = p.N;
+        const size_t S = (size_t)count * W;
+        const u64 dq = q << 1;
+        const size_t ntab = per_ct ? (size_t)count : 1;
+        int r = arena_reserve(d, (4 * S + (size_t)count * (N + 1) + ntab * (q + dq) + 2 * dq) * 8 + 16384);
+        if (r) return r;
+        u64* c0 = arena_take<u64>(d, S);
+        u64* c1 = arena_take<u64>(d, S);
+        u64* c2 = arena_take<u64>(d, S);
+        u64* o = arena_take<u64>(d, S);
+        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
+        u64* dl = arena_take<u64>(d, ntab * q);    // raw LUT(s)
+        u64* dt = arena_take<u64>(d, ntab * dq);   // expanded table(s)
+        u64* df0 = arena_take<u64>(d, dq);
+        r = copy_in(d, d0, c0, ct + (size_t)start * W, S * 8, space);
+        if (r) return r;
+        r = copy_in(d, d0, dl, lut + (per_ct ? (size_t)start * q : 0), ntab * q * 8, space);
+        if (r) return r;
+        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        AccDesc a;
+        if (prop == 0) {
+            AFFINE(c1, c0, nullptr, 1, 0, 0, beta, q, 0);
+            a.mode = per_ct ? ACC_TABLE_PER : ACC_TABLE; a.table = dl; a.fmod = q;
+            r = bootstrap_dev(h, d, count, c1, q, a, q, ext, o, launches);
+            if (r) return r;
+            (*nboot) = 1;
+        }
+        else if (prop == 2) {
+            std::vector<u64> f0(dq);
+            for (u64 x = 0; x < dq; x++)
+                f0[x] = (x < dq / 2) ? dq - dq / 4 : dq / 4;
+            CUDA_TRY(cudaMemcpyAsync(df0, f0.data(), dq * 8, cudaMemcpyHostToDevice, d.stream));
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            AFFINE(c2, c0, nullptr, 1, 0, 0, beta, dq, 0);          // ct2 = ct1 + beta (mod 2q)
+            a.mode = ACC_TABLE; a.table = df0; a.fmod = dq;
+            r = bootstrap_dev(h, d, count, c2, dq, a, dq, ext, c1, launches);   // ct3
+            if (r) return r;
+            AFFINE(c1, c0, c1, 1, -1, 0, beta, dq, 0);              // ct3 = ct1 - ct3 + beta
+            AFFINE(c1, c1, nullptr, 1, 0, 0, dq - (q >> 1), dq, 0); // ct3 -= q/2
+            CUDA_TRY(launch_lut_expand(dt, dl, q, dq, 2, (int)ntab, d.stream));
+            (*launches)++;
+            a.mode = per_ct ? ACC_TABLE_PER : ACC_TABLE; a.table = dt; a.fmod = dq;
+            r = bootstrap_dev(h, d, count, c1, dq, a, dq, ext, c2, launches);   // ct4
+            if (r) return r;
+            AFFINE(o, c2, nullptr, 1, 0, 0, 0, dq, q);              // SetModulus(q)
+            (*nboot) = 2;
+        }
+        else {
+            std::vector<u64> f0(q);
+            for (u64 x = 0; x < q; x++)
+                f0[x] = (x < q / 2) ? q - q / 4 : q / 4;
+            CUDA_TRY(cudaMemcpyAsync(df0, f0.data(), q * 8, cudaMemcpyHostToDevice, d.stream));
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            AFFINE(c1, c0, nullptr, 1, 0, 0, beta, q, 0);
+            a.mode = ACC_TABLE; a.table = df0; a.fmod = q;
+            r = bootstrap_dev(h, d, count, c1, q, a, q, ext, c2, launches);     // ct2
+            if (r) return r;
+            AFFINE(c2, c0, c2, 1, -1, 0, beta, q, 0);               // ct2 = ct - ct2 + beta
+            AFFINE(c2, c2, nullptr, 1, 0, 0, q - (q >> 2), q, 0);   // ct2 -= q/4
+            CUDA_TRY(launch_lut_expand(dt, dl, q, q, 1, (int)ntab, d.stream));
+            (*launches)++;
+            a.mode = per_ct ? ACC_TABLE_PER : ACC_TABLE; a.table = dt; a.fmod = q;
+            r = bootstrap_dev(h, d, count, c2, q, a, q, ext, o, launches);
+            if (r) return r;
+            (*nboot) = 2;
+        }
+        if (d.id == d0.id) {
+            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        }
+        return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
+    });
+}
+
+extern "C" int tfhe_b200_eval_floor(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod,
+                                    uint32_t roundbits, uint64_t* out, int space, tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, ct, out, "EvalFloor");
+    if (rc) return rc;
+    const tfhe_b200_params& p = h->p;
+    const u64 qf = roundbits == 0 ? p.q : p.beta * 2 * (1ULL << roundbits);
+    if (ct_mod == 0 || (2ULL * p.N) % qf)
+        FAIL(TFHE_B200_EINVAL, "EvalFloor: bad modulus");
+    Dev& d0 = h->devs[0];
+    return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
+        const u32 W = p.n + 1, N = p.N;
+        const size_t S = (size_t)count * W;
+        int r = arena_reserve(d, (4 * S + (size_t)count * (N + 1) + qf) * 8 + 8192);
+        if (r) return r;
+        u64* c = arena_take<u64>(d, S);
+        u64* o = arena_take<u64>(d, S);
+        u64* tmp = arena_take<u64>(d, 2 * S);
+        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
+        u64* tab = arena_take<u64>(d, qf);
+        r = copy_in(d, d0, c, ct + (size_t)start * W, S * 8, space);
+        if (r) return r;
+        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        r = floor_dev(h, d, count, c, ct_mod, roundbits, o, tmp, ext, tab, launches, nboot);
+        if (r) return r;
+        if (d.id == d0.id) {
+            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        }
+        return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
+    });
+}
+
+// shared body of EvalSign (binfhe-base-scheme.cpp:989-1037) and EvalDecomp (:1039-1085)
+static int sign_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod, bool decomp, int max_digits,
+                       uint64_t* out, uint64_t* out_mods, int space, tfhe_b200_stats* stats, int* ndigits) {
+    const tfhe_b200_params& p = h->p;
+    const u64 q = p.q, beta = p.beta;
+    if (decomp && ct_mod <= q)
+        FAIL(TFHE_B200_ENOTSUP,
+             "ERROR: EvalDecomp is only for large precision. For small precision, please use bootstrapping directly");
+    // modulus chain
+    std::vector<u64> mods;
+    {
+        u64 m = ct_mod;
+        while (m > q) {
+            mods.push_back(m);
+            m = m / q * 2 * beta;
+            if (mods.size() > 64)
+                FAIL(TFHE_B200_EINVAL, "EvalSign/EvalDecomp: modulus chain does not terminate");
+        }
+        mods.push_back(m);  // final modulus (<= q)
+    }
+    const int nd = (int)mods.size();
+    if (decomp && nd > max_digits)
+        FAIL(TFHE_B200_EINVAL, "EvalDecomp: max_digits too small");
+    const u64 mfin = mods.back();
+    if (!decomp && (mfin == 0 || (2ULL * p.N) % mfin))
+        FAIL(TFHE_B200_EINVAL, "EvalSign: final modulus must divide 2N");
+    if (ndigits)
+        *ndigits = nd;
+    if (decomp && out_mods) {
+        for (int k = 0; k < nd; k++)
+            out_mods[k] = k < nd - 1 ? q : mfin;
+    }
+    Dev& d0 = h->devs[0];
+    return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
+        const int batch = count;
+        const u32 W = p.n + 1, N = p.N;
+        const size_t S = (size_t)count * W;
+        const size_t outw = decomp ? S * max_digits : S;
+        int r = arena_reserve(d, (5 * S + outw + (size_t)count * (N + 1) + 2 * q) * 8 + 16384);
+        if (r) return r;
+        u64* cur = arena_take<u64>(d, S);
+        u64* nxt = arena_take<u64>(d, S);
+        u64* tmp = arena_take<u64>(d, 2 * S);
+        u64* o = arena_take<u64>(d, outw);
+        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
+        u64* tab = arena_take<u64>(d, 2 * q);
+        r = copy_in(d, d0, cur, ct + (size_t)start * W, S * 8, space);
+        if (r) return r;
+        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        u64 mod = ct_mod;
+        int digit = 0;
+        while (mod > q) {
+            if (decomp) {
+                CUDA_TRY(launch_copy_mod(o + (size_t)digit * W, (size_t)max_digits * W, cur, W, q, count, W, d.stream));
+                (*launches)++;
+                digit++;
+            }
+            r = floor_dev(h, d, count, cur, mod, 0, nxt, tmp, ext, tab, launches, nboot);
+            if (r) return r;
+            u64 newmod = mod / q * 2 * beta;
+            CUDA_TRY(launch_mod_switch(cur, nxt, mod, newmod, S, d.stream));   // lwe-pke.cpp:204-215
+            (*launches)++;
+            mod = newmod;
+        }
+        if (decomp) {
+            CUDA_TRY(launch_copy_mod(o + (size_t)digit * W, (size_t)max_digits * W, cur, W, 0, count, W, d.stream));
+            (*launches)++;
+        }
+        else {
+            AFFINE(cur, cur, nullptr, 1, 0, 0, beta, mod, 0);
+            std::vector<u64> f3(mod);
+            for (u64 x = 0; x < mod; x++)
+                f3[x] = (x < mod / 2) ? q / 4 : q - q / 4;
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            CUDA_TRY(cudaMemcpyAsync(tab, f3.data(), mod * 8, cudaMemcpyHostToDevice, d.stream));
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            AccDesc a;
+            a.mode = ACC_TABLE; a.table = tab; a.fmod = q;
+            r = bootstrap_dev(h, d, count, cur, mod, a, q, ext, nxt, launches);
+            if (r) return r;
+            (*nboot)++;
+            AFFINE(o, nxt, nullptr, 1, 0, 0, q - (q >> 2), q, 0);
+        }
+        if (d.id == d0.id) {
+            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        }
+        const size_t ow = decomp ? (size_t)max_digits * W : W;
+        return copy_out(d, d0, out + (size_t)start * ow, o, (size_t)count * ow * 8, space);
+    });
+}
+
+extern "C" int tfhe_b200_eval_sign(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod, uint64_t* out,
+                                   int space, tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, ct, out, "EvalSign");
+    if (rc) return rc;
+    return sign_decomp(h, batch, ct, ct_mod, false, 1, out, nullptr, space, stats, nullptr);
+}
+
+extern "C" int tfhe_b200_eval_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod,
+                                     int max_digits, uint64_t* out, uint64_t* out_mods, int space,
+                                     tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, ct, out, "EvalDecomp");
+    if (rc) return rc;
+    if (max_digits <= 0 || !out_mods)
+        FAIL(TFHE_B200_EINVAL, "EvalDecomp: bad max_digits / out_mods");
+    int nd = 0;
+    rc = sign_decomp(h, batch, ct, ct_mod, true, max_digits, out, out_mods, space, stats, &nd);
+    return rc ? rc : nd;
+}

@@ -1,0 +1,104 @@
+// Internal declarations shared by the translation units of libtfhe_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tfhe_b200.h"
+#include "modarith.cuh"
+
+namespace tfhe_b200 {
+
+// ---- accumulator initialisation descriptor (binfhe-base-scheme.cpp:1087-1138 gate, :1147-1185 function) ----
+enum AccInit : int {
+    ACC_GATE = 0,      // m[j*factor] = in_range((b-j) mod q) ? -Q8 : +Q8
+    ACC_TABLE = 1,     // m[j*factor] = (Q/fmod) * table[(b-j) mod ctmod]          (shared table)
+    ACC_TABLE_PER = 2, // same, table + ct*ctmod
+    ACC_EXPLICIT = 3,  // acc given by the caller ([batch][2][N] u64, COEFFICIENT)  (EvalAcc_CUDA contract)
+};
+
+struct BRCommon {
+    // ring / gadget
+    u32 N, logN, n, d;          // d = number of digit polynomials (2 * kept digits)
+    u32 gBits, numThrow, digitsKept;
+    u32 method;                 // TFHE_B200_METHOD_*
+    u32 baseR, digitsR;
+    u64 q_lwe;                  // params q (DM uses it for the refresh digits, gates for the constants)
+    // per call
+    int batch;
+    const u64* ct;              // [batch][n+1] prepared ciphertext (a, b), modulus ct_mod
+    u64 ct_mod;
+    int acc_init;
+    u64 gate_q1;                // ACC_GATE: q1 = gateConst[gate]
+    u64 Q8;                     // Q/8 + 1
+    u64 scale;                  // ACC_TABLE*: Q / fmod
+    const u64* table;           // ACC_TABLE*: f values, ct_mod entries (per ct: [batch][ct_mod])
+    u64* acc_io;                // ACC_EXPLICIT input and/or optional output [batch][2][N] (may be null)
+    int write_acc;              // write the final accumulator (a transposed) to acc_io
+    u64* ext;                   // [batch][N+1] extracted LWE mod Q (b += Q8 for gates); may be null
+    u64 ext_add_b;              // constant added to b on extraction (Q8 for gates, 0 for functions)
+};
+
+template <typename T>
+struct BRTables {
+    ModCtx<T> mod;
+    const T* tw_fwd;   // [N] psi^bitrev(k) in Montgomery form
+    const T* tw_inv;   // [N] psi^-bitrev(k) in Montgomery form
+    const T* psi_pow;  // [2N] psi^x in Montgomery form (monomial factors)
+    const T* bk;       // generic layout, Montgomery form, pre-multiplied by N^-1
+};
+
+// generic kernels (br_generic.cu)
+template <typename T>
+cudaError_t launch_br_generic(const BRCommon& c, const BRTables<T>& t, cudaStream_t s, int sm_count);
+
+// optimised CGGI kernel for Q < 2^31, N in {512, 1024} (br_cggi32.cu)
+struct CGGI32Tables {
+    ModCtx<u32> mod;
+    const u32* bk;        // [i][k][key][l][j]  Montgomery form * N^-1
+    const u32* psi_pow;   // [2N] Montgomery form
+    const u32* twB;       // per-thread pass-B twiddles + Shoup companions, forward
+    const u32* twA;       // uniform pass-A twiddles + companions (fwd then inv)
+};
+bool cggi32_supported(const tfhe_b200_params& p);
+cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group);
+size_t cggi32_twB_words(u32 N);
+size_t cggi32_twA_words();
+void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::vector<u32>& twB);
+
+// LWE-side kernels (lwe_kernels.cu)
+struct KSArgs {
+    u32 N, n, baseKS, dKS, row_stride;  // row_stride in entries (padded to 16 B)
+    u64 Q, qKS, fmod;
+    int batch;
+    const u64* ext;    // [batch][N+1] mod Q
+    u64* out;          // [batch][n+1] mod fmod
+    const void* ksk;   // [N][baseKS][dKS][row_stride] entries of ksk_bytes each
+    int ksk_bytes;     // 2, 4 or 8
+};
+cudaError_t launch_mkmswitch(const KSArgs& a, cudaStream_t s);
+
+// out = ((sx*x + sy*y) mod m, b += cb) then optionally reduced mod m2 (SetModulus); words = n+1
+cudaError_t launch_lwe_affine(u64* out, const u64* x, const u64* y, int sx, int sy, int dbl, u64 cb, u64 m, u64 m2,
+                              int batch, u32 words, cudaStream_t s);
+// ModSwitch (lwe-pke.cpp:204-215) elementwise
+cudaError_t launch_mod_switch(u64* out, const u64* in, u64 from_mod, u64 to_mod, size_t count, cudaStream_t s);
+// strided copy / reduce helpers
+cudaError_t launch_copy_mod(u64* out, size_t out_stride, const u64* in, size_t in_stride, u64 m, int batch, u32 words,
+                            cudaStream_t s);
+cudaError_t launch_lut_expand(u64* out, const u64* lut, u64 q, u64 tab_len, int mode, int batch, cudaStream_t s);
+cudaError_t launch_mul_matrix(u64* out, const u64* ct, const i64* M, int in, int outc, u32 words, u64 modulus,
+                              cudaStream_t s);
+
+// key re-encoding kernels (lwe_kernels.cu)
+// dst[perm(idx)] = to_mont(src[idx]) * Ninv ; layouts described in capi.cu
+template <typename T>
+cudaError_t launch_bk_convert_generic(T* dst, const u64* src, size_t count, ModCtx<T> mod, T ninvM2, cudaStream_t s);
+cudaError_t launch_bk_convert_cggi32(u32* dst, const u64* src, u32 n, u32 d, u32 N, u32 i0, u32 icount, ModCtx<u32> mod,
+                                     u32 ninvM2, cudaStream_t s);
+cudaError_t launch_ksk_convert(void* dst, int bytes, u32 row_stride, const u64* src, size_t rows, u32 words,
+                               cudaStream_t s);
+
+}  // namespace tfhe_b200

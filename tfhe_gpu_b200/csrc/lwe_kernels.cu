@@ -1,0 +1,395 @@
+// LWE-side kernels: fused ModSwitch -> KeySwitch -> ModSwitch, LWE affine glue between bootstraps, exact integer
+// CiphertextMulMatrix, and the setup-time key re-encoding kernels.
+//
+// References (semantics): LWEEncryptionScheme::RoundqQ/ModSwitch/KeySwitch (lwe-pke.cpp:41-46,204-215,299-321),
+// MKMSwitchKernel (bootstrapping.cu:73-118), EvalAddEq/EvalSubEq/EvalSubEq2/EvalAdd(Sub)ConstEq
+// (lwe-pke.cpp:172-200), LWECiphertextImpl::SetModulus (lwe-ciphertext.h:120-124),
+// CiphertextMulMatrix_CUDA + applyFmod (lwe-operation.cu:42-141).
+#include "engine.cuh"
+
+namespace tfhe_b200 {
+
+// ---------------------------------------------------------------------------------------------------------
+// MS -> KS -> MS.  One CTA per ciphertext.  The key-switching table is re-encoded at setup to the narrowest
+// word that holds qKS (u16 for 2^14, u32 for the 27-bit prime, u64 for 2^35) with rows padded to 16 bytes, so
+// every thread streams the gathered rows with 128-bit loads.  Threads are arranged as RG row groups x TC column
+// vectors; partial column sums are kept in registers (sums of at most N*dKS < 2^15 values below 2^35 fit a u64
+// without reduction), combined through shared memory, and the subtraction mod qKS happens once per column.
+// ---------------------------------------------------------------------------------------------------------
+template <typename TK, int VW>  // VW = entries per 16-byte vector
+struct alignas(16) KVec {
+    TK v[VW];
+};
+
+template <typename TK, int VW, int S>
+__global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 N = A.N, n = A.n, dKS = A.dKS;
+    const u32 rows = N * dKS;
+    unsigned long long* colsum = reinterpret_cast<unsigned long long*>(smem_raw);  // [row_stride]
+    unsigned short* dig = reinterpret_cast<unsigned short*>(colsum + A.row_stride);  // [rows]
+    __shared__ u64 b_ms;
+
+    const int ct = blockIdx.x;
+    const u64* ext = A.ext + (size_t)ct * (N + 1);
+    const double dQ = (double)A.Q, dqKS = (double)A.qKS;
+
+    // ModSwitch Q -> qKS and base-baseKS digit extraction of the N mask entries
+    for (u32 i = threadIdx.x; i <= N; i += blockDim.x) {
+        u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
+        if (i == N)
+            b_ms = v;
+        else {
+            for (u32 j = 0; j < dKS; j++) {
+                dig[i * dKS + j] = (unsigned short)(v % A.baseKS);
+                v /= A.baseKS;
+            }
+        }
+    }
+    for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
+        colsum[k] = 0;
+    __syncthreads();
+
+    const int tc = threadIdx.x % TC, rg = threadIdx.x / TC;
+    const u32 CV = A.row_stride / VW;
+    const KVec<TK, VW>* tab = reinterpret_cast<const KVec<TK, VW>*>(A.ksk);
+    if (rg < RG) {
+        u64 acc[S][VW];
+#pragma unroll
+        for (int s = 0; s < S; s++)
+#pragma unroll
+            for (int v = 0; v < VW; v++)
+                acc[s][v] = 0;
+        for (u32 r = rg; r < rows; r += RG) {
+            u32 i = r / dKS, j = r - i * dKS;
+            u32 a0 = dig[r];
+            size_t row = ((size_t)i * A.baseKS + a0) * dKS + j;
+            const KVec<TK, VW>* rp = tab + row * CV;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                u32 cv = tc + s * TC;
+                if (cv < CV) {
+                    KVec<TK, VW> x = rp[cv];
+#pragma unroll
+                    for (int v = 0; v < VW; v++)
+                        acc[s][v] += (u64)x.v[v];
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            u32 cv = tc + s * TC;
+            if (cv < CV) {
+#pragma unroll
+                for (int v = 0; v < VW; v++)
+                    atomicAdd(&colsum[cv * VW + v], (unsigned long long)acc[s][v]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // a_out = 0 - sum, b_out = b - sum (mod qKS), then ModSwitch qKS -> fmod
+    u64* out = A.out + (size_t)ct * (n + 1);
+    const double dfmod = (double)A.fmod;
+    for (u32 k = threadIdx.x; k <= n; k += blockDim.x) {
+        u64 sum = colsum[k] % A.qKS;
+        u64 base = (k == n) ? b_ms : 0;
+        u64 v = base >= sum ? base - sum : base + A.qKS - sum;
+        out[k] = round_qQ(v, A.fmod, dfmod, dqKS);
+    }
+}
+
+template <typename TK, int VW>
+static cudaError_t launch_ks_t(const KSArgs& a, cudaStream_t s) {
+    const u32 CV = a.row_stride / VW;
+    int TC = CV < 256 ? (int)CV : 256;
+    int S = (int)((CV + TC - 1) / TC);
+    int RG = 256 / TC;
+    if (RG < 1)
+        RG = 1;
+    int threads = TC * RG;
+    threads = (threads + 31) / 32 * 32;
+    size_t smem = (size_t)a.row_stride * 8 + (size_t)a.N * a.dKS * 2 + 16;
+#define KS_LAUNCH(SS)                                                                                            \
+    {                                                                                                            \
+        cudaError_t e = cudaFuncSetAttribute(mkmswitch_kernel<TK, VW, SS>,                                       \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        if (e != cudaSuccess)                                                                                    \
+            return e;                                                                                            \
+        mkmswitch_kernel<TK, VW, SS><<<a.batch, threads, smem, s>>>(a, TC, RG);                                  \
+    }
+    if (S == 1)
+        KS_LAUNCH(1)
+    else if (S == 2)
+        KS_LAUNCH(2)
+    else if (S == 3)
+        KS_LAUNCH(3)
+    else if (S == 4)
+        KS_LAUNCH(4)
+    else if (S <= 8)
+        KS_LAUNCH(8)
+    else
+        return cudaErrorInvalidValue;
+#undef KS_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mkmswitch(const KSArgs& a, cudaStream_t s) {
+    if (a.batch <= 0)
+        return cudaSuccess;
+    switch (a.ksk_bytes) {
+        case 2: return launch_ks_t<unsigned short, 8>(a, s);
+        case 4: return launch_ks_t<u32, 4>(a, s);
+        case 8: return launch_ks_t<u64, 2>(a, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LWE glue
+// ---------------------------------------------------------------------------------------------------------
+__global__ void lwe_affine_kernel(u64* out, const u64* x, const u64* y, int sx, int sy, int dbl, u64 cb, u64 m, u64 m2,
+                                  size_t total, u32 words) {
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        u64 v = x[idx] % m;
+        if (sx < 0)
+            v = v ? m - v : 0;
+        if (sy != 0) {
+            u64 w = y[idx] % m;
+            if (sy < 0)
+                w = w ? m - w : 0;
+            v += w;
+            if (v >= m)
+                v -= m;
+        }
+        if (dbl) {
+            v += v;
+            if (v >= m)
+                v -= m;
+        }
+        if ((idx % words) == words - 1) {
+            v += cb % m;
+            if (v >= m)
+                v -= m;
+        }
+        if (m2)
+            v %= m2;
+        out[idx] = v;
+    }
+}
+
+cudaError_t launch_lwe_affine(u64* out, const u64* x, const u64* y, int sx, int sy, int dbl, u64 cb, u64 m, u64 m2,
+                              int batch, u32 words, cudaStream_t s) {
+    size_t total = (size_t)batch * words;
+    if (!total)
+        return cudaSuccess;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16)
+        blocks = 148 * 16;
+    lwe_affine_kernel<<<blocks, 256, 0, s>>>(out, x, y, sx, sy, dbl, cb, m, m2, total, words);
+    return cudaGetLastError();
+}
+
+__global__ void mod_switch_kernel(u64* out, const u64* in, u64 from_mod, u64 to_mod, size_t count) {
+    const double dq = (double)to_mod, dQ = (double)from_mod;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
+         idx += (size_t)gridDim.x * blockDim.x)
+        out[idx] = round_qQ(in[idx], to_mod, dq, dQ);
+}
+
+cudaError_t launch_mod_switch(u64* out, const u64* in, u64 from_mod, u64 to_mod, size_t count, cudaStream_t s) {
+    if (!count)
+        return cudaSuccess;
+    int blocks = (int)((count + 255) / 256);
+    if (blocks > 148 * 16)
+        blocks = 148 * 16;
+    mod_switch_kernel<<<blocks, 256, 0, s>>>(out, in, from_mod, to_mod, count);
+    return cudaGetLastError();
+}
+
+__global__ void copy_mod_kernel(u64* out, size_t out_stride, const u64* in, size_t in_stride, u64 m, int batch,
+                                u32 words) {
+    size_t total = (size_t)batch * words;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t b = idx / words, w = idx - b * words;
+        u64 v = in[b * in_stride + w];
+        out[b * out_stride + w] = m ? v % m : v;
+    }
+}
+
+cudaError_t launch_copy_mod(u64* out, size_t out_stride, const u64* in, size_t in_stride, u64 m, int batch, u32 words,
+                            cudaStream_t s) {
+    size_t total = (size_t)batch * words;
+    if (!total)
+        return cudaSuccess;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16)
+        blocks = 148 * 16;
+    copy_mod_kernel<<<blocks, 256, 0, s>>>(out, out_stride, in, in_stride, m, batch, words);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CiphertextMulMatrix: out[i][w] = sum_k ct[k][w] * M[k][i] mod modulus, exact.
+// Tiled 32x32 through shared memory; products are reduced with 128-bit arithmetic so any modulus < 2^63 and any
+// int64 matrix entry is handled exactly (the reference's FP64 GEMM is exact only while sums stay below 2^53).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 mulmod_u64(u64 a, u64 b, u64 m) {
+    // a, b < m < 2^63: schoolbook via 128-bit product and division-free reduction using __umul64hi is overkill
+    // here; this kernel is bandwidth/latency trivial compared with the bootstraps, so use the simple form.
+    unsigned __int128 p = (unsigned __int128)a * b;
+    return (u64)(p % m);
+}
+
+__global__ void mul_matrix_kernel(u64* out, const u64* ct, const i64* M, int in, int outc, u32 words, u64 modulus) {
+    __shared__ u64 sC[32][33];  // ct tile   [k][w]
+    __shared__ u64 sM[32][33];  // matrix tile [k][i]
+    const int w = blockIdx.x * 32 + threadIdx.x;  // ciphertext word (column of ct)
+    const int i0 = blockIdx.y * 32;
+    u64 acc[4] = {0, 0, 0, 0};  // threadIdx.y in 0..7 handles i = i0 + threadIdx.y + 8*r
+    for (int k0 = 0; k0 < in; k0 += 32) {
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            int k = k0 + r;
+            sC[r][threadIdx.x] = (k < in && w < (int)words) ? ct[(size_t)k * words + w] % modulus : 0;
+            int i = i0 + threadIdx.x;
+            u64 mv = 0;
+            if (k < in && i < outc) {
+                i64 x = M[(size_t)k * outc + i] % (i64)modulus;
+                mv = (u64)(x < 0 ? x + (i64)modulus : x);
+            }
+            sM[r][threadIdx.x] = mv;
+        }
+        __syncthreads();
+        for (int r = 0; r < 4; r++) {
+            int il = threadIdx.y + 8 * r;
+            u64 a = acc[r];
+            for (int k = 0; k < 32; k++) {
+                u64 p = mulmod_u64(sC[k][threadIdx.x], sM[k][il], modulus);
+                a += p;
+                if (a >= modulus)
+                    a -= modulus;
+            }
+            acc[r] = a;
+        }
+        __syncthreads();
+    }
+    for (int r = 0; r < 4; r++) {
+        int i = i0 + threadIdx.y + 8 * r;
+        if (i < outc && w < (int)words)
+            out[(size_t)i * words + w] = acc[r];
+    }
+}
+
+cudaError_t launch_mul_matrix(u64* out, const u64* ct, const i64* M, int in, int outc, u32 words, u64 modulus,
+                              cudaStream_t s) {
+    dim3 grid((words + 31) / 32, (outc + 31) / 32), block(32, 8);
+    mul_matrix_kernel<<<grid, block, 0, s>>>(out, ct, M, in, outc, words, modulus);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Setup-time key re-encoding (replaces the CPU loops of GPUSetup_core / KeyCopy_FFT, bootstrapping.cu:933-975)
+// ---------------------------------------------------------------------------------------------------------
+// generic layout: same element order as the reference; value -> Montgomery form times N^-1
+template <typename T>
+__global__ void bk_convert_generic_kernel(T* dst, const u64* src, size_t count, ModCtx<T> mod, T ninvM2) {
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
+         idx += (size_t)gridDim.x * blockDim.x)
+        dst[idx] = mod.mont_mul((T)src[idx], ninvM2);
+}
+
+template <typename T>
+cudaError_t launch_bk_convert_generic(T* dst, const u64* src, size_t count, ModCtx<T> mod, T ninvM2, cudaStream_t s) {
+    if (!count)
+        return cudaSuccess;
+    bk_convert_generic_kernel<T><<<148 * 8, 256, 0, s>>>(dst, src, count, mod, ninvM2);
+    return cudaGetLastError();
+}
+template cudaError_t launch_bk_convert_generic<u32>(u32*, const u64*, size_t, ModCtx<u32>, u32, cudaStream_t);
+template cudaError_t launch_bk_convert_generic<u64>(u64*, const u64*, size_t, ModCtx<u64>, u64, cudaStream_t);
+
+// CGGI 32-bit layout: dst[i][k][key][l][j] (32-byte aligned groups per evaluation slot k) from the reference order
+// src[key][i][l][j][k]; src points at the slice for i in [i0, i0+icount) laid out as [key][icount][l][j][N].
+__global__ void bk_convert_cggi32_kernel(u32* dst, const u64* src, u32 d, u32 N, u32 icount, ModCtx<u32> mod,
+                                         u32 ninvM2) {
+    const size_t per_i = (size_t)2 * d * 2 * N;
+    const size_t total = per_i * icount;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        // idx enumerates the destination: [i][k][key][l][j]
+        size_t r = idx;
+        u32 j = r % 2; r /= 2;
+        u32 l = r % d; r /= d;
+        u32 key = r % 2; r /= 2;
+        u32 k = r % N; r /= N;
+        u32 i = (u32)r;
+        size_t sidx = ((((size_t)key * icount + i) * d + l) * 2 + j) * N + k;
+        dst[idx] = mod.mont_mul((u32)src[sidx], ninvM2);
+    }
+}
+
+cudaError_t launch_bk_convert_cggi32(u32* dst, const u64* src, u32 n, u32 d, u32 N, u32 i0, u32 icount, ModCtx<u32> mod,
+                                     u32 ninvM2, cudaStream_t s) {
+    (void)n;
+    (void)i0;
+    bk_convert_cggi32_kernel<<<148 * 8, 256, 0, s>>>(dst, src, d, N, icount, mod, ninvM2);
+    return cudaGetLastError();
+}
+
+// per-ciphertext LUT expansion for EvalFunc(vector, LUT_vec) (binfhe-base-scheme.cpp:791-924)
+//   mode 1 (periodic):  t[x] = x < q/2 ? L[x] : q - L[x - q/2]                       (tab_len = q)
+//   mode 2 (arbitrary): t[x] = x < dq/2 ? L[x mod q] : dq - L[(x - dq/2) mod q]        (tab_len = dq = 2q)
+__global__ void lut_expand_kernel(u64* out, const u64* lut, u64 q, u64 tab_len, int mode, size_t total) {
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t b = idx / tab_len;
+        u64 x = idx - b * tab_len;
+        const u64* L = lut + b * q;
+        u64 v;
+        if (mode == 1)
+            v = (x < q / 2) ? L[x] : q - L[x - q / 2];
+        else
+            v = (x < tab_len / 2) ? L[x % q] : tab_len - L[(x - tab_len / 2) % q];
+        out[idx] = v;
+    }
+}
+
+cudaError_t launch_lut_expand(u64* out, const u64* lut, u64 q, u64 tab_len, int mode, int batch, cudaStream_t s) {
+    size_t total = (size_t)batch * tab_len;
+    if (!total)
+        return cudaSuccess;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16)
+        blocks = 148 * 16;
+    lut_expand_kernel<<<blocks, 256, 0, s>>>(out, lut, q, tab_len, mode, total);
+    return cudaGetLastError();
+}
+
+// KSK: u64 rows of `words` entries -> narrow rows of row_stride entries (zero padded)
+template <typename TK>
+__global__ void ksk_convert_kernel(TK* dst, u32 row_stride, const u64* src, size_t rows, u32 words) {
+    size_t total = rows * row_stride;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx / row_stride;
+        u32 w = (u32)(idx - r * row_stride);
+        dst[idx] = w < words ? (TK)src[r * words + w] : (TK)0;
+    }
+}
+
+cudaError_t launch_ksk_convert(void* dst, int bytes, u32 row_stride, const u64* src, size_t rows, u32 words,
+                               cudaStream_t s) {
+    if (!rows)
+        return cudaSuccess;
+    if (bytes == 2)
+        ksk_convert_kernel<unsigned short><<<148 * 8, 256, 0, s>>>((unsigned short*)dst, row_stride, src, rows, words);
+    else if (bytes == 4)
+        ksk_convert_kernel<u32><<<148 * 8, 256, 0, s>>>((u32*)dst, row_stride, src, rows, words);
+    else
+        ksk_convert_kernel<u64><<<148 * 8, 256, 0, s>>>((u64*)dst, row_stride, src, rows, words);
+    return cudaGetLastError();
+}
+
+}  // namespace tfhe_b200
