@@ -1,9 +1,512 @@
-// placeholder: specialised kernel not built yet
+// Specialised CGGI/GINX blind rotation for 32-bit moduli (Q < 2^32/22, i.e. the 27-bit primes of TOY / STD128 /
+// logQ=11), N in {512, 1024}.  This is the kernel the headline metric (STD128 CGGI NAND gates/s) runs on.
+//
+// Design (B200-first, nothing like the reference's one-CTA-per-ciphertext FP64 FFT kernel):
+//   * a CTA owns a GROUP of G ciphertexts and walks the n rotation steps in lock-step, so the RGSW key of step i
+//     (128 KB for STD128) is read from L2 once per CTA and reused from registers by all G ciphertexts;
+//   * the accumulator never leaves the register file: each (ciphertext, component) polynomial is held in
+//     coefficient form by N/32 threads, 32 coefficients per thread ("A layout": thread T owns T + (N/32) r);
+//   * every NTT is a register-resident radix-32 x radix-(N/32) two-pass transform done by N/32 threads (one warp
+//     for N=1024): pass A (strides >= N/32) uses 31 twiddles that are the same for every thread and are read as
+//     constant-bank operands straight from the kernel parameters; one shared-memory transpose; pass B (strides
+//     < 32) uses 31 per-thread twiddles that stay in registers for the whole kernel.  Butterflies are lazy
+//     (Harvey) with Shoup multiplication: 1 IMAD.HI + 2 IMAD + 2 IADD3, no conditional corrections in the forward
+//     transform (values stay < 22 Q < 2^32);
+//   * the inverse transform re-uses the forward per-thread twiddles through the identity
+//     psi^-bitrev(m+i) = -psi^bitrev(m + (m-1-i)): thread T processes the mirrored block N/32-1-T;
+//   * signed digit decomposition is computed in closed form per digit ((d + offset) >> g*l) & (B-1)) - B/2, which
+//     is bit-identical to the reference's sequential carry loop (rgsw-acc.cpp:86-108);
+//   * the pointwise stage accumulates the d products per output in 64 bits (IMAD.WIDE) and performs ONE Montgomery
+//     reduction per output, then applies the monomial factors (psi-power table in shared memory);
+//   * N^-1 and the Montgomery factor are folded into the key; accumulator init, the LWE-mask modulus switch,
+//     sample extraction and the a(X^-1) transpose are fused in.
+#include <cstring>
+
 #include "engine.cuh"
+
 namespace tfhe_b200 {
-bool cggi32_supported(const tfhe_b200_params&) { return false; }
-cudaError_t launch_br_cggi32(const BRCommon&, const CGGI32Tables&, cudaStream_t, int, int) { return cudaErrorNotSupported; }
-size_t cggi32_twB_words(u32) { return 0; }
-size_t cggi32_twA_words() { return 0; }
-void cggi32_build_tables(const tfhe_b200_params&, std::vector<u32>&, std::vector<u32>&) {}
+
+struct CGGI32Args {
+    BRCommon c;
+    ModCtx<u32> mod;
+    const u32* bk;       // [i][k][key][l'][jout]
+    const u32* psi_pow;  // [2N] Montgomery form
+    const u32* twB;      // [TPN][NTW][2] per-thread pass-B twiddles (value, Shoup companion)
+    u32 twA_f[32][2];    // uniform pass-A twiddles, forward: index (16>>s) + (r>>(s+1))
+    u32 twA_i[32][2];    // inverse
+    u32 Q2;              // 2Q
+    u32 dig_off;         // closed-form decomposition offset  sum_i (B/2) B^i
+    u32 dig_add;         // Q - B/2 (digits are fed to the lazy NTT as r + Q)
+};
+
+__device__ __forceinline__ u32 shoup_mul(u32 y, u32 w, u32 wp, u32 Q) {
+    // y*w mod Q up to one extra Q: result in [0, 2Q) for any 32-bit y
+    u32 q = __umulhi(y, wp);
+    return y * w - q * Q;
 }
+__device__ __forceinline__ u32 cond_sub(u32 x, u32 m) {
+    // x < 2m  ->  x mod m
+    return min(x, x - m);
+}
+__device__ __forceinline__ u32 pos_of(u32 idx) {
+    return idx + ((idx >> 5) << 2);
+}
+
+template <int LOGN, int DK, int G>
+struct KCfg {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int TPN = N / 32;            // threads per NTT
+    static constexpr int PB = LOGN - 5;           // pass-B stages
+    static constexpr int NTW = 32 - (32 >> PB);   // per-thread twiddles
+    static constexpr int D = 2 * DK;              // digit polynomials
+    static constexpr int RS = N + N / 8 + (LOGN == 9 ? 16 : 0);  // padded region stride (words)
+    static constexpr int NT = G * 2 * TPN;        // threads per CTA
+    static constexpr size_t smem_bytes(int n) {
+        return (size_t)G * D * RS * 4 + (size_t)2 * N * 4 + (size_t)G * ((n + 1) / 2 * 2) * 2 + 64;
+    }
+};
+
+// ---- register-resident NTT passes -----------------------------------------------------------------------------
+// forward pass A: Cooley-Tukey stages with stride TPN*2^s, s = 4..0 (uniform twiddles from the parameter bank)
+template <typename A>
+__device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
+#pragma unroll
+    for (int s = 4; s >= 0; s--) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = (16 >> s) + (r >> (s + 1));
+            u32 t = shoup_mul(v[r + (1 << s)], args.twA_f[ti][0], args.twA_f[ti][1], Q);
+            u32 x = v[r];
+            v[r] = x + t;
+            v[r + (1 << s)] = x - t + Q2;
+        }
+    }
+}
+// forward pass B: strides 2^s, s = PB-1..0, per-thread twiddles
+template <int PB>
+__device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2) {
+#pragma unroll
+    for (int s = PB - 1; s >= 0; s--) {
+        const int off = (32 >> (s + 1)) - (32 >> PB);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = off + (r >> (s + 1));
+            u32 t = shoup_mul(v[r + (1 << s)], tw[ti], twp[ti], Q);
+            u32 x = v[r];
+            v[r] = x + t;
+            v[r + (1 << s)] = x - t + Q2;
+        }
+    }
+}
+// inverse pass B' on the MIRRORED block (virtual thread TPN-1-T): Gentleman-Sande stages 2^s, s = 0..PB-1, with
+// (U - V) * psi^-x == (V - U) * psi^{mirror}; all values kept below 2Q
+template <int PB>
+__device__ __forceinline__ void inv_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2) {
+#pragma unroll
+    for (int s = 0; s < PB; s++) {
+        const int off = (32 >> (s + 1)) - (32 >> PB);
+        const int cnt = 32 >> (s + 1);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = off + (cnt - 1 - (r >> (s + 1)));
+            u32 U = v[r], V = v[r + (1 << s)];
+            v[r] = cond_sub(U + V, Q2);
+            v[r + (1 << s)] = shoup_mul(V - U + Q2, tw[ti], twp[ti], Q);
+        }
+    }
+}
+// inverse pass A': strides TPN*2^s, s = 0..4, uniform inverse twiddles
+template <typename A>
+__device__ __forceinline__ void inv_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = (16 >> s) + (r >> (s + 1));
+            u32 U = v[r], V = v[r + (1 << s)];
+            v[r] = cond_sub(U + V, Q2);
+            v[r + (1 << s)] = shoup_mul(U - V + Q2, args.twA_i[ti][0], args.twA_i[ti][1], Q);
+        }
+    }
+}
+
+template <int LOGN, int DK, int G>
+__global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
+    using K = KCfg<LOGN, DK, G>;
+    constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS, NT = K::NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32* Dsm = reinterpret_cast<u32*>(smem_raw);                      // [G][D][RS]
+    u32* psiM = Dsm + (size_t)G * D * RS;                             // [2N]
+    unsigned short* es = reinterpret_cast<unsigned short*>(psiM + 2 * N);  // [G][n] rotation exponents
+
+    const BRCommon& C = A.c;
+    const u32 Q = A.mod.Q, Q2 = A.Q2, qinv = A.mod.qinv, oneM = A.mod.oneM;
+    const u32 n = C.n;
+    const int tid = threadIdx.x;
+    const int g = tid / (2 * TPN);         // ciphertext slot within the CTA
+    const int j = (tid / TPN) & 1;         // accumulator component (0 = a, 1 = b)
+    const int T = tid % TPN;               // thread index within the NTT
+    const int ct = blockIdx.x * G + g;
+    const bool live = ct < C.batch;
+    const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
+
+    // ---- one-time loads: psi-power table, rotation exponents, per-thread twiddles --------------------------
+    for (int x = tid; x < 2 * N; x += NT)
+        psiM[x] = A.psi_pow[x];
+    {
+        // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
+        const u32 mod = (u32)C.ct_mod, fac = (2 * N) / mod;
+        const int lt = tid % (2 * TPN);
+        for (u32 i = lt; i < n; i += 2 * TPN) {
+            u32 ai = (u32)(lwe[i] % mod);
+            u32 e = ((mod - ai) % mod) * fac;
+            es[g * n + i] = live ? (unsigned short)e : 0;
+        }
+    }
+    u32 tw[32], twp[32];
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(A.twB) + (size_t)T * NTW;
+#pragma unroll
+        for (int x = 0; x < NTW; x++) {
+            uint2 w = src[x];
+            tw[x] = w.x;
+            twp[x] = w.y;
+        }
+    }
+
+    // ---- accumulator initialisation in A layout (coefficient idx = T + TPN*r) --------------------------------
+    u32 c[32];
+    if (C.acc_init == ACC_EXPLICIT) {
+        const u64* src = C.acc_io + ((size_t)(live ? ct : 0) * 2 + j) * N;
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            c[r] = live ? (u32)src[T + TPN * r] : 0;
+    }
+    else {
+        const u64 q = C.ct_mod, b = lwe[n] % q;
+        const u32 factor = (u32)((2 * N) / q);
+        const u64 q1 = C.gate_q1;
+        u64 q2 = q1 + (q >> 1);
+        if (q2 >= q)
+            q2 -= q;
+        const u64* tab = C.table + (C.acc_init == ACC_TABLE_PER ? (size_t)(live ? ct : 0) * q : 0);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const u32 idx = T + TPN * r;
+            u32 val = 0;
+            if (j == 1 && live && (idx % factor) == 0) {
+                u64 jj = idx / factor;
+                u64 temp = b >= jj ? b - jj : b + q - jj;
+                if (C.acc_init == ACC_GATE) {
+                    bool in;
+                    if (q1 < q2)
+                        in = (temp >= q1) && (temp < q2);
+                    else
+                        in = !((temp >= q2) && (temp < q1));
+                    val = in ? (u32)(Q - C.Q8) : (u32)C.Q8;
+                }
+                else
+                    val = (u32)(C.scale * tab[temp]);
+            }
+            c[r] = val;
+        }
+    }
+    __syncthreads();
+
+    u32* myD = Dsm + (size_t)g * D * RS;
+    const u32 QHalf = Q >> 1;
+    const u32 gBits = C.gBits, gmask = (1u << gBits) - 1;
+
+    // =========================================================================================================
+    for (u32 i = 0; i < n; i++) {
+        // ---- phase 1: decompose + forward NTT of the DK digit polynomials of component j ---------------------
+#pragma unroll 1
+        for (int l = 0; l < DK; l++) {
+            u32 v[32];
+            const u32 sh = gBits * (l + C.numThrow);
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                // centred representative, closed-form signed digit, fed to the lazy NTT as digit + Q
+                int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
+                u32 Dv = (u32)(dv + (int)A.dig_off);
+                v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
+            }
+            fwd_passA(v, A, Q, Q2);
+            u32* reg = myD + (size_t)(j + 2 * l) * RS;
+            // transpose A layout -> B layout through the (padded) region
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                reg[pos_of(T + TPN * r)] = v[r];
+            __syncwarp();
+            {
+                const uint4* p4 = reinterpret_cast<const uint4*>(reg + 36 * T);
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
+                    uint4 w = p4[x];
+                    v[4 * x] = w.x; v[4 * x + 1] = w.y; v[4 * x + 2] = w.z; v[4 * x + 3] = w.w;
+                }
+            }
+            __syncwarp();
+            fwd_passB<PB>(v, tw, twp, Q, Q2);
+            {
+                uint4* p4 = reinterpret_cast<uint4*>(reg + 36 * T);
+#pragma unroll
+                for (int x = 0; x < 8; x++)
+                    p4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: pointwise MAC against the RGSW keys of step i, monomial factors, delta -> regions 0,1 ---
+        {
+            const u32* bki = A.bk + (size_t)i * N * (4 * D);
+#pragma unroll 1
+            for (int k = tid; k < N; k += NT) {
+                u32 bkv[4 * D];
+                {
+                    const uint4* p4 = reinterpret_cast<const uint4*>(bki + (size_t)k * (4 * D));
+#pragma unroll
+                    for (int x = 0; x < D; x++) {
+                        uint4 w = __ldg(p4 + x);
+                        bkv[4 * x] = w.x; bkv[4 * x + 1] = w.y; bkv[4 * x + 2] = w.z; bkv[4 * x + 3] = w.w;
+                    }
+                }
+                const u32 pk = pos_of(k);
+                const u32 br = __brev((u32)k) >> (32 - LOGN);
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
+                    const u32* dreg = Dsm + (size_t)gg * D * RS + pk;
+                    u64 s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll
+                    for (int l = 0; l < D; l++) {
+                        u32 x = dreg[(size_t)l * RS];
+                        s00 += (u64)x * bkv[(0 * D + l) * 2 + 0];
+                        s01 += (u64)x * bkv[(0 * D + l) * 2 + 1];
+                        s10 += (u64)x * bkv[(1 * D + l) * 2 + 0];
+                        s11 += (u64)x * bkv[(1 * D + l) * 2 + 1];
+                    }
+                    // lazy Montgomery reductions (inputs < 2^63): results < 2^31 + Q, congruent mod Q
+                    auto redc_lazy = [&](u64 x) -> u32 {
+                        u32 lo = (u32)x, hi = (u32)(x >> 32);
+                        u32 m = lo * qinv;
+                        u32 t = __umulhi(m, Q);
+                        return hi - t + Q;
+                    };
+                    u32 r00 = redc_lazy(s00), r01 = redc_lazy(s01), r10 = redc_lazy(s10), r11 = redc_lazy(s11);
+                    const u32 e = es[gg * n + i];
+                    const u32 xx = ((2 * br + 1) * e) & (2 * N - 1);
+                    u32 m1 = psiM[xx], m2 = psiM[(2 * N - xx) & (2 * N - 1)];
+                    m1 = m1 >= oneM ? m1 - oneM : m1 + Q - oneM;
+                    m2 = m2 >= oneM ? m2 - oneM : m2 + Q - oneM;
+                    u64 t0 = (u64)r00 * m1 + (u64)r10 * m2;
+                    u64 t1 = (u64)r01 * m1 + (u64)r11 * m2;
+                    u32* wreg = Dsm + (size_t)gg * D * RS + pk;
+                    wreg[0] = A.mod.redc(t0);
+                    wreg[RS] = A.mod.redc(t1);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: inverse NTT of delta_j (mirrored block), accumulate into c ------------------------------
+        {
+            u32 v[32];
+            u32* reg = myD + (size_t)j * RS;
+            const int Tv = TPN - 1 - T;
+            {
+                const uint4* p4 = reinterpret_cast<const uint4*>(reg + 36 * Tv);
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
+                    uint4 w = p4[x];
+                    v[4 * x] = w.x; v[4 * x + 1] = w.y; v[4 * x + 2] = w.z; v[4 * x + 3] = w.w;
+                }
+            }
+            inv_passB<PB>(v, tw, twp, Q, Q2);
+            __syncwarp();
+            {
+                uint4* p4 = reinterpret_cast<uint4*>(reg + 36 * Tv);
+#pragma unroll
+                for (int x = 0; x < 8; x++)
+                    p4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                v[r] = reg[pos_of(T + TPN * r)];
+            __syncwarp();
+            inv_passA(v, A, Q, Q2);
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                c[r] = cond_sub(cond_sub(c[r] + v[r], Q2), Q);   // c < Q, v < 2Q
+        }
+        // no CTA barrier needed here: phase 1 of the next step writes regions that phase 2 finished reading
+        // (barrier above) and region j, which only this thread group read in phase 3 (__syncwarp above).
+    }
+
+    // ---- extraction: a'(X) = a(X^-1), b = acc_b[0] (+ Q8 for gates) ---------------------------------------------
+    if (live) {
+        if (C.write_acc) {
+            u64* dst = C.acc_io + (size_t)ct * 2 * N;
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const u32 idx = T + TPN * r;
+                if (j == 0) {
+                    u32 val = c[r];
+                    dst[idx == 0 ? 0 : N - idx] = (idx == 0 || val == 0) ? val : Q - val;
+                }
+                else
+                    dst[N + idx] = c[r];
+            }
+        }
+        if (C.ext) {
+            u64* dst = C.ext + (size_t)ct * (N + 1);
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const u32 idx = T + TPN * r;
+                if (j == 0) {
+                    u32 val = c[r];
+                    dst[idx == 0 ? 0 : N - idx] = (idx == 0 || val == 0) ? val : Q - val;
+                }
+                else if (idx == 0) {
+                    u64 val = (u64)c[r] + C.ext_add_b;
+                    dst[N] = val >= Q ? val - Q : val;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+bool cggi32_supported(const tfhe_b200_params& p) {
+    if (p.method != TFHE_B200_METHOD_GINX)
+        return false;
+    if (p.N != 512 && p.N != 1024)
+        return false;
+    if (p.Q >= (1ULL << 32) / 22)  // lazy forward NTT bound: values < 22 Q must fit 32 bits
+        return false;
+    const u32 dk = p.digitsG - p.numDigitsToThrow;
+    if (dk != 2 && dk != 3 && dk != 4 && dk != 6)
+        return false;
+    if (p.n > 4096)
+        return false;
+    return true;
+}
+
+static u32 bitrev_h(u32 x, u32 bits) {
+    u32 r = 0;
+    for (u32 i = 0; i < bits; i++) {
+        r = (r << 1) | (x & 1);
+        x >>= 1;
+    }
+    return r;
+}
+static u32 shoup_h(u64 w, u64 Q) {
+    return (u32)((w << 32) / Q);
+}
+
+size_t cggi32_twA_words() {
+    return 2 * 32 * 2;
+}
+size_t cggi32_twB_words(u32 N) {
+    const u32 logN = N == 512 ? 9 : 10;
+    const u32 PB = logN - 5, NTW = 32 - (32 >> PB);
+    return (size_t)(N / 32) * NTW * 2;
+}
+
+// twA: [fwd|inv][32][2] ; twB: [TPN][NTW][2]   (plain residues + Shoup companions, NOT Montgomery form)
+void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::vector<u32>& twB) {
+    const u64 Q = p.Q, N = p.N;
+    const u32 logN = N == 512 ? 9 : 10;
+    const u32 TPN = N / 32, PB = logN - 5, NTW = 32 - (32 >> PB);
+    std::vector<u64> W(N), WI(N);
+    u64 psi = p.psi % Q, psii = h_powmod(psi, Q - 2, Q), x = 1, xi = 1;
+    for (u64 k = 0; k < N; k++) {
+        u32 r = bitrev_h((u32)k, logN);
+        W[r] = x;
+        WI[r] = xi;
+        x = h_mulmod(x, psi, Q);
+        xi = h_mulmod(xi, psii, Q);
+    }
+    twA.assign(2 * 32 * 2, 0);
+    for (u32 k = 1; k < 32; k++) {
+        twA[(0 * 32 + k) * 2 + 0] = (u32)W[k];
+        twA[(0 * 32 + k) * 2 + 1] = shoup_h(W[k], Q);
+        twA[(1 * 32 + k) * 2 + 0] = (u32)WI[k];
+        twA[(1 * 32 + k) * 2 + 1] = shoup_h(WI[k], Q);
+    }
+    twB.assign((size_t)TPN * NTW * 2, 0);
+    for (u32 T = 0; T < TPN; T++)
+        for (int s = (int)PB - 1; s >= 0; s--) {
+            const u32 cnt = 32 >> (s + 1), off = cnt - (32 >> PB);
+            for (u32 xx = 0; xx < cnt; xx++) {
+                u64 w = W[(N >> (s + 1)) + T * cnt + xx];
+                twB[((size_t)T * NTW + off + xx) * 2 + 0] = (u32)w;
+                twB[((size_t)T * NTW + off + xx) * 2 + 1] = shoup_h(w, Q);
+            }
+        }
+}
+
+template <int LOGN, int DK, int G>
+static cudaError_t launch_t(const CGGI32Args& a, cudaStream_t s) {
+    using K = KCfg<LOGN, DK, G>;
+    const size_t smem = K::smem_bytes((int)a.c.n);
+    if (smem > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    const int grid = (a.c.batch + G - 1) / G;
+    br_cggi32_kernel<LOGN, DK, G><<<grid, K::NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group) {
+    (void)sm_count;
+    CGGI32Args a;
+    a.c = c;
+    a.mod = t.mod;
+    a.bk = t.bk;
+    a.psi_pow = t.psi_pow;
+    a.twB = t.twB;
+    memcpy(a.twA_f, t.twA, sizeof(a.twA_f));
+    memcpy(a.twA_i, t.twA + 64, sizeof(a.twA_i));
+    a.Q2 = 2 * t.mod.Q;
+    const u32 B = 1u << c.gBits, total_digits = c.digitsKept + c.numThrow;
+    u64 off = 0, pw = 1;
+    for (u32 i = 0; i < total_digits; i++) {
+        off += (B / 2) * pw;
+        pw *= B;
+    }
+    a.dig_off = (u32)off;
+    a.dig_add = t.mod.Q - B / 2;
+    const int dk = (int)c.digitsKept;
+#define CASE(LOGN, DK, GG) \
+    if (c.logN == LOGN && dk == DK && group == GG) return launch_t<LOGN, DK, GG>(a, s);
+    if (c.logN == 10) {
+        if (group == 0) group = (dk <= 4) ? 4 : 2;
+        CASE(10, 4, 4) CASE(10, 4, 2) CASE(10, 4, 1)
+        CASE(10, 3, 4) CASE(10, 3, 2)
+        CASE(10, 2, 4)
+        CASE(10, 6, 2)
+    }
+    else if (c.logN == 9) {
+        if (group == 0) group = (dk <= 4) ? 8 : 4;
+        CASE(9, 3, 8) CASE(9, 3, 4)
+        CASE(9, 2, 8)
+        CASE(9, 4, 8)
+        CASE(9, 6, 4)
+    }
+#undef CASE
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace tfhe_b200

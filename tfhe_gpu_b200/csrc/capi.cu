@@ -74,6 +74,7 @@ struct tfhe_b200_handle {
     u32 row_stride = 0;
     size_t bk_words = 0, ksk_words = 0;
     std::vector<Dev> devs;
+    std::vector<u32> twA_host;
     std::string variant;
     std::mutex mu;
 };
@@ -385,11 +386,9 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
             if (r)
                 return r;
             if (h->have_cggi32) {
-                std::vector<u32> twA, twB;
-                cggi32_build_tables(p, twA, twB);
-                CUDA_TRY(cudaMalloc((void**)&d.twA, twA.size() * 4));
+                std::vector<u32> twB;
+                cggi32_build_tables(p, h->twA_host, twB);
                 CUDA_TRY(cudaMalloc((void**)&d.twB, twB.size() * 4));
-                CUDA_TRY(cudaMemcpy(d.twA, twA.data(), twA.size() * 4, cudaMemcpyHostToDevice));
                 CUDA_TRY(cudaMemcpy(d.twB, twB.data(), twB.size() * 4, cudaMemcpyHostToDevice));
             }
             return 0;
@@ -486,7 +485,7 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
         return 0;
     if (h->have_cggi32 && !h->force_generic) {
         CGGI32Tables t;
-        t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = d.twA; t.twB = d.twB;
+        t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB;
         CUDA_TRY(launch_br_cggi32(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->is64) {
