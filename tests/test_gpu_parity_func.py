@@ -126,3 +126,21 @@ def test_ciphertext_mul_matrix(keyset, rng):
     got2 = ks.gpu().CiphertextMulMatrix(ct, M2, qKS)
     ref2 = (ct.astype(object).T @ M2.astype(object)) % int(qKS)
     assert np.array_equal(got2.astype(object), ref2.T)
+
+
+def test_mkmswitch_double_rounding_near_ties(keyset):
+    """The first mod-switch (Q ~ 2^54 -> qKS = 2^35) must reproduce the reference's DOUBLE rounding on near-ties,
+    where it differs from exact integer rounding (lwe-pke.cpp:41-46)."""
+    ks = keyset("toy_func12")
+    p = ks.p
+    inv = pow(1 << 36, -1, p.Q)
+    vals = [(d * inv) % p.Q for d in range(-600, 600) if d]
+    ext = np.array(vals[: (len(vals) // (p.N + 1)) * (p.N + 1)] or vals, dtype=np.uint64)
+    reps = -(-(p.N + 1) // len(vals))
+    ext = np.tile(np.array(vals, dtype=np.uint64), reps + 1)[: 2 * (p.N + 1)].reshape(2, p.N + 1)
+    want = ks.port.mkmswitch(ks.ksk, ext, p.q)
+    got = ks.gpu().MKMSwitch(ext, p.q)
+    assert np.array_equal(got, want)
+    exact = [((2 * int(v) * p.qKS + p.Q) // (2 * p.Q)) % p.qKS for v in ext[0]]
+    dbl = [ks.port.round_qQ(int(v), p.qKS, p.Q) for v in ext[0]]
+    assert exact != dbl      # the vectors really exercise the discrepancy

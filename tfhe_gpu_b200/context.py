@@ -220,7 +220,7 @@ class BinFHEContextB200:
         return buf.shape[0]
 
     # ---- batched operations ---------------------------------------------------------------------------
-    def EvalBinGate(self, gate, ct1, ct2, ct_mod=None):
+    def EvalBinGate(self, gate, ct1, ct2, ct_mod=None, out=None):
         g = GATES[gate] if isinstance(gate, str) else int(gate)
         a, b = _Buf(ct1), _Buf(ct2)
         if a.shape[0] == 0 or b.shape[0] == 0:
@@ -229,8 +229,11 @@ class BinFHEContextB200:
             raise TfheB200Error(-1, "ERROR: EvalBinGate: input ciphertexts size unmatched")
         if a.space != b.space:
             raise TfheB200Error(-1, "EvalBinGate: inputs must live in the same memory space")
-        out = a.empty_like_out(a.shape)
+        if out is None:
+            out = a.empty_like_out(a.shape)
         o = _Buf(out)
+        if o.obj is not out and not _is_torch(out):
+            raise TfheB200Error(-1, "EvalBinGate: `out` must be a contiguous uint64 array")
         self._call("tfhe_b200_eval_bin_gate", self._handle(), g, a.shape[0], a.ptr, b.ptr,
                    C.c_uint64(ct_mod or self.params.q), o.ptr, a.space, self._st())
         return out

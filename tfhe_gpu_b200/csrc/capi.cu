@@ -15,6 +15,9 @@
 
 using namespace tfhe_b200;
 
+static_assert(sizeof(tfhe_b200_params) == 88, "tfhe_b200_params layout is part of the ABI");
+static_assert(sizeof(tfhe_b200_stats) == 32, "tfhe_b200_stats layout is part of the ABI");
+
 static thread_local std::string g_err;
 
 #define CUDA_TRY(x)                                                                                        \

@@ -1,145 +1,162 @@
-// Integer-pipe microbenchmark: measures the peak issue rate of the 32-bit integer multiply-add family on this GPU.
-// The blind-rotation roofline ("fraction of the IMAD peak") uses the number measured here,
-// because MEASURED_PEAKS.json only carries HBM and bf16 figures.
-//
-//   imad_peak [out.json]
-//
-// Variants: IMAD (mad.lo.u32), IMAD.HI.U32 (mul.hi.u32), IMAD.WIDE.U32 (mad.wide.u32), IADD3 (alu pipe), a 1:1
-// IMAD+IADD mix (dual issue across the fma and alu pipes) and the exact instruction mix of one lazy Shoup
-// butterfly (1 IMAD.HI + 2 IMAD + 2 IADD3).
+// Integer-pipe microbenchmark: operand-form dependence of IMAD / IMAD.HI / IMAD.WIDE throughput and the
+// co-issue behaviour with the ALU pipe.  Clocks are warmed for ~1 s first.  Prints JSON.
 #include <cuda_runtime.h>
-
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-
-#define CHECK(x)                                                                          \
-    do {                                                                                  \
-        cudaError_t e = (x);                                                              \
-        if (e != cudaSuccess) {                                                           \
-            fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e));     \
-            exit(1);                                                                      \
-        }                                                                                 \
-    } while (0)
-
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "%s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(e)); exit(1);} } while (0)
 constexpr int ILP = 8;
 
-template <int VARIANT>
-__global__ void __launch_bounds__(256) k(unsigned* out, int iters, unsigned a, unsigned b, long long* cyc) {
-    unsigned x[ILP];
+template <int V>
+__global__ void __launch_bounds__(256) k(unsigned* out, const unsigned* in, int iters, unsigned ua, unsigned ub, long long* cyc) {
+    unsigned x[ILP], y[ILP], z[ILP];
     unsigned long long w[ILP];
+    double dx[ILP];
 #pragma unroll
     for (int i = 0; i < ILP; i++) {
-        x[i] = threadIdx.x * 7 + i + a;
+        x[i] = in[threadIdx.x + 256 * i];
+        y[i] = in[threadIdx.x + 256 * (i + 8)] | 1;
+        z[i] = in[threadIdx.x + 256 * (i + 16)];
         w[i] = x[i];
+        dx[i] = (double)x[i];
     }
+    const double dy = (double)y[0] * 1e-9, dz = (double)z[0];
     long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int i = 0; i < ILP; i++) {
-            if (VARIANT == 0)
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
-            else if (VARIANT == 1)
-                asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
-            else if (VARIANT == 2)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((unsigned)w[i]), "r"(a));
-            else if (VARIANT == 3)
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
-            else if (VARIANT == 4) {
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
-                asm volatile("add.u32 %0, %0, %1;" : "+r"(x[(i + 4) % ILP]) : "r"(b));
-            }
-            else if (VARIANT == 5) {
-                // lazy Shoup butterfly on (x[i], x[i^1]) -- executed for even i only
+            if (V == 0)       asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));          // R,R,R (distinct)
+            else if (V == 1)  asm volatile("mul.lo.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));                           // R,R,RZ
+            else if (V == 2)  asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(ua), "r"(z[i]));             // R,UR,R
+            else if (V == 3)  asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(ub));             // R,R,UR
+            else if (V == 4)  asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(ua), "r"(ub));               // R,UR,UR
+            else if (V == 5)  asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));                           // HI R,R
+            else if (V == 6)  asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(ua));                             // HI R,UR
+            else if (V == 7)  asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"((unsigned)w[i]), "r"(y[i])); // WIDE acc
+            else if (V == 8)  asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"((unsigned)w[i]), "r"(y[i]));    // WIDE no acc
+            else if (V == 9)  asm volatile("add.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(y[i]));                              // IADD3 R,R
+            else if (V == 10) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));        // LOP3
+            else if (V == 11) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dx[i]) : "d"(dy), "d"(dz));               // DFMA
+            else if (V == 12) { // shoup butterfly, register twiddles (pass B form)
                 if ((i & 1) == 0) {
                     unsigned q, t;
-                    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(q) : "r"(x[i + 1]), "r"(b));
-                    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(x[i + 1]), "r"(a));
-                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(q), "r"(0x7ffe001u));
+                    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(q) : "r"(x[i + 1]), "r"(z[i]));
+                    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(x[i + 1]), "r"(y[i]));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(q), "r"(ua));
                     unsigned u = x[i];
                     asm volatile("add.u32 %0, %1, %2;" : "=r"(x[i]) : "r"(u), "r"(t));
-                    asm volatile("sub.u32 %0, %1, %2;" : "=r"(x[i + 1]) : "r"(u), "r"(t));
+                    asm volatile("{ .reg .u32 tt; sub.u32 tt, %1, %2; add.u32 %0, tt, %3; }" : "=r"(x[i + 1]) : "r"(u), "r"(t), "r"(ub));
                 }
+            }
+            else if (V == 13) { // shoup butterfly, uniform twiddles (pass A form)
+                if ((i & 1) == 0) {
+                    unsigned q, t;
+                    asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(q) : "r"(x[i + 1]), "r"(ub));
+                    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(x[i + 1]), "r"(ua));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(q), "r"(ua));
+                    unsigned u = x[i];
+                    asm volatile("add.u32 %0, %1, %2;" : "=r"(x[i]) : "r"(u), "r"(t));
+                    asm volatile("{ .reg .u32 tt; sub.u32 tt, %1, %2; add.u32 %0, tt, %3; }" : "=r"(x[i + 1]) : "r"(u), "r"(t), "r"(ub));
+                }
+            }
+            else if (V == 15) { // shoup butterfly with the quotient taken from a full-rate IMAD.WIDE (no addend)
+                if ((i & 1) == 0) {
+                    unsigned long long qq; unsigned q, t;
+                    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(qq) : "r"(x[i + 1]), "r"(z[i]));
+                    q = (unsigned)(qq >> 32);
+                    asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(x[i + 1]), "r"(y[i]));
+                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(q), "r"(ua));
+                    unsigned u = x[i];
+                    asm volatile("add.u32 %0, %1, %2;" : "=r"(x[i]) : "r"(u), "r"(t));
+                    asm volatile("{ .reg .u32 tt; sub.u32 tt, %1, %2; add.u32 %0, tt, %3; }" : "=r"(x[i + 1]) : "r"(u), "r"(t), "r"(ub));
+                }
+            }
+            else if (V == 16) { // MAC: full-rate IMAD.WIDE (no addend) + 64-bit add on the ALU pipe
+                unsigned long long pp;
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(pp) : "r"(x[i]), "r"(y[i]));
+                asm volatile("add.u64 %0, %0, %1;" : "+l"(w[i]) : "l"(pp));
+                x[i] += (unsigned)w[i];
+            }
+            else if (V == 17) { // MAC: IMAD.WIDE with 64-bit addend
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(y[i]));
+                x[i] += (unsigned)w[i];
+            }
+            else if (V == 14) { // 1 IMAD (R,R,R) + 1 IADD (R,R) interleaved
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(z[(i + 3) % ILP]) : "r"(y[i]));
             }
         }
     }
     long long t1 = clock64();
     unsigned s = 0;
 #pragma unroll
-    for (int i = 0; i < ILP; i++)
-        s += x[i] + (unsigned)w[i] + (unsigned)(w[i] >> 32);
+    for (int i = 0; i < ILP; i++) s += x[i] + y[i] + z[i] + (unsigned)w[i] + (unsigned)(w[i] >> 32) + (unsigned)dx[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0)
-        cyc[blockIdx.x] = t1 - t0;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-struct Res {
-    const char* name;
-    double gops, per_sm_clk, ms;
-    double ops_per_iter;
-};
+struct Res { const char* name; double gops, per_sm_clk, ms; };
+static unsigned *g_out, *g_in; static long long* g_cyc; static int g_sms;
 
 template <int V>
-Res run(const char* name, double ops_per_unrolled_iter, int sms, int ctas_per_sm) {
-    int grid = sms * ctas_per_sm, block = 256, iters = 20000;
-    unsigned* out;
-    long long* cyc;
-    CHECK(cudaMalloc(&out, (size_t)grid * block * 4));
-    CHECK(cudaMalloc(&cyc, grid * 8));
-    cudaEvent_t e0, e1;
-    CHECK(cudaEventCreate(&e0));
-    CHECK(cudaEventCreate(&e1));
-    for (int w = 0; w < 3; w++)
-        k<V><<<grid, block>>>(out, iters, 3, 5, cyc);
+Res run(const char* name, double ops, int ctas_per_sm) {
+    int grid = g_sms * ctas_per_sm, block = 256, iters = 20000;
+    cudaEvent_t e0, e1; CHECK(cudaEventCreate(&e0)); CHECK(cudaEventCreate(&e1));
+    k<V><<<grid, block>>>(g_out, g_in, iters, 3, 0x7ffe001u, g_cyc);
     CHECK(cudaDeviceSynchronize());
     float best = 1e30f;
-    for (int r = 0; r < 5; r++) {
+    for (int r = 0; r < 3; r++) {
         CHECK(cudaEventRecord(e0));
-        k<V><<<grid, block>>>(out, iters, 3, 5, cyc);
-        CHECK(cudaEventRecord(e1));
-        CHECK(cudaEventSynchronize(e1));
-        float ms;
-        CHECK(cudaEventElapsedTime(&ms, e0, e1));
-        if (ms < best)
-            best = ms;
+        k<V><<<grid, block>>>(g_out, g_in, iters, 3, 0x7ffe001u, g_cyc);
+        CHECK(cudaEventRecord(e1)); CHECK(cudaEventSynchronize(e1));
+        float ms; CHECK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
     }
     std::vector<long long> hc(grid);
-    CHECK(cudaMemcpy(hc.data(), cyc, grid * 8, cudaMemcpyDeviceToHost));
-    double avg_cyc = 0;
-    for (auto c : hc)
-        avg_cyc += (double)c;
-    avg_cyc /= grid;
-    double total_ops = (double)grid * block * iters * ops_per_unrolled_iter;
-    Res r;
-    r.name = name;
-    r.ms = best;
-    r.gops = total_ops / (best * 1e-3) / 1e9;
-    // ops issued by one SM (ctas_per_sm resident CTAs run concurrently) per SM clock
-    r.per_sm_clk = (double)ctas_per_sm * block * iters * ops_per_unrolled_iter / avg_cyc;
-    r.ops_per_iter = ops_per_unrolled_iter;
-    CHECK(cudaFree(out));
-    CHECK(cudaFree(cyc));
+    CHECK(cudaMemcpy(hc.data(), g_cyc, grid * 8, cudaMemcpyDeviceToHost));
+    double avg = 0; for (auto c : hc) avg += (double)c; avg /= grid;
+    Res r; r.name = name; r.ms = best;
+    r.gops = (double)grid * block * iters * ops / (best * 1e-3) / 1e9;
+    r.per_sm_clk = (double)ctas_per_sm * block * iters * ops / avg;
     return r;
 }
 
 int main(int argc, char** argv) {
-    cudaDeviceProp p;
-    CHECK(cudaGetDeviceProperties(&p, 0));
-    int sms = p.multiProcessorCount;
+    cudaDeviceProp p; CHECK(cudaGetDeviceProperties(&p, 0)); g_sms = p.multiProcessorCount;
+    int maxgrid = g_sms * 8;
+    CHECK(cudaMalloc(&g_out, (size_t)maxgrid * 256 * 4)); CHECK(cudaMalloc(&g_cyc, maxgrid * 8));
+    std::vector<unsigned> hin(256 * 24); for (size_t i = 0; i < hin.size(); i++) hin[i] = (unsigned)(i * 2654435761u + 12345u);
+    CHECK(cudaMalloc(&g_in, hin.size() * 4)); CHECK(cudaMemcpy(g_in, hin.data(), hin.size() * 4, cudaMemcpyHostToDevice));
+    // warm the clocks for ~1 s
+    for (int i = 0; i < 150; i++) k<0><<<maxgrid, 256>>>(g_out, g_in, 20000, 3, 5, g_cyc);
+    CHECK(cudaDeviceSynchronize());
     std::vector<Res> rs;
-    rs.push_back(run<0>("imad_lo", ILP, sms, 8));
-    rs.push_back(run<1>("imad_hi_u32", ILP, sms, 8));
-    rs.push_back(run<2>("imad_wide_u32", ILP, sms, 8));
-    rs.push_back(run<3>("iadd3", ILP, sms, 8));
-    rs.push_back(run<4>("imad_lo+iadd_1to1", 2 * ILP, sms, 8));
-    rs.push_back(run<5>("shoup_butterfly_5instr", 5 * (ILP / 2), sms, 8));
+    for (int occ : {8, 2}) {
+        rs.push_back(run<0>(occ == 8 ? "imad_rrr" : "imad_rrr_occ2", ILP, occ));
+        rs.push_back(run<5>(occ == 8 ? "imadhi_rr" : "imadhi_rr_occ2", ILP, occ));
+        rs.push_back(run<12>(occ == 8 ? "butterfly_regtw" : "butterfly_regtw_occ2", 5 * (ILP / 2), occ));
+        rs.push_back(run<13>(occ == 8 ? "butterfly_unitw" : "butterfly_unitw_occ2", 5 * (ILP / 2), occ));
+    }
+    rs.push_back(run<1>("imul_rr", ILP, 8));
+    rs.push_back(run<2>("imad_r_ur_r", ILP, 8));
+    rs.push_back(run<3>("imad_r_r_ur", ILP, 8));
+    rs.push_back(run<4>("imad_r_ur_ur", ILP, 8));
+    rs.push_back(run<6>("imadhi_r_ur", ILP, 8));
+    rs.push_back(run<7>("imadwide_acc", ILP, 8));
+    rs.push_back(run<8>("imulwide", ILP, 8));
+    rs.push_back(run<9>("iadd_rr", ILP, 8));
+    rs.push_back(run<10>("lop3_rrr", ILP, 8));
+    rs.push_back(run<11>("dfma", ILP, 8));
+    rs.push_back(run<14>("imad_rrr+iadd", 2 * ILP, 8));
+    rs.push_back(run<15>("butterfly_widehi", 5 * (ILP / 2), 8));
+    rs.push_back(run<15>("butterfly_widehi_occ2", 5 * (ILP / 2), 2));
+    rs.push_back(run<16>("mac_mulwide_add64", ILP, 8));
+    rs.push_back(run<17>("mac_madwide", ILP, 8));
+    rs.push_back(run<16>("mac_mulwide_add64_occ2", ILP, 2));
+    rs.push_back(run<17>("mac_madwide_occ2", ILP, 2));
     FILE* f = argc > 1 ? fopen(argv[1], "w") : stdout;
-    fprintf(f, "{\"gpu\": \"%s\", \"sms\": %d, \"clock_khz_max\": %d, \"variants\": {", p.name, sms, p.clockRate);
+    fprintf(f, "{\"gpu\": \"%s\", \"sms\": %d, \"variants\": {", p.name, g_sms);
     for (size_t i = 0; i < rs.size(); i++)
-        fprintf(f, "%s\"%s\": {\"gops\": %.1f, \"per_sm_per_clk\": %.2f, \"ms\": %.3f}", i ? ", " : "", rs[i].name,
-                rs[i].gops, rs[i].per_sm_clk, rs[i].ms);
-    fprintf(f, "}}\n");
-    if (f != stdout)
-        fclose(f);
+        fprintf(f, "%s\"%s\": {\"gops\": %.1f, \"per_sm_per_clk\": %.2f, \"ghz\": %.3f}", i ? ", " : "", rs[i].name, rs[i].gops, rs[i].per_sm_clk, rs[i].gops / (rs[i].per_sm_clk * g_sms));
+    fprintf(f, "}}\n"); if (f != stdout) fclose(f);
     return 0;
 }
