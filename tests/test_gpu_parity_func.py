@@ -134,10 +134,8 @@ def test_mkmswitch_double_rounding_near_ties(keyset):
     ks = keyset("toy_func12")
     p = ks.p
     inv = pow(1 << 36, -1, p.Q)
-    vals = [(d * inv) % p.Q for d in range(-600, 600) if d]
-    ext = np.array(vals[: (len(vals) // (p.N + 1)) * (p.N + 1)] or vals, dtype=np.uint64)
-    reps = -(-(p.N + 1) // len(vals))
-    ext = np.tile(np.array(vals, dtype=np.uint64), reps + 1)[: 2 * (p.N + 1)].reshape(2, p.N + 1)
+    vals = np.array([(d * inv) % p.Q for d in range(-600, 600) if d], dtype=np.uint64)
+    ext = np.resize(vals, (2, p.N + 1))
     want = ks.port.mkmswitch(ks.ksk, ext, p.q)
     got = ks.gpu().MKMSwitch(ext, p.q)
     assert np.array_equal(got, want)

@@ -29,7 +29,7 @@ namespace tfhe_b200 {
 struct CGGI32Args {
     BRCommon c;
     ModCtx<u32> mod;
-    const u32* bk;       // [i][k][key][l'][jout]
+    const u32* bk;       // [i][x][k][4]: word w = (key*D + l')*2 + jout of slot k lives in plane x = w/4, lane w%4
     const u32* psi_pow;  // [2N] Montgomery form
     const u32* twB;      // [TPN][NTW][2] per-thread pass-B twiddles (value, Shoup companion)
     u32 twA_f[32][2];    // uniform pass-A twiddles, forward: index (16>>s) + (r>>(s+1))
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
 
     // ---- one-time loads: psi-power table, rotation exponents, per-thread twiddles --------------------------
     for (int x = tid; x < 2 * N; x += NT)
-        psiM[x] = A.psi_pow[x];
+        psiM[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))] = A.psi_pow[x];
     {
         // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
         const u32 mod = (u32)C.ct_mod, fac = (2 * N) / mod;
@@ -221,6 +221,15 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
     }
     __syncthreads();
 
+    u32 bk_pre[4 * D];   // key slice of (step, slot tid), requested one step ahead
+    {
+        const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + tid;
+#pragma unroll
+        for (int x = 0; x < D; x++) {
+            uint4 w = __ldg(p4 + (size_t)x * N);
+            bk_pre[4 * x] = w.x; bk_pre[4 * x + 1] = w.y; bk_pre[4 * x + 2] = w.z; bk_pre[4 * x + 3] = w.w;
+        }
+    }
     u32* myD = Dsm + (size_t)g * D * RS;
     const u32 QHalf = Q >> 1;
     const u32 gBits = C.gBits, gmask = (1u << gBits) - 1;
@@ -266,17 +275,25 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
         __syncthreads();
 
         // ---- phase 2: pointwise MAC against the RGSW keys of step i, monomial factors, delta -> regions 0,1 ---
+        // The key slice of evaluation slot k is 4*D words, stored as D "planes" of uint4 ([i][x][k][4]) so a warp
+        // reads 512 contiguous bytes per load.  Loads are double-buffered in registers; the first slot of the NEXT
+        // step is requested before the inverse transform so its latency hides behind phases 3 and 1.
         {
-            const u32* bki = A.bk + (size_t)i * N * (4 * D);
-#pragma unroll 1
-            for (int k = tid; k < N; k += NT) {
-                u32 bkv[4 * D];
-                {
-                    const uint4* p4 = reinterpret_cast<const uint4*>(bki + (size_t)k * (4 * D));
+            constexpr int ITERS = (N + NT - 1) / NT;
+            u32 bkv[4 * D];
+#pragma unroll
+            for (int x = 0; x < 4 * D; x++)
+                bkv[x] = bk_pre[x];
+#pragma unroll
+            for (int it = 0; it < ITERS; it++) {
+                const int k = tid + it * NT;
+                u32 bkn[4 * D];
+                if (it + 1 < ITERS) {
+                    const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (size_t)i * D * N + (k + NT);
 #pragma unroll
                     for (int x = 0; x < D; x++) {
-                        uint4 w = __ldg(p4 + x);
-                        bkv[4 * x] = w.x; bkv[4 * x + 1] = w.y; bkv[4 * x + 2] = w.z; bkv[4 * x + 3] = w.w;
+                        uint4 w = __ldg(p4 + (size_t)x * N);
+                        bkn[4 * x] = w.x; bkn[4 * x + 1] = w.y; bkn[4 * x + 2] = w.z; bkn[4 * x + 3] = w.w;
                     }
                 }
                 const u32 pk = pos_of(k);
@@ -303,7 +320,11 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                     u32 r00 = redc_lazy(s00), r01 = redc_lazy(s01), r10 = redc_lazy(s10), r11 = redc_lazy(s11);
                     const u32 e = es[gg * n + i];
                     const u32 xx = ((2 * br + 1) * e) & (2 * N - 1);
-                    u32 m1 = psiM[xx], m2 = psiM[(2 * N - xx) & (2 * N - 1)];
+                    const u32 x2 = (2 * N - xx) & (2 * N - 1);
+                    // psi-power table is stored bit-rotated (low LOGN-3 bits <-> high 4 bits) so that the 16 distinct
+                    // exponents a warp touches (they differ by multiples of 2N/16) fall into distinct banks
+                    u32 m1 = psiM[((xx & (2 * N / 16 - 1)) << 4) | (xx >> (LOGN + 1 - 4))];
+                    u32 m2 = psiM[((x2 & (2 * N / 16 - 1)) << 4) | (x2 >> (LOGN + 1 - 4))];
                     m1 = m1 >= oneM ? m1 - oneM : m1 + Q - oneM;
                     m2 = m2 >= oneM ? m2 - oneM : m2 + Q - oneM;
                     u64 t0 = (u64)r00 * m1 + (u64)r10 * m2;
@@ -311,6 +332,20 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                     u32* wreg = Dsm + (size_t)gg * D * RS + pk;
                     wreg[0] = A.mod.redc(t0);
                     wreg[RS] = A.mod.redc(t1);
+                }
+                if (it + 1 < ITERS) {
+#pragma unroll
+                    for (int x = 0; x < 4 * D; x++)
+                        bkv[x] = bkn[x];
+                }
+            }
+            // request the first slot of the next step now
+            if (i + 1 < n) {
+                const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (size_t)(i + 1) * D * N + tid;
+#pragma unroll
+                for (int x = 0; x < D; x++) {
+                    uint4 w = __ldg(p4 + (size_t)x * N);
+                    bk_pre[4 * x] = w.x; bk_pre[4 * x + 1] = w.y; bk_pre[4 * x + 2] = w.z; bk_pre[4 * x + 3] = w.w;
                 }
             }
         }

@@ -247,15 +247,17 @@ static int encode_keys(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M, const u6
 
 // the specialised 32-bit CGGI layout is derived on the device from the (already Montgomery-encoded) generic copy
 __global__ void bk_relayout_cggi32_kernel(u32* dst, const u32* src, u32 n, u32 d, u32 N) {
+    // destination [i][x][k][c]: word w = 4x + c = (key*d + l)*2 + j of evaluation slot k  (see br_cggi32.cu)
     const size_t total = (size_t)n * N * 2 * d * 2;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
-        size_t r = idx;  // destination [i][k][key][l][j]
-        u32 j = r % 2; r /= 2;
-        u32 l = r % d; r /= d;
-        u32 key = r % 2; r /= 2;
+        size_t r = idx;
+        u32 c = r % 4; r /= 4;
         u32 k = r % N; r /= N;
+        u32 x = r % d; r /= d;     // 4d words per slot = d planes
         u32 i = (u32)r;
+        u32 w = 4 * x + c;
+        u32 j = w % 2, l = (w / 2) % d, key = w / (2 * d);
         dst[idx] = src[((((size_t)key * n + i) * d + l) * 2 + j) * N + k];
     }
 }
