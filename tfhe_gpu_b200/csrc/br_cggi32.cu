@@ -37,11 +37,24 @@ struct CGGI32Args {
     u32 Q2;              // 2Q
     u32 dig_off;         // closed-form decomposition offset  sum_i (B/2) B^i
     u32 dig_add;         // Q - B/2 (digits are fed to the lazy NTT as r + Q)
+    u32 ninvM;           // N^-1 in Montgomery form (SKIP: the evaluation-domain accumulator is kept scaled by N^-1)
+    u32 zero;            // always 0: third IADD3 operand that keeps ptxas from turning adds into IMAD.IADD (fma-heavy pipe)
 };
 
+__device__ __forceinline__ u32 mulhi_w(u32 a, u32 b) {
+    // high half through IMAD.WIDE (full rate) instead of IMAD.HI (half rate)
+    u32 hi, lo;
+    asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%1, %0}, p; }" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
+    (void)lo;
+    return hi;
+}
 __device__ __forceinline__ u32 shoup_mul(u32 y, u32 w, u32 wp, u32 Q) {
-    // y*w mod Q up to one extra Q: result in [0, 2Q) for any 32-bit y
-    u32 q = __umulhi(y, wp);
+    // y*w mod Q up to one extra Q: result in [0, 2Q) for any 32-bit y.
+    // The quotient estimate is the high half of a full-rate IMAD.WIDE (no addend): measured 129 /clk/SM on B200 vs
+    // 62 /clk/SM for IMAD.HI (profiles/r01_imad_peak.json), so the butterfly costs 3 fma-heavy slots instead of 4.
+    u32 q, lo;
+    asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%1, %0}, p; }" : "=r"(q), "=r"(lo) : "r"(y), "r"(wp));
+    (void)lo;
     return y * w - q * Q;
 }
 __device__ __forceinline__ u32 cond_sub(u32 x, u32 m) {
@@ -70,6 +83,7 @@ struct KCfg {
 // forward pass A: Cooley-Tukey stages with stride TPN*2^s, s = 4..0 (uniform twiddles from the parameter bank)
 template <typename A>
 __device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
+    const u32 Z = args.zero;
 #pragma unroll
     for (int s = 4; s >= 0; s--) {
 #pragma unroll
@@ -79,14 +93,15 @@ __device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u3
             const int ti = (16 >> s) + (r >> (s + 1));
             u32 t = shoup_mul(v[r + (1 << s)], args.twA_f[ti][0], args.twA_f[ti][1], Q);
             u32 x = v[r];
-            v[r] = x + t;
+            v[r] = x + t + Z;
             v[r + (1 << s)] = x - t + Q2;
         }
     }
 }
 // forward pass B: strides 2^s, s = PB-1..0, per-thread twiddles
 template <int PB>
-__device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2) {
+__device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2,
+                                          u32 Z) {
 #pragma unroll
     for (int s = PB - 1; s >= 0; s--) {
         const int off = (32 >> (s + 1)) - (32 >> PB);
@@ -97,7 +112,7 @@ __device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], con
             const int ti = off + (r >> (s + 1));
             u32 t = shoup_mul(v[r + (1 << s)], tw[ti], twp[ti], Q);
             u32 x = v[r];
-            v[r] = x + t;
+            v[r] = x + t + Z;
             v[r + (1 << s)] = x - t + Q2;
         }
     }
@@ -105,7 +120,8 @@ __device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], con
 // inverse pass B' on the MIRRORED block (virtual thread TPN-1-T): Gentleman-Sande stages 2^s, s = 0..PB-1, with
 // (U - V) * psi^-x == (V - U) * psi^{mirror}; all values kept below 2Q
 template <int PB>
-__device__ __forceinline__ void inv_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2) {
+__device__ __forceinline__ void inv_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2,
+                                          u32 Z) {
 #pragma unroll
     for (int s = 0; s < PB; s++) {
         const int off = (32 >> (s + 1)) - (32 >> PB);
@@ -116,7 +132,7 @@ __device__ __forceinline__ void inv_passB(u32 (&v)[32], const u32 (&tw)[32], con
                 continue;
             const int ti = off + (cnt - 1 - (r >> (s + 1)));
             u32 U = v[r], V = v[r + (1 << s)];
-            v[r] = cond_sub(U + V, Q2);
+            v[r] = cond_sub(U + V + Z, Q2);
             v[r + (1 << s)] = shoup_mul(V - U + Q2, tw[ti], twp[ti], Q);
         }
     }
@@ -124,6 +140,7 @@ __device__ __forceinline__ void inv_passB(u32 (&v)[32], const u32 (&tw)[32], con
 // inverse pass A': strides TPN*2^s, s = 0..4, uniform inverse twiddles
 template <typename A>
 __device__ __forceinline__ void inv_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
+    const u32 Z = args.zero;
 #pragma unroll
     for (int s = 0; s < 5; s++) {
 #pragma unroll
@@ -132,13 +149,13 @@ __device__ __forceinline__ void inv_passA(u32 (&v)[32], const A& args, u32 Q, u3
                 continue;
             const int ti = (16 >> s) + (r >> (s + 1));
             u32 U = v[r], V = v[r + (1 << s)];
-            v[r] = cond_sub(U + V, Q2);
+            v[r] = cond_sub(U + V + Z, Q2);
             v[r + (1 << s)] = shoup_mul(U - V + Q2, args.twA_i[ti][0], args.twA_i[ti][1], Q);
         }
     }
 }
 
-template <int LOGN, int DK, int G>
+template <int LOGN, int DK, int G, bool SKIP>
 __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
     using K = KCfg<LOGN, DK, G>;
     constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS, NT = K::NT;
@@ -234,11 +251,55 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
     const u32 QHalf = Q >> 1;
     const u32 gBits = C.gBits, gmask = (1u << gBits) - 1;
 
+    if (SKIP) {
+        // Top-digit elimination.  With no digits thrown and B^(DK-1) * (B/2 - 1) > Q/2 the signed digits satisfy
+        // c = sum_l d_l B^l EXACTLY (the top digit never wraps), hence NTT(d_top) = B^-(DK-1) (NTT(c) - sum_{l<top}
+        // B^l NTT(d_l)).  Substituting into sum_l NTT(d_l) BK_l gives sum_{l<top} NTT(d_l) BK'_l + NTT(c) BK'_top
+        // with BK'_l = BK_l - B^(l-top) BK_top and BK'_top = B^-top BK_top (done once at setup).  NTT(c) is simply the
+        // evaluation-domain accumulator, maintained as acc_eval += delta in the pointwise stage and kept in the
+        // shared-memory region the top digit would have used: 2 of the 2*DK forward transforms per step disappear.
+        u32 v[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            v[r] = c[r];
+        fwd_passA(v, A, Q, Q2);
+        u32* reg = Dsm + (size_t)g * D * RS + (size_t)(j + 2 * (DK - 1)) * RS;
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            reg[pos_of(T + TPN * r)] = v[r];
+        __syncwarp();
+        {
+            const uint4* p4 = reinterpret_cast<const uint4*>(reg + 36 * T);
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                uint4 w = p4[x];
+                v[4 * x] = w.x; v[4 * x + 1] = w.y; v[4 * x + 2] = w.z; v[4 * x + 3] = w.w;
+            }
+        }
+        __syncwarp();
+        fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {   // < 22Q -> canonical
+            u32 x = v[r];
+            x = cond_sub(x, 16 * Q); x = cond_sub(x, 8 * Q); x = cond_sub(x, 4 * Q); x = cond_sub(x, Q2); x = cond_sub(x, Q);
+            // the key carries N^-1 (unscaled inverse transform), so delta = true_delta / N: keep acc_eval / N as well
+            // (the transformed top row carries the compensating factor N, see bk_relayout_cggi32_kernel)
+            v[r] = A.mod.mont_mul(x, A.ninvM);
+        }
+        {
+            uint4* p4 = reinterpret_cast<uint4*>(reg + 36 * T);
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+                p4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+        }
+        __syncthreads();
+    }
+
     // =========================================================================================================
     for (u32 i = 0; i < n; i++) {
         // ---- phase 1: decompose + forward NTT of the DK digit polynomials of component j ---------------------
 #pragma unroll 1
-        for (int l = 0; l < DK; l++) {
+        for (int l = 0; l < (SKIP ? DK - 1 : DK); l++) {
             u32 v[32];
             const u32 sh = gBits * (l + C.numThrow);
 #pragma unroll
@@ -264,7 +325,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                 }
             }
             __syncwarp();
-            fwd_passB<PB>(v, tw, twp, Q, Q2);
+            fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
             {
                 uint4* p4 = reinterpret_cast<uint4*>(reg + 36 * T);
 #pragma unroll
@@ -314,7 +375,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                     auto redc_lazy = [&](u64 x) -> u32 {
                         u32 lo = (u32)x, hi = (u32)(x >> 32);
                         u32 m = lo * qinv;
-                        u32 t = __umulhi(m, Q);
+                        u32 t = mulhi_w(m, Q);
                         return hi - t + Q;
                     };
                     u32 r00 = redc_lazy(s00), r01 = redc_lazy(s01), r10 = redc_lazy(s10), r11 = redc_lazy(s11);
@@ -330,8 +391,20 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                     u64 t0 = (u64)r00 * m1 + (u64)r10 * m2;
                     u64 t1 = (u64)r01 * m1 + (u64)r11 * m2;
                     u32* wreg = Dsm + (size_t)gg * D * RS + pk;
-                    wreg[0] = A.mod.redc(t0);
-                    wreg[RS] = A.mod.redc(t1);
+                    auto redc_full = [&](u64 x) -> u32 {   // x < Q * 2^32 -> [0, Q)
+                        u32 lo = (u32)x, hi = (u32)(x >> 32);
+                        u32 t = mulhi_w(lo * qinv, Q);
+                        u32 r = hi - t;
+                        return hi < t ? r + Q : r;
+                    };
+                    const u32 dl0 = redc_full(t0), dl1 = redc_full(t1);
+                    wreg[0] = dl0;
+                    wreg[RS] = dl1;
+                    if (SKIP) {   // acc_eval += delta (kept canonical)
+                        u32* areg = wreg + (size_t)(2 * (DK - 1)) * RS;
+                        areg[0] = cond_sub(areg[0] + dl0, Q);
+                        areg[RS] = cond_sub(areg[RS] + dl1, Q);
+                    }
                 }
                 if (it + 1 < ITERS) {
 #pragma unroll
@@ -364,7 +437,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                     v[4 * x] = w.x; v[4 * x + 1] = w.y; v[4 * x + 2] = w.z; v[4 * x + 3] = w.w;
                 }
             }
-            inv_passB<PB>(v, tw, twp, Q, Q2);
+            inv_passB<PB>(v, tw, twp, Q, Q2, A.zero);
             __syncwarp();
             {
                 uint4* p4 = reinterpret_cast<uint4*>(reg + 36 * Tv);
@@ -435,6 +508,16 @@ bool cggi32_supported(const tfhe_b200_params& p) {
     return true;
 }
 
+// top-digit elimination is exact iff the top signed digit can never wrap (see the kernel prologue)
+bool cggi32_skip_top_ok(const tfhe_b200_params& p) {
+    if (p.numDigitsToThrow != 0 || p.digitsG < 2)
+        return false;
+    u64 B = p.baseG, m = p.Q >> 1;
+    for (u32 i = 1; i < p.digitsG; i++)
+        m = (m + B / 2 + B - 1) / B;   // upper bound of |d_i|
+    return m <= B / 2 - 1;
+}
+
 static u32 bitrev_h(u32 x, u32 bits) {
     u32 r = 0;
     for (u32 i = 0; i < bits; i++) {
@@ -489,19 +572,24 @@ void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::
         }
 }
 
-template <int LOGN, int DK, int G>
-static cudaError_t launch_t(const CGGI32Args& a, cudaStream_t s) {
+template <int LOGN, int DK, int G, bool SKIP>
+static cudaError_t launch_t2(const CGGI32Args& a, cudaStream_t s) {
     using K = KCfg<LOGN, DK, G>;
     const size_t smem = K::smem_bytes((int)a.c.n);
     if (smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess)
         return e;
     const int grid = (a.c.batch + G - 1) / G;
-    br_cggi32_kernel<LOGN, DK, G><<<grid, K::NT, smem, s>>>(a);
+    br_cggi32_kernel<LOGN, DK, G, SKIP><<<grid, K::NT, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+template <int LOGN, int DK, int G>
+static cudaError_t launch_t(const CGGI32Args& a, cudaStream_t s, bool skip) {
+    return skip ? launch_t2<LOGN, DK, G, true>(a, s) : launch_t2<LOGN, DK, G, false>(a, s);
 }
 
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group) {
@@ -523,9 +611,11 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     }
     a.dig_off = (u32)off;
     a.dig_add = t.mod.Q - B / 2;
+    a.zero = 0;
+    a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
     const int dk = (int)c.digitsKept;
 #define CASE(LOGN, DK, GG) \
-    if (c.logN == LOGN && dk == DK && group == GG) return launch_t<LOGN, DK, GG>(a, s);
+    if (c.logN == LOGN && dk == DK && group == GG) return launch_t<LOGN, DK, GG>(a, s, t.skip_top);
     if (c.logN == 10) {
         if (group == 0) group = (dk <= 4) ? 4 : 2;
         CASE(10, 4, 4) CASE(10, 4, 2) CASE(10, 4, 1)

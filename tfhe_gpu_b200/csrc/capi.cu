@@ -6,6 +6,7 @@
 // std::vector<LWECiphertext> twice per bootstrap, bootstrapping.cu:1616-1667,1877-1905).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -68,6 +69,7 @@ struct tfhe_b200_handle {
     tfhe_b200_params p;
     bool is64 = false;
     bool have_cggi32 = false;
+    bool skip_top = false;
     int force_generic = 0;
     int group = 0;  // ciphertexts per CTA of the cggi32 kernel (0 = default)
     u32 logN = 0, d = 0, gBits = 0;
@@ -246,9 +248,15 @@ static int encode_keys(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M, const u6
 }
 
 // the specialised 32-bit CGGI layout is derived on the device from the (already Montgomery-encoded) generic copy
-__global__ void bk_relayout_cggi32_kernel(u32* dst, const u32* src, u32 n, u32 d, u32 N) {
-    // destination [i][x][k][c]: word w = 4x + c = (key*d + l)*2 + j of evaluation slot k  (see br_cggi32.cu)
+__global__ void bk_relayout_cggi32_kernel(u32* dst, const u32* src, u32 n, u32 d, u32 N, ModCtx<u32> M, int skip,
+                                          const u32* cM /* [d/2] Montgomery constants, see below */) {
+    // destination [i][x][k][c]: word w = 4x + c = (key*d + l')*2 + j of evaluation slot k  (see br_cggi32.cu)
+    // With top-digit elimination (skip != 0) the rows are transformed (row l' = jin + 2l, top = d/2 - 1):
+    //   l < top : BK'_l = BK_l - B^(l-top) * BK_top        (cM[l]   = B^(l-top) in Montgomery form)
+    //   l = top : BK'_top = N * B^-top * BK_top            (cM[top] = N * B^-top in Montgomery form; the kernel
+    //             multiplies this row by acc_eval / N because every stored key word already carries N^-1)
     const size_t total = (size_t)n * N * 2 * d * 2;
+    const u32 top = d / 2 - 1;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x) {
         size_t r = idx;
@@ -257,8 +265,16 @@ __global__ void bk_relayout_cggi32_kernel(u32* dst, const u32* src, u32 n, u32 d
         u32 x = r % d; r /= d;     // 4d words per slot = d planes
         u32 i = (u32)r;
         u32 w = 4 * x + c;
-        u32 j = w % 2, l = (w / 2) % d, key = w / (2 * d);
-        dst[idx] = src[((((size_t)key * n + i) * d + l) * 2 + j) * N + k];
+        u32 j = w % 2, lp = (w / 2) % d, key = w / (2 * d);
+        const size_t base = (((size_t)key * n + i) * d) * 2 * N;
+        u32 val = src[base + ((size_t)lp * 2 + j) * N + k];
+        if (skip) {
+            const u32 jin = lp & 1, l = lp >> 1;
+            const u32 vt = src[base + ((size_t)(jin + 2 * top) * 2 + j) * N + k];
+            const u32 t = M.mont_mul(vt, cM[l]);
+            val = (l == top) ? t : M.sub(val, t);
+        }
+        dst[idx] = val;
     }
 }
 
@@ -277,7 +293,9 @@ extern "C" int tfhe_b200_num_gpus(const tfhe_b200_handle* h) {
 extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
     if (!h)
         return "";
-    return (h->have_cggi32 && !h->force_generic) ? "cggi_u32_ntt32" : h->variant.c_str();
+    if (h->have_cggi32 && !h->force_generic)
+        return h->skip_top ? "cggi_u32_ntt32_skiptop" : "cggi_u32_ntt32";
+    return h->variant.c_str();
 }
 extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value) {
     if (!h || !key)
@@ -370,6 +388,8 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
     else
         h->m32 = make_modctx<u32>(p.Q);
     h->have_cggi32 = !h->is64 && cggi32_supported(p);
+    // TFHE_B200_NO_SKIPTOP=1 (debug) keeps the untransformed keys and the full set of forward transforms
+    h->skip_top = h->have_cggi32 && cggi32_skip_top_ok(p) && !getenv("TFHE_B200_NO_SKIPTOP");
     h->variant = h->is64 ? "generic_u64" : "generic_u32";
     if (p.method == TFHE_B200_METHOD_AP)
         h->variant += "_dm";
@@ -412,8 +432,24 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 return r;
             if (h->have_cggi32) {
                 CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi32, h->bk_words * 4));
+                // constants for the top-digit elimination: B^(l-top) (l < top) and B^-top, Montgomery form
+                const u32 dk = h->d / 2, top = dk - 1;
+                std::vector<u32> cM(dk);
+                const u64 Binv = h_powmod(p.baseG % p.Q, p.Q - 2, p.Q);
+                for (u32 l = 0; l < dk; l++) {
+                    u64 cst = h_powmod(Binv, l == top ? top : top - l, p.Q);
+                    if (l == top)   // the kernel keeps acc_eval scaled by N^-1: compensate in the row it multiplies
+                        cst = h_mulmod(cst, p.N % p.Q, p.Q);
+                    cM[l] = to_mont<u32>(cst, h->m32);
+                }
+                u32* dcM = nullptr;
+                CUDA_TRY(cudaMalloc((void**)&dcM, dk * 4));
+                CUDA_TRY(cudaMemcpy(dcM, cM.data(), dk * 4, cudaMemcpyHostToDevice));
                 bk_relayout_cggi32_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi32, (const u32*)d0.bk_generic, p.n,
-                                                                          h->d, p.N);
+                                                                          h->d, p.N, h->m32, h->skip_top ? 1 : 0, dcM);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaStreamSynchronize(d0.stream));
+                CUDA_TRY(cudaFree(dcM));
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaStreamSynchronize(d0.stream));
             }
@@ -490,7 +526,7 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
         return 0;
     if (h->have_cggi32 && !h->force_generic) {
         CGGI32Tables t;
-        t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB;
+        t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB; t.skip_top = h->skip_top;
         CUDA_TRY(launch_br_cggi32(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->is64) {

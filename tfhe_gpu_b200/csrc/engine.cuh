@@ -60,9 +60,11 @@ struct CGGI32Tables {
     const u32* bk;        // [i][k][key][l][j]  Montgomery form * N^-1
     const u32* psi_pow;   // [2N] Montgomery form
     const u32* twB;       // per-thread pass-B twiddles + Shoup companions, forward
+    bool skip_top;        // keys were transformed for top-digit elimination (see br_cggi32.cu)
     const u32* twA;       // HOST pointer: uniform pass-A twiddles + companions [fwd|inv][32][2] (kernel params)
 };
 bool cggi32_supported(const tfhe_b200_params& p);
+bool cggi32_skip_top_ok(const tfhe_b200_params& p);
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group);
 size_t cggi32_twB_words(u32 N);
 size_t cggi32_twA_words();
