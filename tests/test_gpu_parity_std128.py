@@ -24,6 +24,26 @@ def test_std128_ap_gates(keyset):
     assert ks.port.decrypt_batch(ks.sk, got, q, 4) == [a ^ b for a, b in zip(m1, m2)]
 
 
+def test_std128_ap_specialised_and_generic_kernels_agree(keyset, rng):
+    ks = keyset("std128_ap")
+    q, n = ks.p.q, ks.p.n
+    c1 = rng.integers(0, q, (21, n + 1), dtype=np.uint64)    # ragged vs the CTA group of 4
+    c2 = rng.integers(0, q, (21, n + 1), dtype=np.uint64)
+    c1[0, :n] = 0
+    c2[0, :n] = 0                                            # every refresh digit is zero: all steps sit out
+    g = ks.gpu()
+    assert g.kernel_variant.startswith("dm_u32")
+    a = g.EvalBinGate("NAND", c1, c2)
+    g.set_option("force_generic", 1)
+    try:
+        b = g.EvalBinGate("NAND", c1, c2)
+    finally:
+        g.set_option("force_generic", 0)
+    assert np.array_equal(a, b)
+    want = ks.port.eval_bin_gate(ks.bk, ks.ksk, po.GATES["NAND"], c1[:3], c2[:3], q)
+    assert np.array_equal(a[:3], want)
+
+
 def test_std128_evalfunc_logq12(keyset):
     """configs[3]: arbitrary LUT, two chained bootstraps at N=2048 / 54-bit Q / qKS=2^35."""
     ks = keyset("std128_func12")

@@ -22,7 +22,7 @@
 //     sample extraction and the a(X^-1) transpose are fused in.
 #include <cstring>
 
-#include "engine.cuh"
+#include "ntt32.cuh"
 
 namespace tfhe_b200 {
 
@@ -40,120 +40,6 @@ struct CGGI32Args {
     u32 ninvM;           // N^-1 in Montgomery form (SKIP: the evaluation-domain accumulator is kept scaled by N^-1)
     u32 zero;            // always 0: third IADD3 operand that keeps ptxas from turning adds into IMAD.IADD (fma-heavy pipe)
 };
-
-__device__ __forceinline__ u32 mulhi_w(u32 a, u32 b) {
-    // high half through IMAD.WIDE (full rate) instead of IMAD.HI (half rate)
-    u32 hi, lo;
-    asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%1, %0}, p; }" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
-    (void)lo;
-    return hi;
-}
-__device__ __forceinline__ u32 shoup_mul(u32 y, u32 w, u32 wp, u32 Q) {
-    // y*w mod Q up to one extra Q: result in [0, 2Q) for any 32-bit y.
-    // The quotient estimate is the high half of a full-rate IMAD.WIDE (no addend): measured 129 /clk/SM on B200 vs
-    // 62 /clk/SM for IMAD.HI (profiles/r01_imad_peak.json), so the butterfly costs 3 fma-heavy slots instead of 4.
-    u32 q, lo;
-    asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%1, %0}, p; }" : "=r"(q), "=r"(lo) : "r"(y), "r"(wp));
-    (void)lo;
-    return y * w - q * Q;
-}
-__device__ __forceinline__ u32 cond_sub(u32 x, u32 m) {
-    // x < 2m  ->  x mod m
-    return min(x, x - m);
-}
-__device__ __forceinline__ u32 pos_of(u32 idx) {
-    return idx + ((idx >> 5) << 2);
-}
-
-template <int LOGN, int DK, int G>
-struct KCfg {
-    static constexpr int N = 1 << LOGN;
-    static constexpr int TPN = N / 32;            // threads per NTT
-    static constexpr int PB = LOGN - 5;           // pass-B stages
-    static constexpr int NTW = 32 - (32 >> PB);   // per-thread twiddles
-    static constexpr int D = 2 * DK;              // digit polynomials
-    static constexpr int RS = N + N / 8 + (LOGN == 9 ? 16 : 0);  // padded region stride (words)
-    static constexpr int NT = G * 2 * TPN;        // threads per CTA
-    static constexpr size_t smem_bytes(int n) {
-        return (size_t)G * D * RS * 4 + (size_t)2 * N * 4 + (size_t)G * ((n + 1) / 2 * 2) * 2 + 64;
-    }
-};
-
-// ---- register-resident NTT passes -----------------------------------------------------------------------------
-// forward pass A: Cooley-Tukey stages with stride TPN*2^s, s = 4..0 (uniform twiddles from the parameter bank)
-template <typename A>
-__device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
-    const u32 Z = args.zero;
-#pragma unroll
-    for (int s = 4; s >= 0; s--) {
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (r & (1 << s))
-                continue;
-            const int ti = (16 >> s) + (r >> (s + 1));
-            u32 t = shoup_mul(v[r + (1 << s)], args.twA_f[ti][0], args.twA_f[ti][1], Q);
-            u32 x = v[r];
-            v[r] = x + t + Z;
-            v[r + (1 << s)] = x - t + Q2;
-        }
-    }
-}
-// forward pass B: strides 2^s, s = PB-1..0, per-thread twiddles
-template <int PB>
-__device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2,
-                                          u32 Z) {
-#pragma unroll
-    for (int s = PB - 1; s >= 0; s--) {
-        const int off = (32 >> (s + 1)) - (32 >> PB);
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (r & (1 << s))
-                continue;
-            const int ti = off + (r >> (s + 1));
-            u32 t = shoup_mul(v[r + (1 << s)], tw[ti], twp[ti], Q);
-            u32 x = v[r];
-            v[r] = x + t + Z;
-            v[r + (1 << s)] = x - t + Q2;
-        }
-    }
-}
-// inverse pass B' on the MIRRORED block (virtual thread TPN-1-T): Gentleman-Sande stages 2^s, s = 0..PB-1, with
-// (U - V) * psi^-x == (V - U) * psi^{mirror}; all values kept below 2Q
-template <int PB>
-__device__ __forceinline__ void inv_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2,
-                                          u32 Z) {
-#pragma unroll
-    for (int s = 0; s < PB; s++) {
-        const int off = (32 >> (s + 1)) - (32 >> PB);
-        const int cnt = 32 >> (s + 1);
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (r & (1 << s))
-                continue;
-            const int ti = off + (cnt - 1 - (r >> (s + 1)));
-            u32 U = v[r], V = v[r + (1 << s)];
-            v[r] = cond_sub(U + V + Z, Q2);
-            v[r + (1 << s)] = shoup_mul(V - U + Q2, tw[ti], twp[ti], Q);
-        }
-    }
-}
-// inverse pass A': strides TPN*2^s, s = 0..4, uniform inverse twiddles
-template <typename A>
-__device__ __forceinline__ void inv_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
-    const u32 Z = args.zero;
-#pragma unroll
-    for (int s = 0; s < 5; s++) {
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (r & (1 << s))
-                continue;
-            const int ti = (16 >> s) + (r >> (s + 1));
-            u32 U = v[r], V = v[r + (1 << s)];
-            v[r] = cond_sub(U + V + Z, Q2);
-            v[r + (1 << s)] = shoup_mul(U - V + Q2, args.twA_i[ti][0], args.twA_i[ti][1], Q);
-        }
-    }
-}
 
 template <int LOGN, int DK, int G, bool SKIP>
 __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {

@@ -1,0 +1,331 @@
+// Specialised AP/DM blind rotation for 32-bit moduli (STD128 with method AP: N = 1024, Q 27-bit, baseG = 2^7,
+// baseR = 32, digitsR = 2).  Same register-resident machinery as br_cggi32.cu (ntt32.cuh), adapted to the DM
+// accumulator (rgsw-acc-dm.cpp:80-110, 306-359):
+//
+//   for i < n, for k < digitsR:  a0 = k-th base-baseR digit of (q - a_i) mod q;  if a0 == 0 skip
+//       acc[j] = sum_{l'=1}^{d-1} NTT(digit_l') * BK[i][a0][k][l'][j]            (REPLACE; row l' = 0 is dropped)
+//
+// Differences to the CGGI kernel:
+//   * the key row is selected by the ciphertext's own digit a0, so the G ciphertexts of a CTA do NOT share key words:
+//     every (ciphertext, slot) reads its own 16 words (64 KB per ciphertext-step out of a 2.1 GB table, straight from
+//     HBM); all G loads of a slot are issued before the first multiply;
+//   * the G ciphertexts still walk the n*digitsR steps in lock-step (barriers), a ciphertext whose digit is zero sits
+//     the step out (warp-uniform predicate: a warp is one (ciphertext, component));
+//   * the accumulator is REPLACED, so the evaluation-domain accumulator needed by the top-digit elimination is simply
+//     the pointwise result of the previous active step -- no accumulation, no extra transform;
+//   * top-digit elimination is mandatory here (cggi32_skip_top_ok): 6 forward + 2 inverse transforms per active step;
+//     the dropped row l' = 0 is handled by the key transform (BK'_0 = -B^-top BK_top for component a).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "ntt32.cuh"
+
+namespace tfhe_b200 {
+
+struct DM32Args {
+    BRCommon c;
+    ModCtx<u32> mod;
+    const u32* bk;       // [keyidx = (i*baseR + a0)*digitsR + k][x(D/2)][slot(N)][4]: word w = l'*2 + j
+    const u32* twB;
+    u32 twA_f[32][2];
+    u32 twA_i[32][2];
+    u32 Q2, dig_off, dig_add, ninvM, zero;
+};
+
+template <int LOGN, int DK, int G>
+__global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const __grid_constant__ DM32Args A) {
+    using K = KCfg<LOGN, DK, G>;
+    constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS, NT = K::NT;
+    constexpr int P = D / 2;   // uint4 planes per slot (2*D words)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u32* Dsm = reinterpret_cast<u32*>(smem_raw);              // [G][D][RS]
+    int* kidx = reinterpret_cast<int*>(Dsm + (size_t)G * D * RS);  // [G][steps] key row of the step, -1 = sit out
+
+    const BRCommon& C = A.c;
+    const u32 Q = A.mod.Q, Q2 = A.Q2, qinv = A.mod.qinv;
+    const u32 n = C.n;
+    const u32 steps = n * C.digitsR;
+    const int tid = threadIdx.x;
+    const int g = tid / (2 * TPN), j = (tid / TPN) & 1, T = tid % TPN;
+    const int ct = blockIdx.x * G + g;
+    const bool live = ct < C.batch;
+    const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
+
+    {
+        // rgsw-acc-dm.cpp:102-109: aI = (q - a_i) mod q with q = the scheme's q (NOT the ciphertext modulus)
+        const u32 q = (u32)C.q_lwe;
+        const int lt = tid % (2 * TPN);
+        for (u32 i = lt; i < n; i += 2 * TPN) {
+            u32 aI = (q - (u32)(lwe[i] % q)) % q;
+            for (u32 k = 0; k < C.digitsR; k++, aI /= C.baseR) {
+                u32 a0 = aI % C.baseR;
+                kidx[g * steps + i * C.digitsR + k] = (live && a0) ? (int)((i * C.baseR + a0) * C.digitsR + k) : -1;
+            }
+        }
+    }
+    u32 tw[32], twp[32];
+    {
+        const uint2* src = reinterpret_cast<const uint2*>(A.twB) + (size_t)T * NTW;
+#pragma unroll
+        for (int x = 0; x < NTW; x++) {
+            uint2 w = src[x];
+            tw[x] = w.x;
+            twp[x] = w.y;
+        }
+    }
+
+    // ---- accumulator initialisation in A layout -------------------------------------------------------------------
+    u32 c[32];
+    if (C.acc_init == ACC_EXPLICIT) {
+        const u64* src = C.acc_io + ((size_t)(live ? ct : 0) * 2 + j) * N;
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            c[r] = live ? (u32)src[T + TPN * r] : 0;
+    }
+    else {
+        const u32 q = (u32)C.ct_mod, b = (u32)(lwe[n] % q);
+        const u32 factor = (2 * N) / q, fshift = __ffs(factor) - 1;
+        const u32 q1 = (u32)C.gate_q1;
+        u32 q2 = q1 + (q >> 1);
+        if (q2 >= q)
+            q2 -= q;
+        const u64* tab = C.table + (C.acc_init == ACC_TABLE_PER ? (size_t)(live ? ct : 0) * q : 0);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const u32 idx = T + TPN * r;
+            u32 val = 0;
+            if (j == 1 && live && (idx & (factor - 1)) == 0) {
+                u32 jj = idx >> fshift;
+                u32 temp = b >= jj ? b - jj : b + q - jj;
+                if (C.acc_init == ACC_GATE) {
+                    bool in = (q1 < q2) ? ((temp >= q1) && (temp < q2)) : !((temp >= q2) && (temp < q1));
+                    val = in ? (u32)(Q - C.Q8) : (u32)C.Q8;
+                }
+                else
+                    val = (u32)(C.scale * tab[temp]);
+            }
+            c[r] = val;
+        }
+    }
+
+    u32* myD = Dsm + (size_t)g * D * RS;
+    const u32 QHalf = Q >> 1;
+    const u32 gBits = C.gBits, gmask = (1u << gBits) - 1;
+
+    auto load_B = [&](u32 (&v)[32], const u32* reg, int tt) {
+        const uint4* p4 = reinterpret_cast<const uint4*>(reg + 36 * tt);
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            uint4 w = p4[x];
+            v[4 * x] = w.x; v[4 * x + 1] = w.y; v[4 * x + 2] = w.z; v[4 * x + 3] = w.w;
+        }
+    };
+    auto store_B = [&](const u32 (&v)[32], u32* reg, int tt) {
+        uint4* p4 = reinterpret_cast<uint4*>(reg + 36 * tt);
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+            p4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+    };
+
+    // evaluation-domain accumulator (scaled by N^-1, see br_cggi32.cu) of the initial accumulator -> top-digit region
+    {
+        u32 v[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            v[r] = c[r];
+        fwd_passA(v, A, Q, Q2);
+        u32* reg = myD + (size_t)(j + 2 * (DK - 1)) * RS;
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            reg[pos_of(T + TPN * r)] = v[r];
+        __syncwarp();
+        load_B(v, reg, T);
+        __syncwarp();
+        fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            u32 x = v[r];
+            x = cond_sub(x, 16 * Q); x = cond_sub(x, 8 * Q); x = cond_sub(x, 4 * Q); x = cond_sub(x, Q2); x = cond_sub(x, Q);
+            v[r] = A.mod.mont_mul(x, A.ninvM);
+        }
+        store_B(v, reg, T);
+    }
+    __syncthreads();
+
+    for (u32 s = 0; s < steps; s++) {
+        const bool act = kidx[g * steps + s] >= 0;   // uniform over the (ciphertext, component) thread group
+        // ---- phase 1: digits 0..DK-2 of component j -> forward NTT -------------------------------------------------
+        if (act) {
+#pragma unroll 1
+            for (int l = 0; l < DK - 1; l++) {
+                u32 v[32];
+                const u32 sh = gBits * l;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
+                    u32 Dv = (u32)(dv + (int)A.dig_off);
+                    v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
+                }
+                fwd_passA(v, A, Q, Q2);
+                u32* reg = myD + (size_t)(j + 2 * l) * RS;
+#pragma unroll
+                for (int r = 0; r < 32; r++)
+                    reg[pos_of(T + TPN * r)] = v[r];
+                __syncwarp();
+                load_B(v, reg, T);
+                __syncwarp();
+                fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+                store_B(v, reg, T);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: pointwise product with the ciphertext's own key row; result replaces the accumulator ---------
+        {
+            constexpr int ITERS = N / NT;
+            static_assert(N % NT == 0, "unsupported CTA shape");
+#pragma unroll 1
+            for (int it = 0; it < ITERS; it++) {
+                const int k = tid + it * NT;
+                const u32 pk = pos_of(k);
+                u32 bkv[G][2 * D];
+                int rows[G];
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
+                    rows[gg] = kidx[gg * steps + s];
+                    if (rows[gg] >= 0) {
+                        const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (size_t)rows[gg] * P * N + k;
+#pragma unroll
+                        for (int x = 0; x < P; x++) {
+                            uint4 w = __ldg(p4 + (size_t)x * N);
+                            bkv[gg][4 * x] = w.x; bkv[gg][4 * x + 1] = w.y; bkv[gg][4 * x + 2] = w.z; bkv[gg][4 * x + 3] = w.w;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
+                    if (rows[gg] < 0)
+                        continue;
+                    u32* dreg = Dsm + (size_t)gg * D * RS + pk;
+                    u64 s0 = 0, s1 = 0;
+#pragma unroll
+                    for (int l = 0; l < D; l++) {
+                        u32 x = dreg[(size_t)l * RS];
+                        s0 += (u64)x * bkv[gg][l * 2 + 0];
+                        s1 += (u64)x * bkv[gg][l * 2 + 1];
+                    }
+                    // sums < D * 22Q * Q < 2^62: reduce in two steps (lazy, then canonical)
+                    auto redc2 = [&](u64 x) -> u32 {
+                        u32 lo = (u32)x, hi = (u32)(x >> 32);
+                        u32 t = mulhi_w(lo * qinv, Q);
+                        u32 r = hi - t + Q;                       // < 2^31 + Q, == x R^-1 (mod Q)
+                        r = cond_sub(r, 8 * Q); r = cond_sub(r, 4 * Q); r = cond_sub(r, Q2); r = cond_sub(r, Q);
+                        return r;
+                    };
+                    const u32 d0 = redc2(s0), d1 = redc2(s1);
+                    dreg[0] = d0;                                 // delta for the inverse transform (regions 0, 1)
+                    dreg[RS] = d1;
+                    dreg[(size_t)(2 * (DK - 1)) * RS] = d0;       // and the new evaluation-domain accumulator
+                    dreg[(size_t)(2 * (DK - 1) + 1) * RS] = d1;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: c = INTT(result) (REPLACE) ---------------------------------------------------------------------
+        if (act) {
+            u32 v[32];
+            u32* reg = myD + (size_t)j * RS;
+            const int Tv = TPN - 1 - T;
+            load_B(v, reg, Tv);
+            inv_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+            __syncwarp();
+            store_B(v, reg, Tv);
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                v[r] = reg[pos_of(T + TPN * r)];
+            __syncwarp();
+            inv_passA(v, A, Q, Q2);
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                c[r] = cond_sub(v[r], Q);   // v < 2Q
+        }
+    }
+
+    if (live) {
+        if (C.write_acc) {
+            u64* dst = C.acc_io + (size_t)ct * 2 * N;
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const u32 idx = T + TPN * r;
+                if (j == 0) {
+                    u32 val = c[r];
+                    dst[idx == 0 ? 0 : N - idx] = (idx == 0 || val == 0) ? val : Q - val;
+                }
+                else
+                    dst[N + idx] = c[r];
+            }
+        }
+        if (C.ext) {
+            u64* dst = C.ext + (size_t)ct * (N + 1);
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const u32 idx = T + TPN * r;
+                if (j == 0) {
+                    u32 val = c[r];
+                    dst[idx == 0 ? 0 : N - idx] = (idx == 0 || val == 0) ? val : Q - val;
+                }
+                else if (idx == 0) {
+                    u64 val = (u64)c[r] + C.ext_add_b;
+                    dst[N] = val >= Q ? val - Q : val;
+                }
+            }
+        }
+    }
+}
+
+bool dm32_supported(const tfhe_b200_params& p) {
+    if (p.method != TFHE_B200_METHOD_AP || p.N != 1024 || p.digitsG != 4 || p.numDigitsToThrow != 0)
+        return false;
+    if (p.Q >= (1ULL << 32) / 22)
+        return false;
+    if ((u64)p.n * p.digitsR > 8192)
+        return false;
+    return cggi32_skip_top_ok(p);
+}
+
+cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s) {
+    DM32Args a;
+    a.c = c;
+    a.mod = t.mod;
+    a.bk = t.bk;
+    a.twB = t.twB;
+    memcpy(a.twA_f, t.twA, sizeof(a.twA_f));
+    memcpy(a.twA_i, t.twA + 64, sizeof(a.twA_i));
+    a.Q2 = 2 * t.mod.Q;
+    const u32 B = 1u << c.gBits;
+    u64 off = 0, pw = 1;
+    for (u32 i = 0; i < c.digitsKept; i++) {
+        off += (B / 2) * pw;
+        pw *= B;
+    }
+    a.dig_off = (u32)off;
+    a.dig_add = t.mod.Q - B / 2;
+    a.zero = 0;
+    a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
+    constexpr int G = 4;
+    using K = KCfg<10, 4, G>;
+    const size_t smem = (size_t)G * K::D * K::RS * 4 + (size_t)G * c.n * c.digitsR * 4 + 64;
+    if (smem > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(br_dm32_kernel<10, 4, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    const int grid = (c.batch + G - 1) / G;
+    br_dm32_kernel<10, 4, G><<<grid, K::NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace tfhe_b200

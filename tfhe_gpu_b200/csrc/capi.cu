@@ -70,6 +70,7 @@ struct tfhe_b200_handle {
     bool is64 = false;
     bool have_cggi32 = false;
     bool skip_top = false;
+    bool have_dm32 = false;
     int force_generic = 0;
     int group = 0;  // ciphertexts per CTA of the cggi32 kernel (0 = default)
     u32 logN = 0, d = 0, gBits = 0;
@@ -278,6 +279,38 @@ __global__ void bk_relayout_cggi32_kernel(u32* dst, const u32* src, u32 n, u32 d
     }
 }
 
+// AP/DM variant of the re-layout: source [row][l'(d)][j(2)][N] (row = (i*baseR + a0)*digitsR + k), destination
+// [row][x(d/2)][slot][4] with word w = l'*2 + j.  The DM accumulator drops row l' = 0 (rgsw-acc-dm.cpp:353,357) and the
+// kernel eliminates the top digit, so:  l < top: BK' = [l' >= 1] BK_l' - B^(l-top) BK_top(jin);  l = top: N B^-top BK_top.
+__global__ void bk_relayout_dm32_kernel(u32* dst, const u32* src, size_t rows, u32 d, u32 N, ModCtx<u32> M,
+                                        const u32* cM) {
+    const size_t per_row = (size_t)d * 2 * N;
+    const size_t total = rows * per_row;
+    const u32 top = d / 2 - 1;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        u32 c = r % 4; r /= 4;
+        u32 k = r % N; r /= N;
+        u32 x = r % (d / 2); r /= (d / 2);
+        size_t row = r;
+        u32 w = 4 * x + c;
+        u32 j = w % 2, lp = w / 2;
+        const u32 jin = lp & 1, l = lp >> 1;
+        const size_t base = row * per_row;
+        const u32 vt = src[base + ((size_t)(jin + 2 * top) * 2 + j) * N + k];
+        const u32 t = M.mont_mul(vt, cM[l]);
+        u32 val;
+        if (l == top)
+            val = t;
+        else {
+            u32 own = lp >= 1 ? src[base + ((size_t)lp * 2 + j) * N + k] : 0;
+            val = M.sub(own, t);
+        }
+        dst[idx] = val;
+    }
+}
+
 extern "C" size_t tfhe_b200_bk_words(const tfhe_b200_params* p) {
     return p ? bk_words_of(p) : 0;
 }
@@ -295,6 +328,8 @@ extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
         return "";
     if (h->have_cggi32 && !h->force_generic)
         return h->skip_top ? "cggi_u32_ntt32_skiptop" : "cggi_u32_ntt32";
+    if (h->have_dm32 && !h->force_generic)
+        return "dm_u32_ntt32_skiptop";
     return h->variant.c_str();
 }
 extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value) {
@@ -389,6 +424,7 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
         h->m32 = make_modctx<u32>(p.Q);
     h->have_cggi32 = !h->is64 && cggi32_supported(p);
     // TFHE_B200_NO_SKIPTOP=1 (debug) keeps the untransformed keys and the full set of forward transforms
+    h->have_dm32 = !h->is64 && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
     h->skip_top = h->have_cggi32 && cggi32_skip_top_ok(p) && !getenv("TFHE_B200_NO_SKIPTOP");
     h->variant = h->is64 ? "generic_u64" : "generic_u32";
     if (p.method == TFHE_B200_METHOD_AP)
@@ -410,7 +446,7 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
             int r = h->is64 ? build_tables<u64>(h, d, h->m64) : build_tables<u32>(h, d, h->m32);
             if (r)
                 return r;
-            if (h->have_cggi32) {
+            if (h->have_cggi32 || h->have_dm32) {
                 std::vector<u32> twB;
                 cggi32_build_tables(p, h->twA_host, twB);
                 CUDA_TRY(cudaMalloc((void**)&d.twB, twB.size() * 4));
@@ -453,6 +489,27 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaStreamSynchronize(d0.stream));
             }
+            if (h->have_dm32) {
+                const u32 dk = h->d / 2, top = dk - 1;
+                std::vector<u32> cM(dk);
+                const u64 Binv = h_powmod(p.baseG % p.Q, p.Q - 2, p.Q);
+                for (u32 l = 0; l < dk; l++) {
+                    u64 cst = h_powmod(Binv, l == top ? top : top - l, p.Q);
+                    if (l == top)
+                        cst = h_mulmod(cst, p.N % p.Q, p.Q);
+                    cM[l] = to_mont<u32>(cst, h->m32);
+                }
+                u32* dcM = nullptr;
+                CUDA_TRY(cudaMalloc((void**)&dcM, dk * 4));
+                CUDA_TRY(cudaMemcpy(dcM, cM.data(), dk * 4, cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi32, h->bk_words * 4));
+                bk_relayout_dm32_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi32, (const u32*)d0.bk_generic,
+                                                                        (size_t)p.n * p.baseR * p.digitsR, h->d, p.N,
+                                                                        h->m32, dcM);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaStreamSynchronize(d0.stream));
+                CUDA_TRY(cudaFree(dcM));
+            }
             const size_t tsz = h->is64 ? 8 : 4;
             const size_t ksk_bytes_total = (size_t)p.N * p.baseKS * p.dKS * h->row_stride * h->ksk_bytes;
             for (size_t k = 1; k < h->devs.size(); k++) {
@@ -468,7 +525,7 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 }
                 CUDA_TRY(cudaMalloc(&d.bk_generic, h->bk_words * tsz));
                 CUDA_TRY(cudaMemcpyPeerAsync(d.bk_generic, d.id, d0.bk_generic, d0.id, h->bk_words * tsz, d.stream));
-                if (h->have_cggi32) {
+                if (h->have_cggi32 || h->have_dm32) {
                     CUDA_TRY(cudaMalloc((void**)&d.bk_cggi32, h->bk_words * 4));
                     CUDA_TRY(cudaMemcpyPeerAsync(d.bk_cggi32, d.id, d0.bk_cggi32, d0.id, h->bk_words * 4, d.stream));
                 }
@@ -528,6 +585,12 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
         CGGI32Tables t;
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB; t.skip_top = h->skip_top;
         CUDA_TRY(launch_br_cggi32(c, t, d.stream, d.sm_count, h->group));
+    }
+    else if (h->have_dm32 && !h->force_generic) {
+        CGGI32Tables t;
+        t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB;
+        t.skip_top = true;
+        CUDA_TRY(launch_br_dm32(c, t, d.stream));
     }
     else if (h->is64) {
         BRTables<u64> t;

@@ -68,6 +68,8 @@ bool cggi32_skip_top_ok(const tfhe_b200_params& p);
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group);
 size_t cggi32_twB_words(u32 N);
 size_t cggi32_twA_words();
+bool dm32_supported(const tfhe_b200_params& p);
+cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s);
 void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::vector<u32>& twB);
 
 // LWE-side kernels (lwe_kernels.cu)
