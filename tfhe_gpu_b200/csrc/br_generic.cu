@@ -72,6 +72,69 @@ __device__ __forceinline__ void ntt_inv_smem(T* a, u32 npoly, u32 N, u32 logN, c
     }
 }
 
+// ---- 64-bit lazy variants (Q < 2^59 / 26): Shoup butterflies, no per-stage corrections in the forward transform ------
+__device__ __forceinline__ u64 shoup_mul64(u64 y, u64 w, u64 wp, u64 Q) {
+    u64 q = __umul64hi(y, wp);
+    return y * w - q * Q;   // in [0, 2Q) for any 64-bit y
+}
+__device__ __forceinline__ void ntt_fwd_lazy64(u64* a, u32 npoly, u32 N, const u64* __restrict__ sh, u64 Q) {
+    // forward: values grow by 2Q per stage (digits < Q on entry, < (1 + 2 logN) Q <= 25 Q on exit)
+    const u32 half = N >> 1;
+    const u64 Q2 = 2 * Q;
+    u32 t = N;
+    for (u32 m = 1; m < N; m <<= 1) {
+        t >>= 1;
+        const u32 tshift = __ffs(t) - 1;
+        for (u32 b = threadIdx.x; b < npoly * half; b += blockDim.x) {
+            u32 p = b / half, x = b - p * half;
+            u32 i = x >> tshift, jj = x & (t - 1);
+            u32 j = (i << (tshift + 1)) + jj;
+            u64* P = a + (size_t)p * N;
+            u64 U = P[j], V = shoup_mul64(P[j + t], sh[m + i], sh[N + m + i], Q);
+            P[j] = U + V;
+            P[j + t] = U - V + Q2;
+        }
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ void ntt_inv_lazy64(u64* a, u32 npoly, u32 N, const u64* __restrict__ sh, u64 Q) {
+    // inverse (no N^-1): all values kept below 2Q
+    const u32 half = N >> 1;
+    const u64 Q2 = 2 * Q;
+    u32 t = 1;
+    for (u32 m = N; m > 1; m >>= 1) {
+        const u32 h = m >> 1;
+        const u32 tshift = __ffs(t) - 1;
+        for (u32 b = threadIdx.x; b < npoly * half; b += blockDim.x) {
+            u32 p = b / half, x = b - p * half;
+            u32 i = x >> tshift, jj = x & (t - 1);
+            u32 j = (i << (tshift + 1)) + jj;
+            u64* P = a + (size_t)p * N;
+            u64 U = P[j], V = P[j + t];
+            u64 sum = U + V;
+            P[j] = sum >= Q2 ? sum - Q2 : sum;
+            P[j + t] = shoup_mul64(U - V + Q2, sh[h + i], sh[N + h + i], Q);
+        }
+        __syncthreads();
+        t <<= 1;
+    }
+}
+struct Acc128 {
+    u64 lo, hi;
+    __device__ __forceinline__ void mac(u64 x, u64 b) {
+        u64 pl = x * b, ph = __umul64hi(x, b);
+        lo += pl;
+        hi += ph + (lo < pl);
+    }
+};
+// Montgomery reduction of a 128-bit value X < Q * 2^64 -> [0, Q)
+__device__ __forceinline__ u64 redc128(const Acc128& X, const ModCtx<u64>& M) {
+    u64 m = X.lo * M.qinv;
+    u64 t = __umul64hi(m, M.Q);
+    u64 r = X.hi - t;
+    return X.hi < t ? r + M.Q : r;
+}
+
 template <typename T>
 __device__ __forceinline__ void decompose_smem(const T* c, T* D, u32 N, u32 gBits, u32 numThrow, u32 kept,
                                                const ModCtx<T>& M) {
@@ -185,9 +248,50 @@ __global__ void __launch_bounds__(1024, 1) br_generic_kernel(GenArgs<T> A) {
 
             decompose_smem<T>(c, D, N, C.gBits, C.numThrow, C.digitsKept, M);
             __syncthreads();
-            ntt_fwd_smem<T>(D, d, N, logN, A.t.tw_fwd, M);
+            if constexpr (sizeof(T) == 8)
+                ntt_fwd_lazy64(reinterpret_cast<u64*>(D), d, N, reinterpret_cast<const u64*>(A.t.sh_fwd), Q);
+            else
+                ntt_fwd_smem<T>(D, d, N, logN, A.t.tw_fwd, M);
 
             // pointwise multiply-accumulate against the RGSW key(s); delta written over D[0], D[1]
+            if constexpr (sizeof(T) == 8) {
+                // 64-bit path: lazy digits (< 25 Q) times key words (< Q) accumulate in 128 bits, ONE Montgomery
+                // reduction per output (sum < d * 25 Q^2 < Q 2^64 because Q < 2^55 and d <= 12: checked at setup)
+                const ModCtx<u64>& M8 = reinterpret_cast<const ModCtx<u64>&>(M);
+                const u64* D8 = reinterpret_cast<const u64*>(D);
+                const u64* e0 = reinterpret_cast<const u64*>(ek0);
+                const u64* e1 = reinterpret_cast<const u64*>(ek1);
+                for (u32 k = threadIdx.x; k < N; k += blockDim.x) {
+                    Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+                    const u32 l0 = dm ? 1 : 0;
+                    for (u32 l = l0; l < d; l++) {
+                        u64 x = D8[(size_t)l * N + k];
+                        a00.mac(x, e0[((size_t)l * 2 + 0) * N + k]);
+                        a01.mac(x, e0[((size_t)l * 2 + 1) * N + k]);
+                        if (!dm) {
+                            a10.mac(x, e1[((size_t)l * 2 + 0) * N + k]);
+                            a11.mac(x, e1[((size_t)l * 2 + 1) * N + k]);
+                        }
+                    }
+                    u64 s00 = redc128(a00, M8), s01 = redc128(a01, M8);
+                    if (!dm) {
+                        u64 s10 = redc128(a10, M8), s11 = redc128(a11, M8);
+                        u32 br = __brev(k) >> (32 - logN);
+                        u32 x = ((2 * br + 1) * e) & (twoN - 1);
+                        const u64* pp = reinterpret_cast<const u64*>(A.t.psi_pow);
+                        u64 m1 = M8.sub(pp[x], M8.oneM);
+                        u64 m2 = M8.sub(pp[(twoN - x) & (twoN - 1)], M8.oneM);
+                        Acc128 t0{0, 0}, t1{0, 0};
+                        t0.mac(s00, m1); t0.mac(s10, m2);
+                        t1.mac(s01, m1); t1.mac(s11, m2);
+                        s00 = redc128(t0, M8);
+                        s01 = redc128(t1, M8);
+                    }
+                    reinterpret_cast<u64*>(D)[k] = s00;
+                    reinterpret_cast<u64*>(D)[N + k] = s01;
+                }
+            }
+            else
             for (u32 k = threadIdx.x; k < N; k += blockDim.x) {
                 T s00 = 0, s01 = 0, s10 = 0, s11 = 0;
                 const u32 l0 = dm ? 1 : 0;  // rgsw-acc-dm.cpp:353,357: the DM sums start at l = 1
@@ -214,14 +318,24 @@ __global__ void __launch_bounds__(1024, 1) br_generic_kernel(GenArgs<T> A) {
                 D[N + k] = s01;
             }
             __syncthreads();
-            ntt_inv_smem<T>(D, 2, N, logN, A.t.tw_inv, M);
-            if (dm) {
-                for (u32 idx = threadIdx.x; idx < 2 * N; idx += blockDim.x)
-                    c[idx] = D[idx];
+            if constexpr (sizeof(T) == 8) {
+                ntt_inv_lazy64(reinterpret_cast<u64*>(D), 2, N, reinterpret_cast<const u64*>(A.t.sh_inv), Q);
+                for (u32 idx = threadIdx.x; idx < 2 * N; idx += blockDim.x) {   // D < 2Q
+                    u64 v = (u64)D[idx];
+                    v = v >= Q ? v - Q : v;
+                    c[idx] = dm ? (T)v : M.add(c[idx], (T)v);
+                }
             }
             else {
-                for (u32 idx = threadIdx.x; idx < 2 * N; idx += blockDim.x)
-                    c[idx] = M.add(c[idx], D[idx]);
+                ntt_inv_smem<T>(D, 2, N, logN, A.t.tw_inv, M);
+                if (dm) {
+                    for (u32 idx = threadIdx.x; idx < 2 * N; idx += blockDim.x)
+                        c[idx] = D[idx];
+                }
+                else {
+                    for (u32 idx = threadIdx.x; idx < 2 * N; idx += blockDim.x)
+                        c[idx] = M.add(c[idx], D[idx]);
+                }
             }
             __syncthreads();
         }

@@ -57,6 +57,8 @@ struct Dev {
     void* tw_fwd = nullptr;
     void* tw_inv = nullptr;
     void* psi_pow = nullptr;
+    void* sh_fwd = nullptr;
+    void* sh_inv = nullptr;
     u32* twA = nullptr;
     u32* twB = nullptr;
     void* ksk = nullptr;
@@ -192,6 +194,25 @@ static int build_tables(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M) {
     CUDA_TRY(cudaMemcpy(d.tw_fwd, fw.data(), N * sizeof(T), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d.tw_inv, iv.data(), N * sizeof(T), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d.psi_pow, pp.data(), 2 * N * sizeof(T), cudaMemcpyHostToDevice));
+    // plain twiddles + Shoup companions for the lazy 64-bit transform
+    {
+        std::vector<T> sf(2 * N), si(2 * N);
+        const int w = sizeof(T) * 8;
+        x = 1; xi = 1;
+        for (u64 k = 0; k < N; k++) {
+            u32 r = bitrev32((u32)k, h->logN);
+            sf[r] = (T)x;
+            sf[N + r] = (T)((((unsigned __int128)x) << w) / Q);
+            si[r] = (T)xi;
+            si[N + r] = (T)((((unsigned __int128)xi) << w) / Q);
+            x = h_mulmod(x, psi, Q);
+            xi = h_mulmod(xi, psii, Q);
+        }
+        CUDA_TRY(cudaMalloc(&d.sh_fwd, 2 * N * sizeof(T)));
+        CUDA_TRY(cudaMalloc(&d.sh_inv, 2 * N * sizeof(T)));
+        CUDA_TRY(cudaMemcpy(d.sh_fwd, sf.data(), 2 * N * sizeof(T), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.sh_inv, si.data(), 2 * N * sizeof(T), cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -349,7 +370,7 @@ static int free_dev(Dev& d) {
     cudaSetDevice(d.id);
     if (d.stream)
         cudaStreamSynchronize(d.stream);
-    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.twA, d.twB, d.ksk, d.ws.base};
+    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.twA, d.twB, d.ksk, d.ws.base};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -381,8 +402,8 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
         FAIL(TFHE_B200_ENOTSUP, "setup: ring dimension N must be a power of two in [16, 4096]");
     if (p.method != TFHE_B200_METHOD_GINX && p.method != TFHE_B200_METHOD_AP)
         FAIL(TFHE_B200_EINVAL, "setup: method must be AP (1) or GINX (2)");
-    if (p.Q >= (1ULL << 62) || !(p.Q & 1))
-        FAIL(TFHE_B200_ENOTSUP, "setup: Q must be an odd prime below 2^62");
+    if (p.Q >= (1ULL << 55) || !(p.Q & 1))
+        FAIL(TFHE_B200_ENOTSUP, "setup: Q must be an odd prime below 2^55 (lazy 128-bit accumulation bound)");
     if ((p.Q - 1) % (2ULL * p.N) != 0 || h_powmod(p.psi, p.N, p.Q) != p.Q - 1)
         FAIL(TFHE_B200_EINVAL, "setup: psi is not a primitive 2N-th root of unity mod Q");
     if (p.baseG == 0 || (p.baseG & (p.baseG - 1)) || p.digitsG <= p.numDigitsToThrow)
@@ -596,12 +617,14 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
         BRTables<u64> t;
         t.mod = h->m64; t.tw_fwd = (const u64*)d.tw_fwd; t.tw_inv = (const u64*)d.tw_inv;
         t.psi_pow = (const u64*)d.psi_pow; t.bk = (const u64*)d.bk_generic;
+        t.sh_fwd = (const u64*)d.sh_fwd; t.sh_inv = (const u64*)d.sh_inv;
         CUDA_TRY(launch_br_generic<u64>(c, t, d.stream, d.sm_count));
     }
     else {
         BRTables<u32> t;
         t.mod = h->m32; t.tw_fwd = (const u32*)d.tw_fwd; t.tw_inv = (const u32*)d.tw_inv;
         t.psi_pow = (const u32*)d.psi_pow; t.bk = (const u32*)d.bk_generic;
+        t.sh_fwd = (const u32*)d.sh_fwd; t.sh_inv = (const u32*)d.sh_inv;
         CUDA_TRY(launch_br_generic<u32>(c, t, d.stream, d.sm_count));
     }
     if (launches)

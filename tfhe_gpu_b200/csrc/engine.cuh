@@ -47,6 +47,8 @@ struct BRTables {
     const T* tw_fwd;   // [N] psi^bitrev(k) in Montgomery form
     const T* tw_inv;   // [N] psi^-bitrev(k) in Montgomery form
     const T* psi_pow;  // [2N] psi^x in Montgomery form (monomial factors)
+    const T* sh_fwd;   // [2][N] plain psi^bitrev(k) and its Shoup companion floor(w 2^w / Q)  (64-bit lazy NTT path)
+    const T* sh_inv;   // [2][N] same for psi^-bitrev(k)
     const T* bk;       // generic layout, Montgomery form, pre-multiplied by N^-1
 };
 
