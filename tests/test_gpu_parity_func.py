@@ -142,3 +142,26 @@ def test_mkmswitch_double_rounding_near_ties(keyset):
     exact = [((2 * int(v) * p.qKS + p.Q) // (2 * p.Q)) % p.qKS for v in ext[0]]
     dbl = [ks.port.round_qQ(int(v), p.qKS, p.Q) for v in ext[0]]
     assert exact != dbl      # the vectors really exercise the discrepancy
+
+
+@pytest.mark.parametrize("name", ["toy_func12", "toy_sign17", "toy_func12_throw1"])
+def test_u64_specialised_and_generic_kernels_agree(keyset, rng, name):
+    """br_cggi64 (register-resident, shuffle stage) vs br_generic<u64> on random inputs, ragged batch."""
+    ks = keyset(name)
+    p = ks.p
+    g = ks.gpu()
+    assert g.kernel_variant.startswith("cggi_u64")
+    ct = rng.integers(0, p.q, (5, p.n + 1), dtype=np.uint64)
+    tab = rng.integers(0, p.q, p.q, dtype=np.uint64)
+    a = g.BootstrapFunc(ct, p.q, tab, p.q)
+    g.set_option("force_generic", 1)
+    try:
+        b = g.BootstrapFunc(ct, p.q, tab, p.q)
+    finally:
+        g.set_option("force_generic", 0)
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, ks.port.bootstrap_func(ks.bk, ks.ksk, ct, p.q, tab, p.q))
+    # explicit-accumulator entry point (EvalAcc_CUDA contract) on the same kernel
+    acc = rng.integers(0, p.Q, (3, 2, p.N), dtype=np.uint64)
+    am = rng.integers(0, p.q, (3, p.n), dtype=np.uint64)
+    assert np.array_equal(g.EvalAcc(am, p.q, acc), ks.port.eval_acc(ks.bk, am, p.q, acc))

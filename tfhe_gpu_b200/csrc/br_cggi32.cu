@@ -398,10 +398,21 @@ bool cggi32_supported(const tfhe_b200_params& p) {
 bool cggi32_skip_top_ok(const tfhe_b200_params& p) {
     if (p.numDigitsToThrow != 0 || p.digitsG < 2)
         return false;
-    u64 B = p.baseG, m = p.Q >> 1;
-    for (u32 i = 1; i < p.digitsG; i++)
-        m = (m + B / 2 + B - 1) / B;   // upper bound of |d_i|
-    return m <= B / 2 - 1;
+    // Exact check: the digit extraction d -> floor((d + B/2) / B) is monotone, so the extreme top digits come from
+    // the extreme centred values d_max = QHalf - 1 and d_min = QHalf - Q (rgsw-acc.cpp:83).  The top digit is exact
+    // iff it lies in [-B/2, B/2 - 1] BEFORE the sign-extension truncates it.
+    const __int128 B = p.baseG, QH = p.Q >> 1;
+    __int128 ext[2] = {QH - 1, QH - (__int128)p.Q};
+    for (int e = 0; e < 2; e++) {
+        __int128 d = ext[e];
+        for (u32 i = 1; i < p.digitsG; i++) {
+            __int128 t = d + B / 2;                       // floor division for negative values
+            d = (t >= 0) ? t / B : -((-t + B - 1) / B);
+        }
+        if (d < -(B / 2) || d > B / 2 - 1)
+            return false;
+    }
+    return true;
 }
 
 static u32 bitrev_h(u32 x, u32 bits) {

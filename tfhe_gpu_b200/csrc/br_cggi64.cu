@@ -1,0 +1,538 @@
+// Specialised CGGI/GINX blind rotation for the 54-bit functional-bootstrapping parameter sets (N = 2048,
+// 2^31 <= Q < 2^55): EvalFunc / EvalFloor / EvalSign / EvalDecomp (BASELINE.json configs[3], [4]).
+//
+// Same design as br_cggi32.cu, in 64-bit words:
+//   * a CTA owns G ciphertexts that walk the n steps in lock-step and share the RGSW key words of the step;
+//   * each accumulator polynomial lives in coefficient form in registers: 64 threads x 32 coefficients (u64);
+//   * register-resident three-part NTT: pass A (strides 1024..64, twiddles identical in every thread -> kernel-parameter
+//     constant bank), one swizzled shared-memory transpose, the stride-32 stage done between neighbouring lanes with
+//     warp shuffles (each lane takes half of the butterflies), pass B (strides 16..1, per-thread twiddles read from a
+//     shared-memory table);
+//   * lazy Harvey/Shoup butterflies on 64-bit words (values < 24 Q < 2^59), inverse transform through the mirrored
+//     block so the forward twiddle table serves both directions;
+//   * pointwise stage accumulates in 128 bits with one Montgomery reduction per output;
+//   * closed-form signed digits, top-digit elimination when provably exact (cggi32_skip_top_ok; true for logQ = 12:
+//     2 forward + 2 inverse transforms per step instead of 4 + 2), fused accumulator init / extraction / transpose.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "engine.cuh"
+
+namespace tfhe_b200 {
+
+namespace {
+
+constexpr int LOGN = 11, N = 2048, TPN = 64, NTW = 31;
+
+struct CGGI64Args {
+    BRCommon c;
+    ModCtx<u64> mod;
+    const u64* bk;       // [i][x(2D planes)][slot][2]: word w = (key*D + l')*2 + j lives in plane w/2, lane w%2
+    const u64* psi_pow;  // [2N] Montgomery form (global memory)
+    const u64* twB;      // [NTW][TPN][2] per-thread pass-B twiddles (value, Shoup companion), already [x][T] order
+    const u64* tw32;     // [32][2] stride-32 stage twiddles: psi^bitrev(32 + u) and companion
+    u64 twA_f[32][2];    // uniform pass-A twiddles (value, companion), index (16>>s) + (r>>(s+1))
+    u64 twA_i[32][2];
+    u64 Q2, dig_off, dig_add, ninvM;
+    u32 zero;
+};
+
+__device__ __forceinline__ u64 shoup64(u64 y, u64 w, u64 wp, u64 Q) {
+    u64 q = __umul64hi(y, wp);
+    return y * w - q * Q;   // [0, 2Q) for any 64-bit y
+}
+__device__ __forceinline__ u64 csub(u64 x, u64 m) {
+    return x >= m ? x - m : x;
+}
+// u64 position -> physical u64 index inside a region: XOR the 16-byte chunk index with the owner block's low bits
+__device__ __forceinline__ u32 pos64(u32 p) {
+    return p ^ (((p >> 5) & 7) << 1);
+}
+__device__ __forceinline__ void group_sync(int id) {
+    asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ u64 shfl_xor64(u64 v) {
+    u32 lo = (u32)v, hi = (u32)(v >> 32);
+    lo = __shfl_xor_sync(0xffffffffu, lo, 1);
+    hi = __shfl_xor_sync(0xffffffffu, hi, 1);
+    return ((u64)hi << 32) | lo;
+}
+
+struct A128 {
+    u64 lo, hi;
+    __device__ __forceinline__ void mac(u64 x, u64 b) {
+        u64 pl = x * b, ph = __umul64hi(x, b);
+        lo += pl;
+        hi += ph + (lo < pl);
+    }
+};
+__device__ __forceinline__ u64 redc128(const A128& X, u64 Q, u64 qinv) {
+    u64 m = X.lo * qinv;
+    u64 t = __umul64hi(m, Q);
+    u64 r = X.hi - t;
+    return X.hi < t ? r + Q : r;
+}
+
+__device__ __forceinline__ void load_B(u64 (&v)[32], const u64* reg, int blk) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(reg) + 16 * blk;
+#pragma unroll
+    for (int x = 0; x < 16; x++) {
+        ulonglong2 w = p[x ^ (blk & 7)];
+        v[2 * x] = w.x;
+        v[2 * x + 1] = w.y;
+    }
+}
+__device__ __forceinline__ void store_B(const u64 (&v)[32], u64* reg, int blk) {
+    ulonglong2* p = reinterpret_cast<ulonglong2*>(reg) + 16 * blk;
+#pragma unroll
+    for (int x = 0; x < 16; x++)
+        p[x ^ (blk & 7)] = make_ulonglong2(v[2 * x], v[2 * x + 1]);
+}
+
+// ---- forward: pass A (uniform), stride-32 shuffle stage, pass B (per-thread) ------------------------------------------
+__device__ __forceinline__ void fwd_passA(u64 (&v)[32], const CGGI64Args& A, u64 Q, u64 Q2) {
+#pragma unroll
+    for (int s = 4; s >= 0; s--) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = (16 >> s) + (r >> (s + 1));
+            u64 t = shoup64(v[r + (1 << s)], A.twA_f[ti][0], A.twA_f[ti][1], Q);
+            u64 x = v[r];
+            v[r] = x + t;
+            v[r + (1 << s)] = x - t + Q2;
+        }
+    }
+}
+// stride 32: positions p (block 2u) and p + 32 (block 2u + 1) are held by neighbouring lanes.  Each lane computes half
+// of the 32 butterflies: the even lane those of its local slots 0..15, the odd lane those of its local slots 16..31.
+template <bool INV>
+__device__ __forceinline__ void stage32(u64 (&v)[32], bool odd_blk, u64 w, u64 wp, u64 Q, u64 Q2) {
+    // odd_blk: this lane holds the upper block (the "y" side) of the pair
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        const u64 lo = v[k], hi = v[16 + k];
+        const u64 send = odd_blk ? lo : hi;
+        const u64 own = odd_blk ? hi : lo;
+        const u64 recv = shfl_xor64(send);
+        const u64 x = odd_blk ? recv : own;
+        const u64 y = odd_blk ? own : recv;
+        u64 nx, ny;
+        if (!INV) {
+            u64 t = shoup64(y, w, wp, Q);
+            nx = x + t;
+            ny = x - t + Q2;
+        }
+        else {
+            // Gentleman-Sande with the mirrored (negated) forward twiddle: y' = (x - y) * (-w) = (y - x) * w
+            nx = csub(x + y, Q2);
+            ny = shoup64(y - x + Q2, w, wp, Q);
+        }
+        const u64 keep = odd_blk ? ny : nx;
+        const u64 ret = odd_blk ? nx : ny;
+        const u64 recv2 = shfl_xor64(ret);
+        v[k] = odd_blk ? recv2 : keep;
+        v[16 + k] = odd_blk ? keep : recv2;
+    }
+}
+__device__ __forceinline__ void fwd_passB(u64 (&v)[32], const ulonglong2* __restrict__ twS, int T, u64 Q, u64 Q2) {
+#pragma unroll
+    for (int s = 4; s >= 0; s--) {
+        const int off = (32 >> (s + 1)) - 1, cnt = 32 >> (s + 1);
+        ulonglong2 w[16];
+#pragma unroll
+        for (int x = 0; x < cnt; x++)
+            w[x] = twS[(off + x) * TPN + T];
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = r >> (s + 1);
+            u64 t = shoup64(v[r + (1 << s)], w[ti].x, w[ti].y, Q);
+            u64 x = v[r];
+            v[r] = x + t;
+            v[r + (1 << s)] = x - t + Q2;
+        }
+    }
+}
+// inverse pass B' on the mirrored block (thread T processes block 63 - T with its own forward twiddles, negated)
+__device__ __forceinline__ void inv_passB(u64 (&v)[32], const ulonglong2* __restrict__ twS, int T, u64 Q, u64 Q2) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int off = (32 >> (s + 1)) - 1, cnt = 32 >> (s + 1);
+        ulonglong2 w[16];
+#pragma unroll
+        for (int x = 0; x < cnt; x++)
+            w[x] = twS[(off + x) * TPN + T];
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = cnt - 1 - (r >> (s + 1));
+            u64 U = v[r], V = v[r + (1 << s)];
+            v[r] = csub(U + V, Q2);
+            v[r + (1 << s)] = shoup64(V - U + Q2, w[ti].x, w[ti].y, Q);
+        }
+    }
+}
+__device__ __forceinline__ void inv_passA(u64 (&v)[32], const CGGI64Args& A, u64 Q, u64 Q2) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = (16 >> s) + (r >> (s + 1));
+            u64 U = v[r], V = v[r + (1 << s)];
+            v[r] = csub(U + V, Q2);
+            v[r + (1 << s)] = shoup64(U - V + Q2, A.twA_i[ti][0], A.twA_i[ti][1], Q);
+        }
+    }
+}
+
+template <int DK, int G>
+struct K64 {
+    static constexpr int D = 2 * DK;
+    static constexpr int NT = G * 2 * TPN;
+    static constexpr size_t smem = (size_t)G * D * N * 8 + (size_t)NTW * TPN * 16 + 64;
+};
+
+template <int DK, int G, bool SKIP>
+__global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __grid_constant__ CGGI64Args A) {
+    using K = K64<DK, G>;
+    constexpr int D = K::D, NT = K::NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* Dsm = reinterpret_cast<u64*>(smem_raw);                                  // [G][D][N]
+    ulonglong2* twS = reinterpret_cast<ulonglong2*>(Dsm + (size_t)G * D * N);    // [NTW][TPN]
+
+    const BRCommon& C = A.c;
+    const u64 Q = A.mod.Q, Q2 = A.Q2, qinv = A.mod.qinv, oneM = A.mod.oneM;
+    const u32 n = C.n;
+    const int tid = threadIdx.x;
+    const int g = tid / (2 * TPN), j = (tid / TPN) & 1, T = tid % TPN;
+    const int bar_id = 1 + g * 2 + j;
+    const int ct = blockIdx.x * G + g;
+    const bool live = ct < C.batch;
+    const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
+
+    for (int x = tid; x < NTW * TPN; x += NT)
+        twS[x] = reinterpret_cast<const ulonglong2*>(A.twB)[x];
+    const u64 w32 = A.tw32[(T >> 1) * 2], w32p = A.tw32[(T >> 1) * 2 + 1];
+
+    // ---- accumulator initialisation in A layout (coefficient idx = T + 64 r) ------------------------------------
+    u64 c[32];
+    if (C.acc_init == ACC_EXPLICIT) {
+        const u64* src = C.acc_io + ((size_t)(live ? ct : 0) * 2 + j) * N;
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            c[r] = live ? src[T + TPN * r] : 0;
+    }
+    else {
+        const u32 q = (u32)C.ct_mod, b = (u32)(lwe[n] % q);
+        const u32 factor = (2 * N) / q, fshift = __ffs(factor) - 1;
+        const u32 q1 = (u32)C.gate_q1;
+        u32 q2 = q1 + (q >> 1);
+        if (q2 >= q)
+            q2 -= q;
+        const u64* tab = C.table + (C.acc_init == ACC_TABLE_PER ? (size_t)(live ? ct : 0) * q : 0);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const u32 idx = T + TPN * r;
+            u64 val = 0;
+            if (j == 1 && live && (idx & (factor - 1)) == 0) {
+                u32 jj = idx >> fshift;
+                u32 temp = b >= jj ? b - jj : b + q - jj;
+                if (C.acc_init == ACC_GATE) {
+                    bool in = (q1 < q2) ? ((temp >= q1) && (temp < q2)) : !((temp >= q2) && (temp < q1));
+                    val = in ? Q - C.Q8 : C.Q8;
+                }
+                else
+                    val = C.scale * tab[temp];
+            }
+            c[r] = val;
+        }
+    }
+    __syncthreads();
+
+    u64* myD = Dsm + (size_t)g * D * N;
+    const u64 QHalf = Q >> 1;
+    const u32 gBits = C.gBits;
+    const u64 gmask = ((u64)1 << gBits) - 1;
+    const bool odd_blk_f = T & 1;          // forward: lane holds block T
+    const bool odd_blk_i = !(T & 1);       // inverse: lane holds mirrored block 63 - T
+
+    // forward transform of v (A layout in) through region `reg`, result left in registers in B layout of block T
+    auto forward = [&](u64 (&v)[32], u64* reg) {
+        fwd_passA(v, A, Q, Q2);
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            reg[pos64(T + TPN * r)] = v[r];
+        group_sync(bar_id);
+        load_B(v, reg, T);
+        group_sync(bar_id);
+        stage32<false>(v, odd_blk_f, w32, w32p, Q, Q2);
+        fwd_passB(v, twS, T, Q, Q2);
+    };
+
+    if (SKIP) {
+        // evaluation-domain accumulator (scaled by N^-1), see br_cggi32.cu
+        u64 v[32];
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            v[r] = c[r];
+        u64* reg = myD + (size_t)(j + 2 * (DK - 1)) * N;
+        forward(v, reg);
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            v[r] = A.mod.mont_mul(v[r], A.ninvM);   // lazy (< 24 Q) * (N^-1 R) * R^-1 -> canonical
+        store_B(v, reg, T);
+        __syncthreads();
+    }
+
+    for (u32 i = 0; i < n; i++) {
+        // ---- phase 1 ---------------------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int l = 0; l < (SKIP ? DK - 1 : DK); l++) {
+            u64 v[32];
+            const u32 sh = gBits * (l + C.numThrow);
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                i64 dv = (c[r] < QHalf) ? (i64)c[r] : (i64)c[r] - (i64)Q;
+                u64 Dv = (u64)(dv + (i64)A.dig_off);
+                v[r] = ((u64)((i64)Dv >> sh) & gmask) + A.dig_add;
+            }
+            u64* reg = myD + (size_t)(j + 2 * l) * N;
+            forward(v, reg);
+            store_B(v, reg, T);
+        }
+        __syncthreads();
+
+        // ---- phase 2: pointwise stage -------------------------------------------------------------------------------
+        {
+            constexpr int ITERS = N / NT;
+            static_assert(N % NT == 0, "unsupported CTA shape");
+            constexpr int PL = 2 * D;   // uint4-sized planes per slot (4D u64 words)
+            const ulonglong2* bki = reinterpret_cast<const ulonglong2*>(A.bk) + (size_t)i * PL * N;
+            u64 ee[G];
+#pragma unroll
+            for (int gg = 0; gg < G; gg++) {
+                // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
+                const int cg = blockIdx.x * G + gg;
+                u64 e = 0;
+                if (cg < C.batch) {
+                    u64 ai = C.ct[(size_t)cg * (n + 1) + i] % C.ct_mod;
+                    e = ((C.ct_mod - ai) % C.ct_mod) * ((2 * N) / C.ct_mod);
+                }
+                ee[gg] = e;
+            }
+#pragma unroll 1
+            for (int it = 0; it < ITERS; it++) {
+                const int k = tid + it * NT;
+                u64 bkv[4 * D];
+#pragma unroll
+                for (int x = 0; x < PL; x++) {
+                    ulonglong2 w = bki[(size_t)x * N + k];
+                    bkv[2 * x] = w.x;
+                    bkv[2 * x + 1] = w.y;
+                }
+                const u32 pk = pos64(k);
+                const u32 br = __brev((u32)k) >> (32 - LOGN);
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
+                    u64* dreg = Dsm + (size_t)gg * D * N + pk;
+                    A128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+#pragma unroll
+                    for (int l = 0; l < D; l++) {
+                        const u64 x = dreg[(size_t)l * N];
+                        a00.mac(x, bkv[(0 * D + l) * 2 + 0]);
+                        a01.mac(x, bkv[(0 * D + l) * 2 + 1]);
+                        a10.mac(x, bkv[(1 * D + l) * 2 + 0]);
+                        a11.mac(x, bkv[(1 * D + l) * 2 + 1]);
+                    }
+                    const u64 s00 = redc128(a00, Q, qinv), s01 = redc128(a01, Q, qinv);
+                    const u64 s10 = redc128(a10, Q, qinv), s11 = redc128(a11, Q, qinv);
+                    const u32 xx = (u32)(((2 * br + 1) * ee[gg]) & (2 * N - 1));
+                    u64 m1 = __ldg(A.psi_pow + xx), m2 = __ldg(A.psi_pow + ((2 * N - xx) & (2 * N - 1)));
+                    m1 = m1 >= oneM ? m1 - oneM : m1 + Q - oneM;
+                    m2 = m2 >= oneM ? m2 - oneM : m2 + Q - oneM;
+                    A128 t0{0, 0}, t1{0, 0};
+                    t0.mac(s00, m1); t0.mac(s10, m2);
+                    t1.mac(s01, m1); t1.mac(s11, m2);
+                    const u64 dl0 = redc128(t0, Q, qinv), dl1 = redc128(t1, Q, qinv);
+                    dreg[0] = dl0;
+                    dreg[N] = dl1;
+                    if (SKIP) {
+                        u64* areg = dreg + (size_t)(2 * (DK - 1)) * N;
+                        areg[0] = csub(areg[0] + dl0, Q);
+                        areg[N] = csub(areg[N] + dl1, Q);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 3: inverse transform of delta_j through the mirrored block, accumulate -------------------------
+        {
+            u64 v[32];
+            u64* reg = myD + (size_t)j * N;
+            const int Tv = TPN - 1 - T;
+            load_B(v, reg, Tv);
+            inv_passB(v, twS, T, Q, Q2);
+            stage32<true>(v, odd_blk_i, w32, w32p, Q, Q2);
+            group_sync(bar_id);
+            store_B(v, reg, Tv);
+            group_sync(bar_id);
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                v[r] = reg[pos64(T + TPN * r)];
+            group_sync(bar_id);
+            inv_passA(v, A, Q, Q2);
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                c[r] = csub(csub(c[r] + v[r], Q2), Q);
+        }
+    }
+
+    if (live) {
+        if (C.write_acc) {
+            u64* dst = C.acc_io + (size_t)ct * 2 * N;
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const u32 idx = T + TPN * r;
+                if (j == 0) {
+                    u64 val = c[r];
+                    dst[idx == 0 ? 0 : N - idx] = (idx == 0 || val == 0) ? val : Q - val;
+                }
+                else
+                    dst[N + idx] = c[r];
+            }
+        }
+        if (C.ext) {
+            u64* dst = C.ext + (size_t)ct * (N + 1);
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const u32 idx = T + TPN * r;
+                if (j == 0) {
+                    u64 val = c[r];
+                    dst[idx == 0 ? 0 : N - idx] = (idx == 0 || val == 0) ? val : Q - val;
+                }
+                else if (idx == 0) {
+                    u64 val = c[r] + C.ext_add_b;
+                    dst[N] = val >= Q ? val - Q : val;
+                }
+            }
+        }
+    }
+}
+
+u32 bitrev_h(u32 x, u32 bits) {
+    u32 r = 0;
+    for (u32 i = 0; i < bits; i++) {
+        r = (r << 1) | (x & 1);
+        x >>= 1;
+    }
+    return r;
+}
+u64 shoup_h(u64 w, u64 Q) {
+    return (u64)((((unsigned __int128)w) << 64) / Q);
+}
+
+template <int DK, int G, bool SKIP>
+cudaError_t launch_t(const CGGI64Args& a, cudaStream_t s) {
+    using K = K64<DK, G>;
+    if (K::smem > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(br_cggi64_kernel<DK, G, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)K::smem);
+    if (e != cudaSuccess)
+        return e;
+    const int grid = (a.c.batch + G - 1) / G;
+    br_cggi64_kernel<DK, G, SKIP><<<grid, K::NT, K::smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool cggi64_supported(const tfhe_b200_params& p) {
+    if (p.method != TFHE_B200_METHOD_GINX || p.N != 2048)
+        return false;
+    if (p.Q < (1ULL << 31) || p.Q >= (1ULL << 55))
+        return false;
+    const u32 dk = p.digitsG - p.numDigitsToThrow;
+    return dk >= 1 && dk <= 4;
+}
+
+// twB: [NTW][TPN][2] (x-major, so the kernel copies it straight to shared memory); tw32: [32][2]; twA: [fwd|inv][32][2]
+void cggi64_build_tables(const tfhe_b200_params& p, std::vector<u64>& twA, std::vector<u64>& twB, std::vector<u64>& tw32) {
+    const u64 Q = p.Q;
+    std::vector<u64> W(N), WI(N);
+    u64 psi = p.psi % Q, psii = h_powmod(psi, Q - 2, Q), x = 1, xi = 1;
+    for (u32 k = 0; k < (u32)N; k++) {
+        u32 r = bitrev_h(k, LOGN);
+        W[r] = x;
+        WI[r] = xi;
+        x = h_mulmod(x, psi, Q);
+        xi = h_mulmod(xi, psii, Q);
+    }
+    twA.assign(2 * 32 * 2, 0);
+    for (u32 k = 1; k < 32; k++) {
+        twA[(0 * 32 + k) * 2 + 0] = W[k];
+        twA[(0 * 32 + k) * 2 + 1] = shoup_h(W[k], Q);
+        twA[(1 * 32 + k) * 2 + 0] = WI[k];
+        twA[(1 * 32 + k) * 2 + 1] = shoup_h(WI[k], Q);
+    }
+    tw32.assign(32 * 2, 0);
+    for (u32 u = 0; u < 32; u++) {
+        tw32[u * 2] = W[32 + u];
+        tw32[u * 2 + 1] = shoup_h(W[32 + u], Q);
+    }
+    twB.assign((size_t)NTW * TPN * 2, 0);
+    for (int s = 4; s >= 0; s--) {
+        const u32 cnt = 32 >> (s + 1), off = cnt - 1;
+        for (u32 T = 0; T < (u32)TPN; T++)
+            for (u32 xx = 0; xx < cnt; xx++) {
+                u64 w = W[(N >> (s + 1)) + T * cnt + xx];
+                twB[((size_t)(off + xx) * TPN + T) * 2 + 0] = w;
+                twB[((size_t)(off + xx) * TPN + T) * 2 + 1] = shoup_h(w, Q);
+            }
+    }
+}
+
+cudaError_t launch_br_cggi64(const BRCommon& c, const CGGI64Tables& t, cudaStream_t s, int group) {
+    CGGI64Args a;
+    a.c = c;
+    a.mod = t.mod;
+    a.bk = t.bk;
+    a.psi_pow = t.psi_pow;
+    a.twB = t.twB;
+    a.tw32 = t.tw32;
+    memcpy(a.twA_f, t.twA, sizeof(a.twA_f));
+    memcpy(a.twA_i, t.twA + 64, sizeof(a.twA_i));
+    a.Q2 = 2 * t.mod.Q;
+    const u64 B = 1ULL << c.gBits;
+    const u32 total_digits = c.digitsKept + c.numThrow;
+    unsigned __int128 off = 0, pw = 1;
+    for (u32 i = 0; i < total_digits; i++) {
+        off += (B / 2) * pw;
+        pw *= B;
+    }
+    a.dig_off = (u64)off;
+    a.dig_add = t.mod.Q - B / 2;
+    a.zero = 0;
+    a.ninvM = to_mont<u64>(h_powmod((u64)N, t.mod.Q - 2, t.mod.Q), t.mod);
+    const int dk = (int)c.digitsKept;
+    (void)group;
+    if (dk == 1)
+        return launch_t<1, 2, false>(a, s);
+    if (dk == 2)
+        return t.skip_top ? launch_t<2, 2, true>(a, s) : launch_t<2, 2, false>(a, s);
+    if (dk == 3)
+        return t.skip_top ? launch_t<3, 2, true>(a, s) : launch_t<3, 2, false>(a, s);
+    if (dk == 4)
+        return t.skip_top ? launch_t<4, 1, true>(a, s) : launch_t<4, 1, false>(a, s);
+    return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace tfhe_b200

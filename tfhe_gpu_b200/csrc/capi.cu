@@ -61,6 +61,9 @@ struct Dev {
     void* sh_inv = nullptr;
     u32* twA = nullptr;
     u32* twB = nullptr;
+    u64* bk_cggi64 = nullptr;
+    u64* twB64 = nullptr;
+    u64* tw32_64 = nullptr;
     void* ksk = nullptr;
     Arena ws;
 };
@@ -73,6 +76,8 @@ struct tfhe_b200_handle {
     bool have_cggi32 = false;
     bool skip_top = false;
     bool have_dm32 = false;
+    bool have_cggi64 = false;
+    std::vector<u64> twA64_host;
     int force_generic = 0;
     int group = 0;  // ciphertexts per CTA of the cggi32 kernel (0 = default)
     u32 logN = 0, d = 0, gBits = 0;
@@ -300,6 +305,32 @@ __global__ void bk_relayout_cggi32_kernel(u32* dst, const u32* src, u32 n, u32 d
     }
 }
 
+// 64-bit CGGI layout: destination [i][x(2d)][slot][2], word w = 2x + c = (key*d + l')*2 + j; optional top-digit transform
+__global__ void bk_relayout_cggi64_kernel(u64* dst, const u64* src, u32 n, u32 d, u32 N, ModCtx<u64> M, int skip,
+                                          const u64* cM) {
+    const size_t total = (size_t)n * N * 2 * d * 2;
+    const u32 top = d / 2 - 1;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        u32 c = r % 2; r /= 2;
+        u32 k = r % N; r /= N;
+        u32 x = r % (2 * d); r /= (2 * d);
+        u32 i = (u32)r;
+        u32 w = 2 * x + c;
+        u32 j = w % 2, lp = (w / 2) % d, key = w / (2 * d);
+        const size_t base = (((size_t)key * n + i) * d) * 2 * N;
+        u64 val = src[base + ((size_t)lp * 2 + j) * N + k];
+        if (skip) {
+            const u32 jin = lp & 1, l = lp >> 1;
+            const u64 vt = src[base + ((size_t)(jin + 2 * top) * 2 + j) * N + k];
+            const u64 t = M.mont_mul(vt, cM[l]);
+            val = (l == top) ? t : M.sub(val, t);
+        }
+        dst[idx] = val;
+    }
+}
+
 // AP/DM variant of the re-layout: source [row][l'(d)][j(2)][N] (row = (i*baseR + a0)*digitsR + k), destination
 // [row][x(d/2)][slot][4] with word w = l'*2 + j.  The DM accumulator drops row l' = 0 (rgsw-acc-dm.cpp:353,357) and the
 // kernel eliminates the top digit, so:  l < top: BK' = [l' >= 1] BK_l' - B^(l-top) BK_top(jin);  l = top: N B^-top BK_top.
@@ -351,6 +382,8 @@ extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
         return h->skip_top ? "cggi_u32_ntt32_skiptop" : "cggi_u32_ntt32";
     if (h->have_dm32 && !h->force_generic)
         return "dm_u32_ntt32_skiptop";
+    if (h->have_cggi64 && !h->force_generic)
+        return h->skip_top ? "cggi_u64_ntt32x64_skiptop" : "cggi_u64_ntt32x64";
     return h->variant.c_str();
 }
 extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value) {
@@ -370,7 +403,7 @@ static int free_dev(Dev& d) {
     cudaSetDevice(d.id);
     if (d.stream)
         cudaStreamSynchronize(d.stream);
-    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.twA, d.twB, d.ksk, d.ws.base};
+    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twA, d.twB, d.ksk, d.ws.base};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -445,8 +478,9 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
         h->m32 = make_modctx<u32>(p.Q);
     h->have_cggi32 = !h->is64 && cggi32_supported(p);
     // TFHE_B200_NO_SKIPTOP=1 (debug) keeps the untransformed keys and the full set of forward transforms
+    h->have_cggi64 = h->is64 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64");
     h->have_dm32 = !h->is64 && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
-    h->skip_top = h->have_cggi32 && cggi32_skip_top_ok(p) && !getenv("TFHE_B200_NO_SKIPTOP");
+    h->skip_top = (h->have_cggi32 || h->have_cggi64) && cggi32_skip_top_ok(p) && !getenv("TFHE_B200_NO_SKIPTOP");
     h->variant = h->is64 ? "generic_u64" : "generic_u32";
     if (p.method == TFHE_B200_METHOD_AP)
         h->variant += "_dm";
@@ -472,6 +506,14 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 cggi32_build_tables(p, h->twA_host, twB);
                 CUDA_TRY(cudaMalloc((void**)&d.twB, twB.size() * 4));
                 CUDA_TRY(cudaMemcpy(d.twB, twB.data(), twB.size() * 4, cudaMemcpyHostToDevice));
+            }
+            if (h->have_cggi64) {
+                std::vector<u64> twB, tw32;
+                cggi64_build_tables(p, h->twA64_host, twB, tw32);
+                CUDA_TRY(cudaMalloc((void**)&d.twB64, twB.size() * 8));
+                CUDA_TRY(cudaMalloc((void**)&d.tw32_64, tw32.size() * 8));
+                CUDA_TRY(cudaMemcpy(d.twB64, twB.data(), twB.size() * 8, cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(d.tw32_64, tw32.data(), tw32.size() * 8, cudaMemcpyHostToDevice));
             }
             return 0;
         };
@@ -509,6 +551,26 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 CUDA_TRY(cudaFree(dcM));
                 CUDA_TRY(cudaGetLastError());
                 CUDA_TRY(cudaStreamSynchronize(d0.stream));
+            }
+            if (h->have_cggi64) {
+                const u32 dk = h->d / 2, top = dk - 1;
+                std::vector<u64> cM(dk);
+                const u64 Binv = h_powmod(p.baseG % p.Q, p.Q - 2, p.Q);
+                for (u32 l = 0; l < dk; l++) {
+                    u64 cst = h_powmod(Binv, l == top ? top : top - l, p.Q);
+                    if (l == top)
+                        cst = h_mulmod(cst, p.N % p.Q, p.Q);
+                    cM[l] = to_mont<u64>(cst, h->m64);
+                }
+                u64* dcM = nullptr;
+                CUDA_TRY(cudaMalloc((void**)&dcM, dk * 8));
+                CUDA_TRY(cudaMemcpy(dcM, cM.data(), dk * 8, cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi64, h->bk_words * 8));
+                bk_relayout_cggi64_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi64, (const u64*)d0.bk_generic, p.n,
+                                                                          h->d, p.N, h->m64, h->skip_top ? 1 : 0, dcM);
+                CUDA_TRY(cudaGetLastError());
+                CUDA_TRY(cudaStreamSynchronize(d0.stream));
+                CUDA_TRY(cudaFree(dcM));
             }
             if (h->have_dm32) {
                 const u32 dk = h->d / 2, top = dk - 1;
@@ -549,6 +611,10 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 if (h->have_cggi32 || h->have_dm32) {
                     CUDA_TRY(cudaMalloc((void**)&d.bk_cggi32, h->bk_words * 4));
                     CUDA_TRY(cudaMemcpyPeerAsync(d.bk_cggi32, d.id, d0.bk_cggi32, d0.id, h->bk_words * 4, d.stream));
+                }
+                if (h->have_cggi64) {
+                    CUDA_TRY(cudaMalloc((void**)&d.bk_cggi64, h->bk_words * 8));
+                    CUDA_TRY(cudaMemcpyPeerAsync(d.bk_cggi64, d.id, d0.bk_cggi64, d0.id, h->bk_words * 8, d.stream));
                 }
                 CUDA_TRY(cudaMalloc(&d.ksk, ksk_bytes_total));
                 CUDA_TRY(cudaMemcpyPeerAsync(d.ksk, d.id, d0.ksk, d0.id, ksk_bytes_total, d.stream));
@@ -612,6 +678,12 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB;
         t.skip_top = true;
         CUDA_TRY(launch_br_dm32(c, t, d.stream));
+    }
+    else if (h->have_cggi64 && !h->force_generic) {
+        CGGI64Tables t;
+        t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twB = d.twB64; t.tw32 = d.tw32_64;
+        t.twA = h->twA64_host.data(); t.skip_top = h->skip_top;
+        CUDA_TRY(launch_br_cggi64(c, t, d.stream, h->group));
     }
     else if (h->is64) {
         BRTables<u64> t;

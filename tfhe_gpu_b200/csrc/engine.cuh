@@ -74,6 +74,20 @@ bool dm32_supported(const tfhe_b200_params& p);
 cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s);
 void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::vector<u32>& twB);
 
+// optimised CGGI kernel for the 54-bit sets, N = 2048 (br_cggi64.cu)
+struct CGGI64Tables {
+    ModCtx<u64> mod;
+    const u64* bk;        // [i][x(2D)][slot][2]
+    const u64* psi_pow;   // [2N] Montgomery form
+    const u64* twB;       // device [31][64][2]
+    const u64* tw32;      // device [32][2]
+    const u64* twA;       // HOST [fwd|inv][32][2]
+    bool skip_top;
+};
+bool cggi64_supported(const tfhe_b200_params& p);
+void cggi64_build_tables(const tfhe_b200_params& p, std::vector<u64>& twA, std::vector<u64>& twB, std::vector<u64>& tw32);
+cudaError_t launch_br_cggi64(const BRCommon& c, const CGGI64Tables& t, cudaStream_t s, int group);
+
 // LWE-side kernels (lwe_kernels.cu)
 struct KSArgs {
     u32 N, n, baseKS, dKS, row_stride;  // row_stride in entries (padded to 16 B)
