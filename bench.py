@@ -32,6 +32,8 @@ sys.path.insert(0, ROOT)
 # algorithmic work per STD128 CGGI bootstrap
 IMAD32_PER_BOOTSTRAP = 129.0e6          # 3 IMAD32 per modular multiplication, 42.99 M modmults
 KS_BYTES_PER_BOOTSTRAP = 2_101_248      # N*dKS*(n+1)*2 B gathered from the u16 key-switching table
+DRAM_TRAFFIC_PER_LAUNCH_16384 = 1.475e9 + 0.139e9      # br_cggi32 (profiles/r01_prof_cggi32_summary.md, r01c)
+KS_DRAM_TRAFFIC_PER_LAUNCH_16384 = 18.42e9 + 0.07e9    # mkmswitch (same file)
 IMAD_PEAK_FALLBACK = 18.5e12            # profiles/r01_imad_peak.json (sustained, power-capped), this pool's B200
 HBM_FALLBACK_GBS = 6650.0               # B200_PROFILING.md fallback
 
@@ -302,12 +304,16 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "imad", "kernel": "br_cggi32_kernel", "achieved": achieved_imad / 1e12,
                          "peak": imad_peak / 1e12, "unit": "TIMAD32/s", "frac": achieved_imad / imad_peak,
-                         "traffic": None, "peak_source": imad_src,
+                         "traffic": DRAM_TRAFFIC_PER_LAUNCH_16384 * batch / 16384 if args.gate == "NAND" else None,
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                           "16384-ciphertext launch (profiles/r01_prof_cggi32_summary.md), bytes",
+                         "peak_source": imad_src,
                          "algorithmic": f"{IMAD32_PER_BOOTSTRAP:.4g} IMAD32 per bootstrap x {batch} per launch",
                          "avg_launch_ms": br_s * 1e3, "share_of_step": br_ms / max(dev_ms, 1e-9)},
             "roofline_hbm": {"bound": "hbm", "kernel": "mkmswitch_kernel", "achieved": achieved_ks,
                              "peak": peaks.get("hbm_gbs", HBM_FALLBACK_GBS), "unit": "GB/s",
-                             "frac": achieved_ks / peaks.get("hbm_gbs", HBM_FALLBACK_GBS), "traffic": None,
+                             "frac": achieved_ks / peaks.get("hbm_gbs", HBM_FALLBACK_GBS),
+                             "traffic": KS_DRAM_TRAFFIC_PER_LAUNCH_16384 * batch / 16384,
                              "peak_source": f"MEASURED_PEAKS.json ({peaks_src})",
                              "algorithmic": f"{KS_BYTES_PER_BOOTSTRAP} gathered bytes per bootstrap x {batch}",
                              "avg_launch_ms": ks_s * 1e3, "share_of_step": ks_ms / max(dev_ms, 1e-9)},
