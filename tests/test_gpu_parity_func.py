@@ -165,3 +165,27 @@ def test_u64_specialised_and_generic_kernels_agree(keyset, rng, name):
     acc = rng.integers(0, p.Q, (3, 2, p.N), dtype=np.uint64)
     am = rng.integers(0, p.q, (3, p.n), dtype=np.uint64)
     assert np.array_equal(g.EvalAcc(am, p.q, acc), ks.port.eval_acc(ks.bk, am, p.q, acc))
+
+
+def test_functional_error_behaviour(keyset):
+    """Same preconditions as the reference's OPENFHE_THROWs (binfhe-base-scheme.cpp:682-686, 709-713, 1050-1054)."""
+    from tfhe_gpu_b200 import TfheB200Error
+
+    ks = keyset("toy_sign17")          # q = 2N = 4096: arbitrary LUTs are not allowed (q > N)
+    g = ks.gpu()
+    q, n = ks.p.q, ks.p.n
+    ct = np.zeros((2, n + 1), dtype=np.uint64)
+    arb = np.arange(q, dtype=np.uint64)
+    arb[0], arb[q // 2] = 1, 7
+    with pytest.raises(TfheB200Error, match="needs to be <= ring dimension"):
+        g.EvalFunc(ct, arb)
+    with pytest.raises(TfheB200Error, match="only for large precision"):
+        g.EvalDecomp(ct, q)
+    with pytest.raises(TfheB200Error, match="input vector is empty"):
+        g.EvalSign(np.zeros((0, n + 1), dtype=np.uint64), 1 << 17)
+    with pytest.raises(TfheB200Error, match="LUT length"):
+        g.EvalFunc(ct, arb[: q // 2])
+    with pytest.raises(TfheB200Error, match="number of rows"):
+        g.CiphertextMulMatrix(ct, np.ones((3, 2), dtype=np.int64), q)
+    with pytest.raises(TfheB200Error, match="unmatched with LUT size"):
+        g.EvalFunc(ct, np.stack([arb, arb, arb]))

@@ -515,14 +515,14 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     if (c.logN == LOGN && dk == DK && group == GG) return launch_t<LOGN, DK, GG>(a, s, t.skip_top);
     if (c.logN == 10) {
         if (group == 0) group = (dk <= 4) ? 4 : 2;
-        CASE(10, 4, 4) CASE(10, 4, 2) CASE(10, 4, 1)
-        CASE(10, 3, 4) CASE(10, 3, 2)
+        CASE(10, 4, 4) CASE(10, 4, 2)
+        CASE(10, 3, 4)
         CASE(10, 2, 4)
         CASE(10, 6, 2)
     }
     else if (c.logN == 9) {
         if (group == 0) group = (dk <= 4) ? 8 : 4;
-        CASE(9, 3, 8) CASE(9, 3, 4)
+        CASE(9, 3, 8)
         CASE(9, 2, 8)
         CASE(9, 4, 8)
         CASE(9, 6, 4)
