@@ -406,6 +406,48 @@ class Ref:
         self._chk(self.L.ref_key_switch(self.h, C.c_int(x.shape[0]), _p(x), _p(out)))
         return out
 
+    # ---- fused C++ adapter (tfhe_gpu_b200/adapter/binfhe_b200.hpp; only in the drop-in build) ----
+    def fused_create(self, num_gpus=1):
+        self.L.fused_create.restype = C.c_void_p
+        self.L.fused_create.argtypes = [C.c_void_p, C.c_int]
+        f = self.L.fused_create(self.h, num_gpus)
+        if not f:
+            raise RuntimeError(self.L.ref_last_error().decode())
+        self._fused = C.c_void_p(f)
+
+    def fused_destroy(self):
+        self.L.fused_destroy.argtypes = [C.c_void_p]
+        self.L.fused_destroy(self._fused)
+        self._fused = None
+
+    def fused_eval_bin_gate(self, gate, ct1, ct2, mod):
+        ct1, ct2 = _u64(ct1), _u64(ct2)
+        out = np.zeros_like(ct1)
+        self._chk(self.L.fused_eval_bin_gate(self.h, self._fused, C.c_int(gate), C.c_int(ct1.shape[0]), _p(ct1), _p(ct2),
+                                             C.c_uint64(mod), _p(out)))
+        return out
+
+    def fused_eval_func(self, ct, mod, lut):
+        ct, lut = _u64(ct), _u64(lut)
+        out = np.zeros_like(ct)
+        self._chk(self.L.fused_eval_func(self.h, self._fused, C.c_int(ct.shape[0]), _p(ct), C.c_uint64(mod), _p(lut),
+                                         C.c_uint64(lut.shape[0]), _p(out)))
+        return out
+
+    def fused_eval_sign(self, ct, mod):
+        ct = _u64(ct)
+        out = np.zeros_like(ct)
+        self._chk(self.L.fused_eval_sign(self.h, self._fused, C.c_int(ct.shape[0]), _p(ct), C.c_uint64(mod), _p(out)))
+        return out
+
+    def fused_eval_decomp(self, ct, mod, max_digits=8):
+        ct = _u64(ct)
+        out = np.zeros((ct.shape[0], max_digits, self.n + 1), dtype=np.uint64)
+        mods = np.zeros(max_digits, dtype=np.uint64)
+        nd = self._chk(self.L.fused_eval_decomp(self.h, self._fused, C.c_int(ct.shape[0]), _p(ct), C.c_uint64(mod),
+                                                C.c_int(max_digits), _p(out), _p(mods)))
+        return out[:, :nd].copy(), [int(m) for m in mods[:nd]]
+
     def gpu_setup(self, num_gpus=1):
         self._chk(self.L.ref_gpu_setup(self.h, C.c_int(num_gpus)))
 

@@ -15,6 +15,9 @@
 //
 // Ciphertext wire format everywhere: (n+1) u64 per ciphertext = a[0..n-1], b.  The modulus is passed beside it.
 #include "binfhecontext.h"
+#ifdef TFHE_B200_DROPIN
+#include "binfhe_b200.hpp"   // fused C++ adapter (only in the drop-in build, which links libtfhe_b200.so)
+#endif
 
 #include <omp.h>
 #include <cstring>
@@ -587,6 +590,64 @@ int ref_batched_mul_matrix(void* h, int in, int out_cols, const u64* ct, u64 mod
     return 0;
     REF_CATCH(-1)
 }
+
+#ifdef TFHE_B200_DROPIN
+// ---------------------------------------------------------------------------------------------------------
+// Fused C++ adapter (tfhe_gpu_b200/adapter/binfhe_b200.hpp) driven with the reference's own objects: keys come from
+// cc.GetRefreshKey()/GetSwitchKey(), inputs/outputs are std::vector<LWECiphertext>.
+// ---------------------------------------------------------------------------------------------------------
+void* fused_create(void* h, int num_gpus) {
+    REF_TRY
+    return new tfhe_b200::BatchedBinFHE(((RefCtx*)h)->cc, num_gpus);
+    REF_CATCH(nullptr)
+}
+void fused_destroy(void* f) {
+    delete (tfhe_b200::BatchedBinFHE*)f;
+}
+int fused_eval_bin_gate(void* h, void* f, int gate, int batch, const u64* ct1, const u64* ct2, u64 mod, u64* out) {
+    REF_TRY
+    uint32_t n = ((RefCtx*)h)->cc.GetParams()->GetLWEParams()->Getn();
+    auto r = ((tfhe_b200::BatchedBinFHE*)f)->EvalBinGate((BINGATE)gate, make_vec(ct1, batch, n, mod), make_vec(ct2, batch, n, mod));
+    put_vec(r, out, n);
+    return 0;
+    REF_CATCH(-1)
+}
+int fused_eval_func(void* h, void* f, int batch, const u64* ct, u64 mod, const u64* lut, u64 lut_len, u64* out) {
+    REF_TRY
+    uint32_t n = ((RefCtx*)h)->cc.GetParams()->GetLWEParams()->Getn();
+    std::vector<NativeInteger> LUT(lut_len);
+    for (u64 i = 0; i < lut_len; i++)
+        LUT[i] = NativeInteger(lut[i]);
+    auto r = ((tfhe_b200::BatchedBinFHE*)f)->EvalFunc(make_vec(ct, batch, n, mod), LUT);
+    put_vec(r, out, n);
+    return 0;
+    REF_CATCH(-1)
+}
+int fused_eval_sign(void* h, void* f, int batch, const u64* ct, u64 mod, u64* out) {
+    REF_TRY
+    uint32_t n = ((RefCtx*)h)->cc.GetParams()->GetLWEParams()->Getn();
+    auto r = ((tfhe_b200::BatchedBinFHE*)f)->EvalSign(make_vec(ct, batch, n, mod));
+    put_vec(r, out, n);
+    return 0;
+    REF_CATCH(-1)
+}
+int fused_eval_decomp(void* h, void* f, int batch, const u64* ct, u64 mod, int max_digits, u64* out, u64* out_mods) {
+    REF_TRY
+    uint32_t n = ((RefCtx*)h)->cc.GetParams()->GetLWEParams()->Getn();
+    auto r = ((tfhe_b200::BatchedBinFHE*)f)->EvalDecomp(make_vec(ct, batch, n, mod));
+    int nd = r.empty() ? 0 : (int)r[0].size();
+    if (nd > max_digits)
+        throw std::runtime_error("too many digits");
+    for (size_t s = 0; s < r.size(); s++)
+        for (int k = 0; k < nd; k++) {
+            put_ct(r[s][k], out + (s * max_digits + k) * (n + 1));
+            if (s == 0)
+                out_mods[k] = r[s][k]->GetModulus().ConvertToInt();
+        }
+    return nd;
+    REF_CATCH(-1)
+}
+#endif
 
 int ref_num_threads() {
     return omp_get_max_threads();

@@ -65,3 +65,40 @@ def test_reference_batched_sign_and_decomp_on_our_engine():
         assert am == bm and np.array_equal(a, b)
     finally:
         r.gpu_clean()
+
+
+def test_fused_cpp_adapter_on_reference_objects():
+    """tfhe_gpu_b200/adapter/binfhe_b200.hpp: the batched BinFHEContext surface on std::vector<LWECiphertext> through
+    the FUSED C-ABI calls, constructed from the reference's own context/keys; equal to the reference scalar CPU API."""
+    r = po.Ref.named(po.TOY, po.GINX, so=po.DROPIN_SO)
+    r.keygen()
+    r.fused_create(1)
+    try:
+        q = r.p.q
+        m1 = [i & 1 for i in range(10)]
+        m2 = [(i >> 1) & 1 for i in range(10)]
+        c1, c2 = r.encrypt_batch(m1, 4, q), r.encrypt_batch(m2, 4, q)
+        for g in ("NAND", "XNOR"):
+            assert np.array_equal(r.fused_eval_bin_gate(po.GATES[g], c1, c2, q),
+                                  r.eval_bin_gate(po.GATES[g], c1, c2, q)), g
+    finally:
+        r.fused_destroy()
+    r = po.Ref.func(po.TOY, False, 17, so=po.DROPIN_SO)
+    r.keygen()
+    r.fused_create(1)
+    try:
+        Qin, q = 1 << 17, r.p.q
+        P = Qin // q * (q // (2 * r.p.beta))
+        ct = r.encrypt_batch([P // 2 + i - 2 for i in range(4)], P, Qin)
+        assert np.array_equal(r.fused_eval_sign(ct, Qin), r.eval_sign(ct, Qin))
+        a, am = r.fused_eval_decomp(ct, Qin)
+        b, bm = r.eval_decomp(ct, Qin)
+        assert am == bm and np.array_equal(a, b)
+        # a periodic LUT through EvalFunc (q = 2N here, arbitrary LUTs are rejected like in the reference)
+        p = q // (2 * r.p.beta)
+        ct2 = r.encrypt_batch(list(range(p)), p, q)
+        per = np.array([((x // (q // p)) % (p // 2)) * (q // p) for x in range(q)], dtype=np.uint64)
+        per[q // 2:] = per[: q // 2]
+        assert np.array_equal(r.fused_eval_func(ct2, q, per), r.eval_func(ct2, q, per))
+    finally:
+        r.fused_destroy()
