@@ -427,15 +427,6 @@ static u32 shoup_h(u64 w, u64 Q) {
     return (u32)((w << 32) / Q);
 }
 
-size_t cggi32_twA_words() {
-    return 2 * 32 * 2;
-}
-size_t cggi32_twB_words(u32 N) {
-    const u32 logN = N == 512 ? 9 : 10;
-    const u32 PB = logN - 5, NTW = 32 - (32 >> PB);
-    return (size_t)(N / 32) * NTW * 2;
-}
-
 // twA: [fwd|inv][32][2] ; twB: [TPN][NTW][2]   (plain residues + Shoup companions, NOT Montgomery form)
 void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::vector<u32>& twB) {
     const u64 Q = p.Q, N = p.N;

@@ -32,8 +32,7 @@ struct CGGI64Args {
     const u64* psi_pow;  // [2N] Montgomery form (global memory)
     const u64* twB;      // [NTW][TPN][2] per-thread pass-B twiddles (value, Shoup companion), already [x][T] order
     const u64* tw32;     // [32][2] stride-32 stage twiddles: psi^bitrev(32 + u) and companion
-    u64 twA_f[32][2];    // uniform pass-A twiddles (value, companion), index (16>>s) + (r>>(s+1))
-    u64 twA_i[32][2];
+    const u64* twU;      // [2][31][2] uniform pass-A twiddles: forward W[e+1], then NEGATED inverse Q - WI[e+1]
     u64 Q2, dig_off, dig_add, ninvM;
     u32 zero;
 };
@@ -90,19 +89,50 @@ __device__ __forceinline__ void store_B(const u64 (&v)[32], u64* reg, int blk) {
         p[x ^ (blk & 7)] = make_ulonglong2(v[2 * x], v[2 * x + 1]);
 }
 
-// ---- forward: pass A (uniform), stride-32 shuffle stage, pass B (per-thread) ------------------------------------------
-__device__ __forceinline__ void fwd_passA(u64 (&v)[32], const CGGI64Args& A, u64 Q, u64 Q2) {
+// ---- five in-register stages on v[32] with twiddles (value, companion) read from a shared-memory table ------------
+// One body serves pass A (uniform twiddles: stride 0 table twU) and pass B (per-thread twiddles: twS[x][T]); it is
+// executed from a non-unrolled loop so the code exists once (the fully unrolled 64-bit transforms did not fit the
+// instruction cache: ncu showed `no_instruction` as the top stall).  Table entry e of a pass = twiddle (off(s) + x).
+__device__ __forceinline__ void fwd_pass5(u64 (&v)[32], const ulonglong2* __restrict__ tab, int stride, int lane_off,
+                                          u64 Q, u64 Q2) {
 #pragma unroll
     for (int s = 4; s >= 0; s--) {
+        const int off = (32 >> (s + 1)) - 1, cnt = 32 >> (s + 1);
+        ulonglong2 w[16];
+#pragma unroll
+        for (int x = 0; x < cnt; x++)
+            w[x] = tab[(off + x) * stride + lane_off];
 #pragma unroll
         for (int r = 0; r < 32; r++) {
             if (r & (1 << s))
                 continue;
-            const int ti = (16 >> s) + (r >> (s + 1));
-            u64 t = shoup64(v[r + (1 << s)], A.twA_f[ti][0], A.twA_f[ti][1], Q);
+            const int ti = r >> (s + 1);
+            u64 t = shoup64(v[r + (1 << s)], w[ti].x, w[ti].y, Q);
             u64 x = v[r];
             v[r] = x + t;
             v[r + (1 << s)] = x - t + Q2;
+        }
+    }
+}
+// Gentleman-Sande stages 2^s, s = 0..4, in the form v' = (V - U) * w: pass B' reads the FORWARD per-thread table
+// mirrored (psi^-bitrev(m+i) = -psi^bitrev(m + m-1-i)), pass A' reads a table of NEGATED inverse uniform twiddles.
+__device__ __forceinline__ void inv_pass5(u64 (&v)[32], const ulonglong2* __restrict__ tab, int stride, int lane_off,
+                                          bool mirror, u64 Q, u64 Q2) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int off = (32 >> (s + 1)) - 1, cnt = 32 >> (s + 1);
+        ulonglong2 w[16];
+#pragma unroll
+        for (int x = 0; x < cnt; x++)
+            w[x] = tab[(off + (mirror ? cnt - 1 - x : x)) * stride + lane_off];
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = r >> (s + 1);
+            u64 U = v[r], V = v[r + (1 << s)];
+            v[r] = csub(U + V, Q2);
+            v[r + (1 << s)] = shoup64(V - U + Q2, w[ti].x, w[ti].y, Q);
         }
     }
 }
@@ -137,66 +167,11 @@ __device__ __forceinline__ void stage32(u64 (&v)[32], bool odd_blk, u64 w, u64 w
         v[16 + k] = odd_blk ? keep : recv2;
     }
 }
-__device__ __forceinline__ void fwd_passB(u64 (&v)[32], const ulonglong2* __restrict__ twS, int T, u64 Q, u64 Q2) {
-#pragma unroll
-    for (int s = 4; s >= 0; s--) {
-        const int off = (32 >> (s + 1)) - 1, cnt = 32 >> (s + 1);
-        ulonglong2 w[16];
-#pragma unroll
-        for (int x = 0; x < cnt; x++)
-            w[x] = twS[(off + x) * TPN + T];
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (r & (1 << s))
-                continue;
-            const int ti = r >> (s + 1);
-            u64 t = shoup64(v[r + (1 << s)], w[ti].x, w[ti].y, Q);
-            u64 x = v[r];
-            v[r] = x + t;
-            v[r + (1 << s)] = x - t + Q2;
-        }
-    }
-}
-// inverse pass B' on the mirrored block (thread T processes block 63 - T with its own forward twiddles, negated)
-__device__ __forceinline__ void inv_passB(u64 (&v)[32], const ulonglong2* __restrict__ twS, int T, u64 Q, u64 Q2) {
-#pragma unroll
-    for (int s = 0; s < 5; s++) {
-        const int off = (32 >> (s + 1)) - 1, cnt = 32 >> (s + 1);
-        ulonglong2 w[16];
-#pragma unroll
-        for (int x = 0; x < cnt; x++)
-            w[x] = twS[(off + x) * TPN + T];
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (r & (1 << s))
-                continue;
-            const int ti = cnt - 1 - (r >> (s + 1));
-            u64 U = v[r], V = v[r + (1 << s)];
-            v[r] = csub(U + V, Q2);
-            v[r + (1 << s)] = shoup64(V - U + Q2, w[ti].x, w[ti].y, Q);
-        }
-    }
-}
-__device__ __forceinline__ void inv_passA(u64 (&v)[32], const CGGI64Args& A, u64 Q, u64 Q2) {
-#pragma unroll
-    for (int s = 0; s < 5; s++) {
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (r & (1 << s))
-                continue;
-            const int ti = (16 >> s) + (r >> (s + 1));
-            u64 U = v[r], V = v[r + (1 << s)];
-            v[r] = csub(U + V, Q2);
-            v[r + (1 << s)] = shoup64(U - V + Q2, A.twA_i[ti][0], A.twA_i[ti][1], Q);
-        }
-    }
-}
-
 template <int DK, int G>
 struct K64 {
     static constexpr int D = 2 * DK;
     static constexpr int NT = G * 2 * TPN;
-    static constexpr size_t smem = (size_t)G * D * N * 8 + (size_t)NTW * TPN * 16 + 64;
+    static constexpr size_t smem = (size_t)G * D * N * 8 + (size_t)NTW * TPN * 16 + 2 * NTW * 16 + 64;
 };
 
 template <int DK, int G, bool SKIP>
@@ -206,6 +181,8 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* Dsm = reinterpret_cast<u64*>(smem_raw);                                  // [G][D][N]
     ulonglong2* twS = reinterpret_cast<ulonglong2*>(Dsm + (size_t)G * D * N);    // [NTW][TPN]
+    ulonglong2* twUf = twS + NTW * TPN;                                           // [NTW] uniform forward
+    ulonglong2* twUi = twUf + NTW;                                                // [NTW] uniform inverse, negated
 
     const BRCommon& C = A.c;
     const u64 Q = A.mod.Q, Q2 = A.Q2, qinv = A.mod.qinv, oneM = A.mod.oneM;
@@ -219,6 +196,8 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
 
     for (int x = tid; x < NTW * TPN; x += NT)
         twS[x] = reinterpret_cast<const ulonglong2*>(A.twB)[x];
+    for (int x = tid; x < 2 * NTW; x += NT)
+        twUf[x] = reinterpret_cast<const ulonglong2*>(A.twU)[x];
     const u64 w32 = A.tw32[(T >> 1) * 2], w32p = A.tw32[(T >> 1) * 2 + 1];
 
     // ---- accumulator initialisation in A layout (coefficient idx = T + 64 r) ------------------------------------
@@ -265,15 +244,19 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
 
     // forward transform of v (A layout in) through region `reg`, result left in registers in B layout of block T
     auto forward = [&](u64 (&v)[32], u64* reg) {
-        fwd_passA(v, A, Q, Q2);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            fwd_pass5(v, pass ? twS : twUf, pass ? TPN : 1, pass ? T : 0, Q, Q2);
+            if (pass == 0) {
 #pragma unroll
-        for (int r = 0; r < 32; r++)
-            reg[pos64(T + TPN * r)] = v[r];
-        group_sync(bar_id);
-        load_B(v, reg, T);
-        group_sync(bar_id);
-        stage32<false>(v, odd_blk_f, w32, w32p, Q, Q2);
-        fwd_passB(v, twS, T, Q, Q2);
+                for (int r = 0; r < 32; r++)
+                    reg[pos64(T + TPN * r)] = v[r];
+                group_sync(bar_id);
+                load_B(v, reg, T);
+                group_sync(bar_id);
+                stage32<false>(v, odd_blk_f, w32, w32p, Q, Q2);
+            }
+        }
     };
 
     if (SKIP) {
@@ -379,16 +362,20 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
             u64* reg = myD + (size_t)j * N;
             const int Tv = TPN - 1 - T;
             load_B(v, reg, Tv);
-            inv_passB(v, twS, T, Q, Q2);
-            stage32<true>(v, odd_blk_i, w32, w32p, Q, Q2);
-            group_sync(bar_id);
-            store_B(v, reg, Tv);
-            group_sync(bar_id);
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                inv_pass5(v, pass ? twUi : twS, pass ? 1 : TPN, pass ? 0 : T, pass == 0, Q, Q2);
+                if (pass == 0) {
+                    stage32<true>(v, odd_blk_i, w32, w32p, Q, Q2);
+                    group_sync(bar_id);
+                    store_B(v, reg, Tv);
+                    group_sync(bar_id);
 #pragma unroll
-            for (int r = 0; r < 32; r++)
-                v[r] = reg[pos64(T + TPN * r)];
-            group_sync(bar_id);
-            inv_passA(v, A, Q, Q2);
+                    for (int r = 0; r < 32; r++)
+                        v[r] = reg[pos64(T + TPN * r)];
+                    group_sync(bar_id);
+                }
+            }
 #pragma unroll
             for (int r = 0; r < 32; r++)
                 c[r] = csub(csub(c[r] + v[r], Q2), Q);
@@ -476,12 +463,15 @@ void cggi64_build_tables(const tfhe_b200_params& p, std::vector<u64>& twA, std::
         x = h_mulmod(x, psi, Q);
         xi = h_mulmod(xi, psii, Q);
     }
-    twA.assign(2 * 32 * 2, 0);
-    for (u32 k = 1; k < 32; k++) {
-        twA[(0 * 32 + k) * 2 + 0] = W[k];
-        twA[(0 * 32 + k) * 2 + 1] = shoup_h(W[k], Q);
-        twA[(1 * 32 + k) * 2 + 0] = WI[k];
-        twA[(1 * 32 + k) * 2 + 1] = shoup_h(WI[k], Q);
+    // uniform tables, entry e <-> twiddle index e + 1 = (16 >> s) + x: forward W, then NEGATED inverse (pass A' uses
+    // the (V - U) * w form)
+    twA.assign(2 * NTW * 2, 0);
+    for (u32 e = 0; e < (u32)NTW; e++) {
+        twA[(0 * NTW + e) * 2 + 0] = W[e + 1];
+        twA[(0 * NTW + e) * 2 + 1] = shoup_h(W[e + 1], Q);
+        u64 neg = (Q - WI[e + 1]) % Q;
+        twA[(1 * NTW + e) * 2 + 0] = neg;
+        twA[(1 * NTW + e) * 2 + 1] = shoup_h(neg, Q);
     }
     tw32.assign(32 * 2, 0);
     for (u32 u = 0; u < 32; u++) {
@@ -508,8 +498,7 @@ cudaError_t launch_br_cggi64(const BRCommon& c, const CGGI64Tables& t, cudaStrea
     a.psi_pow = t.psi_pow;
     a.twB = t.twB;
     a.tw32 = t.tw32;
-    memcpy(a.twA_f, t.twA, sizeof(a.twA_f));
-    memcpy(a.twA_i, t.twA + 64, sizeof(a.twA_i));
+    a.twU = t.twA;
     a.Q2 = 2 * t.mod.Q;
     const u64 B = 1ULL << c.gBits;
     const u32 total_digits = c.digitsKept + c.numThrow;

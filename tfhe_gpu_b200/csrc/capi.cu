@@ -59,11 +59,11 @@ struct Dev {
     void* psi_pow = nullptr;
     void* sh_fwd = nullptr;
     void* sh_inv = nullptr;
-    u32* twA = nullptr;
     u32* twB = nullptr;
     u64* bk_cggi64 = nullptr;
     u64* twB64 = nullptr;
     u64* tw32_64 = nullptr;
+    u64* twU64 = nullptr;
     void* ksk = nullptr;
     Arena ws;
 };
@@ -403,7 +403,7 @@ static int free_dev(Dev& d) {
     cudaSetDevice(d.id);
     if (d.stream)
         cudaStreamSynchronize(d.stream);
-    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twA, d.twB, d.ksk, d.ws.base};
+    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twU64, d.twB, d.ksk, d.ws.base};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -514,6 +514,8 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 CUDA_TRY(cudaMalloc((void**)&d.tw32_64, tw32.size() * 8));
                 CUDA_TRY(cudaMemcpy(d.twB64, twB.data(), twB.size() * 8, cudaMemcpyHostToDevice));
                 CUDA_TRY(cudaMemcpy(d.tw32_64, tw32.data(), tw32.size() * 8, cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMalloc((void**)&d.twU64, h->twA64_host.size() * 8));
+                CUDA_TRY(cudaMemcpy(d.twU64, h->twA64_host.data(), h->twA64_host.size() * 8, cudaMemcpyHostToDevice));
             }
             return 0;
         };
@@ -682,7 +684,7 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
     else if (h->have_cggi64 && !h->force_generic) {
         CGGI64Tables t;
         t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twB = d.twB64; t.tw32 = d.tw32_64;
-        t.twA = h->twA64_host.data(); t.skip_top = h->skip_top;
+        t.twA = d.twU64; t.skip_top = h->skip_top;
         CUDA_TRY(launch_br_cggi64(c, t, d.stream, h->group));
     }
     else if (h->is64) {
@@ -733,18 +735,6 @@ static int bootstrap_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, 
         if (launches)                                                                                     \
             (*launches)++;                                                                                \
     } while (0)
-
-// upload a host-built table to the device arena
-static int put_table(Dev& d, const std::vector<u64>& t, u64** out) {
-    u64* p = arena_take<u64>(d, t.size());
-    if (!p)
-        FAIL(TFHE_B200_ENOMEM, "workspace too small for LUT");
-    CUDA_TRY(cudaMemcpyAsync(p, t.data(), t.size() * 8, cudaMemcpyHostToDevice, d.stream));
-    // the host vector may die before the async copy runs when it is pageable: make it synchronous
-    CUDA_TRY(cudaStreamSynchronize(d.stream));
-    *out = p;
-    return 0;
-}
 
 // binfhe-base-scheme.cpp:598-677
 static int gate_dev(tfhe_b200_handle* h, Dev& d, int gate, int batch, const u64* c1, const u64* c2, u64 q, u64* out,

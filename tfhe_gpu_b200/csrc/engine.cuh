@@ -68,8 +68,6 @@ struct CGGI32Tables {
 bool cggi32_supported(const tfhe_b200_params& p);
 bool cggi32_skip_top_ok(const tfhe_b200_params& p);
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group);
-size_t cggi32_twB_words(u32 N);
-size_t cggi32_twA_words();
 bool dm32_supported(const tfhe_b200_params& p);
 cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s);
 void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::vector<u32>& twB);
@@ -81,7 +79,7 @@ struct CGGI64Tables {
     const u64* psi_pow;   // [2N] Montgomery form
     const u64* twB;       // device [31][64][2]
     const u64* tw32;      // device [32][2]
-    const u64* twA;       // HOST [fwd|inv][32][2]
+    const u64* twA;       // device [fwd | negated inv][31][2] uniform pass-A twiddles
     bool skip_top;
 };
 bool cggi64_supported(const tfhe_b200_params& p);
@@ -116,8 +114,6 @@ cudaError_t launch_mul_matrix(u64* out, const u64* ct, const i64* M, int in, int
 // dst[perm(idx)] = to_mont(src[idx]) * Ninv ; layouts described in capi.cu
 template <typename T>
 cudaError_t launch_bk_convert_generic(T* dst, const u64* src, size_t count, ModCtx<T> mod, T ninvM2, cudaStream_t s);
-cudaError_t launch_bk_convert_cggi32(u32* dst, const u64* src, u32 n, u32 d, u32 N, u32 i0, u32 icount, ModCtx<u32> mod,
-                                     u32 ninvM2, cudaStream_t s);
 cudaError_t launch_ksk_convert(void* dst, int bytes, u32 row_stride, const u64* src, size_t rows, u32 words,
                                cudaStream_t s);
 

@@ -441,34 +441,6 @@ cudaError_t launch_bk_convert_generic(T* dst, const u64* src, size_t count, ModC
 template cudaError_t launch_bk_convert_generic<u32>(u32*, const u64*, size_t, ModCtx<u32>, u32, cudaStream_t);
 template cudaError_t launch_bk_convert_generic<u64>(u64*, const u64*, size_t, ModCtx<u64>, u64, cudaStream_t);
 
-// CGGI 32-bit layout: dst[i][k][key][l][j] (32-byte aligned groups per evaluation slot k) from the reference order
-// src[key][i][l][j][k]; src points at the slice for i in [i0, i0+icount) laid out as [key][icount][l][j][N].
-__global__ void bk_convert_cggi32_kernel(u32* dst, const u64* src, u32 d, u32 N, u32 icount, ModCtx<u32> mod,
-                                         u32 ninvM2) {
-    const size_t per_i = (size_t)2 * d * 2 * N;
-    const size_t total = per_i * icount;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        // idx enumerates the destination: [i][k][key][l][j]
-        size_t r = idx;
-        u32 j = r % 2; r /= 2;
-        u32 l = r % d; r /= d;
-        u32 key = r % 2; r /= 2;
-        u32 k = r % N; r /= N;
-        u32 i = (u32)r;
-        size_t sidx = ((((size_t)key * icount + i) * d + l) * 2 + j) * N + k;
-        dst[idx] = mod.mont_mul((u32)src[sidx], ninvM2);
-    }
-}
-
-cudaError_t launch_bk_convert_cggi32(u32* dst, const u64* src, u32 n, u32 d, u32 N, u32 i0, u32 icount, ModCtx<u32> mod,
-                                     u32 ninvM2, cudaStream_t s) {
-    (void)n;
-    (void)i0;
-    bk_convert_cggi32_kernel<<<148 * 8, 256, 0, s>>>(dst, src, d, N, icount, mod, ninvM2);
-    return cudaGetLastError();
-}
-
 // per-ciphertext LUT expansion for EvalFunc(vector, LUT_vec) (binfhe-base-scheme.cpp:791-924)
 //   mode 1 (periodic):  t[x] = x < q/2 ? L[x] : q - L[x - q/2]                       (tab_len = q)
 //   mode 2 (arbitrary): t[x] = x < dq/2 ? L[x mod q] : dq - L[(x - dq/2) mod q]        (tab_len = dq = 2q)
