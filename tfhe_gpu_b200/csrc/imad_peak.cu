@@ -81,6 +81,25 @@ __global__ void __launch_bounds__(256) k(unsigned* out, const unsigned* in, int 
                 asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x[i]), "r"(y[i]));
                 x[i] += (unsigned)w[i];
             }
+            else if (V == 18 || V == 19 || V == 20) {
+                // pipe-overlap probe: V18 = even warps integer butterflies / odd warps DFMA; V19 = butterflies only in
+                // even warps (odd idle); V20 = DFMA only in odd warps (even idle)
+                const bool int_warp = ((threadIdx.x >> 5) & 1) == 0;
+                if (int_warp && V != 20) {
+                    if ((i & 1) == 0) {
+                        unsigned q, t;
+                        asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(q) : "r"(x[i + 1]), "r"(z[i]));
+                        asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(t) : "r"(x[i + 1]), "r"(y[i]));
+                        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(t) : "r"(q), "r"(ua));
+                        unsigned u = x[i];
+                        asm volatile("add.u32 %0, %1, %2;" : "=r"(x[i]) : "r"(u), "r"(t));
+                        asm volatile("{ .reg .u32 tt; sub.u32 tt, %1, %2; add.u32 %0, tt, %3; }" : "=r"(x[i + 1]) : "r"(u), "r"(t), "r"(ub));
+                    }
+                }
+                else if (!int_warp && V != 19) {
+                    asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dx[i]) : "d"(dy), "d"(dz));
+                }
+            }
             else if (V == 14) { // 1 IMAD (R,R,R) + 1 IADD (R,R) interleaved
                 asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(y[i]), "r"(z[i]));
                 asm volatile("add.u32 %0, %0, %1;" : "+r"(z[(i + 3) % ILP]) : "r"(y[i]));
@@ -147,6 +166,9 @@ int main(int argc, char** argv) {
     rs.push_back(run<10>("lop3_rrr", ILP, 8));
     rs.push_back(run<11>("dfma", ILP, 8));
     rs.push_back(run<14>("imad_rrr+iadd", 2 * ILP, 8));
+    rs.push_back(run<18>("overlap_int_even_dfma_odd", 1, 8));
+    rs.push_back(run<19>("overlap_int_even_only", 1, 8));
+    rs.push_back(run<20>("overlap_dfma_odd_only", 1, 8));
     rs.push_back(run<15>("butterfly_widehi", 5 * (ILP / 2), 8));
     rs.push_back(run<15>("butterfly_widehi_occ2", 5 * (ILP / 2), 2));
     rs.push_back(run<16>("mac_mulwide_add64", ILP, 8));
@@ -156,7 +178,7 @@ int main(int argc, char** argv) {
     FILE* f = argc > 1 ? fopen(argv[1], "w") : stdout;
     fprintf(f, "{\"gpu\": \"%s\", \"sms\": %d, \"variants\": {", p.name, g_sms);
     for (size_t i = 0; i < rs.size(); i++)
-        fprintf(f, "%s\"%s\": {\"gops\": %.1f, \"per_sm_per_clk\": %.2f, \"ghz\": %.3f}", i ? ", " : "", rs[i].name, rs[i].gops, rs[i].per_sm_clk, rs[i].gops / (rs[i].per_sm_clk * g_sms));
+        fprintf(f, "%s\"%s\": {\"gops\": %.1f, \"per_sm_per_clk\": %.2f, \"ms\": %.3f}", i ? ", " : "", rs[i].name, rs[i].gops, rs[i].per_sm_clk, rs[i].ms);
     fprintf(f, "}}\n"); if (f != stdout) fclose(f);
     return 0;
 }
