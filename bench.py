@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--gate", default="NAND")
     ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the cpu_baseline sample (0 = 4 x cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own GPU path (comparison build)")
     return ap.parse_args()
 
 
@@ -101,6 +102,23 @@ def imad_peak_live():
         return d["variants"]["imad_rrr"]["gops"] * 1e9, "measured live (imad_peak, sustained, all-register IMAD)"
     except Exception as e:  # noqa: BLE001
         return IMAD_PEAK_FALLBACK, f"fallback (profiles/r01_imad_peak.json): {e}"
+
+
+def reference_gpu_arm(batch):
+    """The reference's OWN CUDA path (FFT kernels) on this box, when the comparison build exists
+    (oracle/Makefile `refgpu`: patched copy that dispatches its SM<900> templates on cc 10.0).  Runs in a subprocess
+    AFTER our engine has released the GPU; reported beside our numbers, never mixed into them."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libtfhe_ref_gpu.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libtfhe_ref_gpu.so not built (make -C oracle refgpu)"}
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_gpu_bench.py"), str(batch), "3"],
+                             capture_output=True, text=True, timeout=600).stdout
+        d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+        return {"value": d["gates_per_s"], "unit": "gates/s", "ms_per_ctx": d["ms_per_ctx"], "batch": d["batch"],
+                "decrypt_ok": d["decrypt_ok"], "kind": "reference GPU path (cuFFTDx FFT, SM<900> templates on sm_100)"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"reference GPU run failed: {e}"}
 
 
 def std128_keys():
@@ -321,6 +339,9 @@ def main():
         if not args.no_cpu_baseline:
             arm = CpuArm(po, p, port, bk, ksk, args.gate)
             _, line["cpu_baseline"] = arm.measure(args.cpu_sample or 8 * arm.cores)
+        ctx.GPUClean()
+        if not args.no_ref_gpu and world == 1:
+            line["reference_gpu"] = reference_gpu_arm(batch)
         print(json.dumps(line), flush=True)
     ctx.GPUClean()
     if world > 1:
