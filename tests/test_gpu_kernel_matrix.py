@@ -1,0 +1,92 @@
+"""Every template instantiation of the specialised kernels, on small custom rings (short LWE dimension, so the
+oracle is instant): N in {512, 1024} x digitsG in {2, 3, 4, 6} for br_cggi32 (with and without top-digit elimination,
+as the safety predicate decides), the AP/DM kernel, ragged batches, all-zero masks, gate and LUT accumulators, and
+the explicit-accumulator operator entry point.  Keys come from the oracle's deterministic key generator."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+Q27 = 134215681
+
+
+def _ctx(p, port, seed=5):
+    from tfhe_gpu_b200 import BinFHEContextB200
+
+    sk, bk, ksk = port.keygen(seed)
+    return sk, bk, ksk, BinFHEContextB200().GPUSetup(p.as_dict(), bk, ksk, numGPUs=1)
+
+
+@pytest.mark.parametrize("N", [512, 1024])
+@pytest.mark.parametrize("baseG", [1 << 14, 1 << 9, 1 << 7, 1 << 5])      # digitsG = 2, 3, 4, 6
+def test_cggi32_instantiations(N, baseG, rng):
+    p = po.Port.params_custom(12, N, N, Q27, 128, baseG, 32, po.GINX)       # q = N (so LUTs of every class are allowed)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant.startswith("cggi_u32_ntt32")
+        q, n = p.q, p.n
+        c1 = rng.integers(0, q, (11, n + 1), dtype=np.uint64)              # ragged vs every CTA group size
+        c2 = rng.integers(0, q, (11, n + 1), dtype=np.uint64)
+        c1[0, :n] = 0
+        c2[0, :n] = 0                                                      # all rotation exponents zero
+        for gate in ("NAND", "XNOR_FAST"):
+            want = port.eval_bin_gate(bk, ksk, po.GATES[gate], c1, c2, q)
+            assert np.array_equal(g.EvalBinGate(gate, c1, c2), want), gate
+        tab = rng.integers(0, q, (11, q), dtype=np.uint64)                 # per-ciphertext tables
+        want = port.bootstrap_func(bk, ksk, c1, q, tab, q)
+        assert np.array_equal(g.BootstrapFunc(c1, q, tab, q), want)
+        half = q // 2                                                      # smaller ciphertext modulus: factor 2N/q = 4
+        ch = c1 % half
+        th = rng.integers(0, half, half, dtype=np.uint64)
+        assert np.array_equal(g.BootstrapFunc(ch, half, th, q), port.bootstrap_func(bk, ksk, ch, half, th, q))
+        acc = rng.integers(0, p.Q, (3, 2, N), dtype=np.uint64)
+        am = rng.integers(0, q, (3, n), dtype=np.uint64)
+        assert np.array_equal(g.EvalAcc(am, q, acc), port.eval_acc(bk, am, q, acc))
+        # the generic kernel agrees as well
+        g.set_option("force_generic", 1)
+        assert np.array_equal(g.EvalBinGate("NAND", c1, c2), port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, q))
+    finally:
+        g.GPUClean()
+
+
+def test_dm32_small_ring(rng):
+    p = po.Port.params_custom(12, 1024, 1024, Q27, 128, 1 << 7, 32, po.AP)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant.startswith("dm_u32")
+        q, n = p.q, p.n
+        c1 = rng.integers(0, q, (7, n + 1), dtype=np.uint64)
+        c2 = rng.integers(0, q, (7, n + 1), dtype=np.uint64)
+        c1[1, :n] = 0
+        c2[1, :n] = 0
+        c1[2, :n] = 32                                                     # low refresh digit zero, high digit non-zero
+        c2[2, :n] = 0
+        want = port.eval_bin_gate(bk, ksk, po.GATES["NOR"], c1, c2, q)
+        assert np.array_equal(g.EvalBinGate("NOR", c1, c2), want)
+        acc = rng.integers(0, p.Q, (2, 2, 1024), dtype=np.uint64)
+        am = rng.integers(0, q, (2, n), dtype=np.uint64)
+        assert np.array_equal(g.EvalAcc(am, q, acc), port.eval_acc(bk, am, q, acc))
+    finally:
+        g.GPUClean()
+
+
+def test_top_digit_elimination_extreme_coefficients(rng):
+    """Accumulator coefficients at the edges of the centred range (0, 1, Q-1, QHalf-1, QHalf, QHalf+1): where a wrapping
+    top digit would break the elimination identity.  STD128-like gadget (B = 2^7, 4 digits: provably safe)."""
+    p = po.Port.params_custom(12, 1024, 1024, Q27, 128, 1 << 7, 32, po.GINX)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant.endswith("skiptop")
+        Q, QH = p.Q, p.Q >> 1
+        edge = np.array([0, 1, Q - 1, QH - 1, QH, QH + 1, QH - 64, QH + 64], dtype=np.uint64)
+        acc = np.resize(edge, (4, 2, 1024)).copy()
+        acc[1] = rng.integers(QH - 200, QH + 200, (2, 1024), dtype=np.uint64)
+        am = rng.integers(0, p.q, (4, p.n), dtype=np.uint64)
+        assert np.array_equal(g.EvalAcc(am, p.q, acc), port.eval_acc(bk, am, p.q, acc))
+    finally:
+        g.GPUClean()
