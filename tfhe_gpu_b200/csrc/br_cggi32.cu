@@ -245,51 +245,70 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                 }
                 const u32 pk = pos_of(k);
                 const u32 br = __brev((u32)k) >> (32 - LOGN);
+                // Ciphertexts are processed GB at a time: all shared-memory loads of the group first, then the
+                // arithmetic (independent streams the scheduler can interleave), then the stores.  Written per ciphertext
+                // the store of one and the loads of the next cannot be reordered (possible aliasing), which serialises the
+                // long multiply-accumulate / reduction chains (ncu: `wait` was half of this phase's samples).
+                constexpr int GB = (G % 2 == 0) ? 2 : 1;   // 4 at a time measured slower (register pressure)
+                auto redc_lazy = [&](u64 x) -> u32 {   // x < 2^63 -> < 2^31 + Q, congruent x R^-1 (mod Q)
+                    u32 lo = (u32)x, hi = (u32)(x >> 32);
+                    u32 t = mulhi_w(lo * qinv, Q);
+                    return hi - t + Q;
+                };
+                auto redc_full = [&](u64 x) -> u32 {   // x < Q * 2^32 -> [0, Q)
+                    u32 lo = (u32)x, hi = (u32)(x >> 32);
+                    u32 t = mulhi_w(lo * qinv, Q);
+                    u32 r = hi - t;
+                    return hi < t ? r + Q : r;
+                };
 #pragma unroll
-                for (int gg = 0; gg < G; gg++) {
-                    const u32* dreg = Dsm + (size_t)gg * D * RS + pk;
-                    u64 s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+                for (int g0 = 0; g0 < G; g0 += GB) {
+                    u32 xd[GB][D], m1[GB], m2[GB], dl0[GB], dl1[GB];
 #pragma unroll
-                    for (int l = 0; l < D; l++) {
-                        u32 x = dreg[(size_t)l * RS];
-                        s00 += (u64)x * bkv[(0 * D + l) * 2 + 0];
-                        s01 += (u64)x * bkv[(0 * D + l) * 2 + 1];
-                        s10 += (u64)x * bkv[(1 * D + l) * 2 + 0];
-                        s11 += (u64)x * bkv[(1 * D + l) * 2 + 1];
+                    for (int b = 0; b < GB; b++) {
+                        const u32* dreg = Dsm + (size_t)(g0 + b) * D * RS + pk;
+#pragma unroll
+                        for (int l = 0; l < D; l++)
+                            xd[b][l] = dreg[(size_t)l * RS];
+                        const u32 e = es[(g0 + b) * n + i];
+                        const u32 xx = ((2 * br + 1) * e) & (2 * N - 1);
+                        const u32 x2 = (2 * N - xx) & (2 * N - 1);
+                        // psi-power table is stored bit-rotated (low LOGN-3 bits <-> high 4 bits) so that the 16 distinct
+                        // exponents a warp touches (they differ by multiples of 2N/16) fall into distinct banks
+                        m1[b] = psiM[((xx & (2 * N / 16 - 1)) << 4) | (xx >> (LOGN + 1 - 4))];
+                        m2[b] = psiM[((x2 & (2 * N / 16 - 1)) << 4) | (x2 >> (LOGN + 1 - 4))];
                     }
-                    // lazy Montgomery reductions (inputs < 2^63): results < 2^31 + Q, congruent mod Q
-                    auto redc_lazy = [&](u64 x) -> u32 {
-                        u32 lo = (u32)x, hi = (u32)(x >> 32);
-                        u32 m = lo * qinv;
-                        u32 t = mulhi_w(m, Q);
-                        return hi - t + Q;
-                    };
-                    u32 r00 = redc_lazy(s00), r01 = redc_lazy(s01), r10 = redc_lazy(s10), r11 = redc_lazy(s11);
-                    const u32 e = es[gg * n + i];
-                    const u32 xx = ((2 * br + 1) * e) & (2 * N - 1);
-                    const u32 x2 = (2 * N - xx) & (2 * N - 1);
-                    // psi-power table is stored bit-rotated (low LOGN-3 bits <-> high 4 bits) so that the 16 distinct
-                    // exponents a warp touches (they differ by multiples of 2N/16) fall into distinct banks
-                    u32 m1 = psiM[((xx & (2 * N / 16 - 1)) << 4) | (xx >> (LOGN + 1 - 4))];
-                    u32 m2 = psiM[((x2 & (2 * N / 16 - 1)) << 4) | (x2 >> (LOGN + 1 - 4))];
-                    m1 = m1 >= oneM ? m1 - oneM : m1 + Q - oneM;
-                    m2 = m2 >= oneM ? m2 - oneM : m2 + Q - oneM;
-                    u64 t0 = (u64)r00 * m1 + (u64)r10 * m2;
-                    u64 t1 = (u64)r01 * m1 + (u64)r11 * m2;
-                    u32* wreg = Dsm + (size_t)gg * D * RS + pk;
-                    auto redc_full = [&](u64 x) -> u32 {   // x < Q * 2^32 -> [0, Q)
-                        u32 lo = (u32)x, hi = (u32)(x >> 32);
-                        u32 t = mulhi_w(lo * qinv, Q);
-                        u32 r = hi - t;
-                        return hi < t ? r + Q : r;
-                    };
-                    const u32 dl0 = redc_full(t0), dl1 = redc_full(t1);
-                    wreg[0] = dl0;
-                    wreg[RS] = dl1;
-                    if (SKIP) {   // acc_eval += delta (kept canonical)
-                        u32* areg = wreg + (size_t)(2 * (DK - 1)) * RS;
-                        areg[0] = cond_sub(areg[0] + dl0, Q);
-                        areg[RS] = cond_sub(areg[RS] + dl1, Q);
+#pragma unroll
+                    for (int b = 0; b < GB; b++) {
+                        u64 s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll
+                        for (int l = 0; l < D; l++) {
+                            const u32 x = xd[b][l];
+                            s00 += (u64)x * bkv[(0 * D + l) * 2 + 0];
+                            s01 += (u64)x * bkv[(0 * D + l) * 2 + 1];
+                            s10 += (u64)x * bkv[(1 * D + l) * 2 + 0];
+                            s11 += (u64)x * bkv[(1 * D + l) * 2 + 1];
+                        }
+                        const u32 r00 = redc_lazy(s00), r01 = redc_lazy(s01), r10 = redc_lazy(s10), r11 = redc_lazy(s11);
+                        u32 a1 = m1[b], a2 = m2[b];
+                        a1 = a1 >= oneM ? a1 - oneM : a1 + Q - oneM;
+                        a2 = a2 >= oneM ? a2 - oneM : a2 + Q - oneM;
+                        dl0[b] = redc_full((u64)r00 * a1 + (u64)r10 * a2);
+                        dl1[b] = redc_full((u64)r01 * a1 + (u64)r11 * a2);
+                        if (SKIP) {   // acc_eval += delta (kept canonical); its old value is the top row just loaded
+                            m1[b] = cond_sub(xd[b][2 * (DK - 1)] + dl0[b], Q);
+                            m2[b] = cond_sub(xd[b][2 * (DK - 1) + 1] + dl1[b], Q);
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < GB; b++) {
+                        u32* wreg = Dsm + (size_t)(g0 + b) * D * RS + pk;
+                        wreg[0] = dl0[b];
+                        wreg[RS] = dl1[b];
+                        if (SKIP) {
+                            wreg[(size_t)(2 * (DK - 1)) * RS] = m1[b];
+                            wreg[(size_t)(2 * (DK - 1) + 1) * RS] = m2[b];
+                        }
                     }
                 }
                 if (it + 1 < ITERS) {
