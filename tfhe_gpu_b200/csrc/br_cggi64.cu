@@ -322,13 +322,25 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
                 }
                 const u32 pk = pos64(k);
                 const u32 br = __brev((u32)k) >> (32 - LOGN);
+                // all shared-memory loads of the CTA's ciphertexts first, then the arithmetic (independent streams), then
+                // the stores: written per ciphertext, the store of one and the loads of the next cannot be reordered
+                u64 xd[G][D], m1[G], m2[G], dl0[G], dl1[G];
 #pragma unroll
                 for (int gg = 0; gg < G; gg++) {
-                    u64* dreg = Dsm + (size_t)gg * D * N + pk;
+                    const u64* dreg = Dsm + (size_t)gg * D * N + pk;
+#pragma unroll
+                    for (int l = 0; l < D; l++)
+                        xd[gg][l] = dreg[(size_t)l * N];
+                    const u32 xx = (u32)(((2 * br + 1) * ee[gg]) & (2 * N - 1));
+                    m1[gg] = __ldg(A.psi_pow + xx);
+                    m2[gg] = __ldg(A.psi_pow + ((2 * N - xx) & (2 * N - 1)));
+                }
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
                     A128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
 #pragma unroll
                     for (int l = 0; l < D; l++) {
-                        const u64 x = dreg[(size_t)l * N];
+                        const u64 x = xd[gg][l];
                         a00.mac(x, bkv[(0 * D + l) * 2 + 0]);
                         a01.mac(x, bkv[(0 * D + l) * 2 + 1]);
                         a10.mac(x, bkv[(1 * D + l) * 2 + 0]);
@@ -336,20 +348,27 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
                     }
                     const u64 s00 = redc128(a00, Q, qinv), s01 = redc128(a01, Q, qinv);
                     const u64 s10 = redc128(a10, Q, qinv), s11 = redc128(a11, Q, qinv);
-                    const u32 xx = (u32)(((2 * br + 1) * ee[gg]) & (2 * N - 1));
-                    u64 m1 = __ldg(A.psi_pow + xx), m2 = __ldg(A.psi_pow + ((2 * N - xx) & (2 * N - 1)));
-                    m1 = m1 >= oneM ? m1 - oneM : m1 + Q - oneM;
-                    m2 = m2 >= oneM ? m2 - oneM : m2 + Q - oneM;
+                    u64 f1 = m1[gg], f2 = m2[gg];
+                    f1 = f1 >= oneM ? f1 - oneM : f1 + Q - oneM;
+                    f2 = f2 >= oneM ? f2 - oneM : f2 + Q - oneM;
                     A128 t0{0, 0}, t1{0, 0};
-                    t0.mac(s00, m1); t0.mac(s10, m2);
-                    t1.mac(s01, m1); t1.mac(s11, m2);
-                    const u64 dl0 = redc128(t0, Q, qinv), dl1 = redc128(t1, Q, qinv);
-                    dreg[0] = dl0;
-                    dreg[N] = dl1;
+                    t0.mac(s00, f1); t0.mac(s10, f2);
+                    t1.mac(s01, f1); t1.mac(s11, f2);
+                    dl0[gg] = redc128(t0, Q, qinv);
+                    dl1[gg] = redc128(t1, Q, qinv);
                     if (SKIP) {
-                        u64* areg = dreg + (size_t)(2 * (DK - 1)) * N;
-                        areg[0] = csub(areg[0] + dl0, Q);
-                        areg[N] = csub(areg[N] + dl1, Q);
+                        m1[gg] = csub(xd[gg][2 * (DK - 1)] + dl0[gg], Q);
+                        m2[gg] = csub(xd[gg][2 * (DK - 1) + 1] + dl1[gg], Q);
+                    }
+                }
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
+                    u64* dreg = Dsm + (size_t)gg * D * N + pk;
+                    dreg[0] = dl0[gg];
+                    dreg[N] = dl1[gg];
+                    if (SKIP) {
+                        dreg[(size_t)(2 * (DK - 1)) * N] = m1[gg];
+                        dreg[(size_t)(2 * (DK - 1) + 1) * N] = m2[gg];
                     }
                 }
             }

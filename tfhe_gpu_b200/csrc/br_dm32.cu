@@ -203,15 +203,21 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
                         }
                     }
                 }
+                // loads of all active ciphertexts first, arithmetic, then stores (see br_cggi32.cu)
+                u32 xd[G][D], d0[G], d1[G];
 #pragma unroll
                 for (int gg = 0; gg < G; gg++) {
-                    if (rows[gg] < 0)
-                        continue;
-                    u32* dreg = Dsm + (size_t)gg * D * RS + pk;
+                    const u32* dreg = Dsm + (size_t)gg * D * RS + pk;
+#pragma unroll
+                    for (int l = 0; l < D; l++)
+                        xd[gg][l] = dreg[(size_t)l * RS];
+                }
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
                     u64 s0 = 0, s1 = 0;
 #pragma unroll
                     for (int l = 0; l < D; l++) {
-                        u32 x = dreg[(size_t)l * RS];
+                        const u32 x = xd[gg][l];
                         s0 += (u64)x * bkv[gg][l * 2 + 0];
                         s1 += (u64)x * bkv[gg][l * 2 + 1];
                     }
@@ -223,11 +229,18 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
                         r = cond_sub(r, 8 * Q); r = cond_sub(r, 4 * Q); r = cond_sub(r, Q2); r = cond_sub(r, Q);
                         return r;
                     };
-                    const u32 d0 = redc2(s0), d1 = redc2(s1);
-                    dreg[0] = d0;                                 // delta for the inverse transform (regions 0, 1)
-                    dreg[RS] = d1;
-                    dreg[(size_t)(2 * (DK - 1)) * RS] = d0;       // and the new evaluation-domain accumulator
-                    dreg[(size_t)(2 * (DK - 1) + 1) * RS] = d1;
+                    d0[gg] = redc2(s0);
+                    d1[gg] = redc2(s1);
+                }
+#pragma unroll
+                for (int gg = 0; gg < G; gg++) {
+                    if (rows[gg] < 0)
+                        continue;
+                    u32* dreg = Dsm + (size_t)gg * D * RS + pk;
+                    dreg[0] = d0[gg];                             // delta for the inverse transform (regions 0, 1)
+                    dreg[RS] = d1[gg];
+                    dreg[(size_t)(2 * (DK - 1)) * RS] = d0[gg];   // and the new evaluation-domain accumulator
+                    dreg[(size_t)(2 * (DK - 1) + 1) * RS] = d1[gg];
                 }
             }
         }
