@@ -90,3 +90,38 @@ def test_top_digit_elimination_extreme_coefficients(rng):
         assert np.array_equal(g.EvalAcc(am, p.q, acc), port.eval_acc(bk, am, p.q, acc))
     finally:
         g.GPUClean()
+
+
+Q54 = 18014398509404161
+
+
+@pytest.mark.parametrize("baseG", [1 << 27, 1 << 18, 1 << 14])            # digitsG = 2, 3, 4
+def test_cggi64_wrapped_top_digit_repair(baseG, rng):
+    """54-bit rings: for B^d = 2^54 the reference's truncated top digit wraps for centred values >= B^d/2 - B/2 - ...
+    (just below Q/2), so top-digit elimination needs the kernel's wrap repair.  Accumulators are built to hit it:
+    every coefficient in the wrap zone, a single wrapped coefficient, a random mix around the zone's lower edge."""
+    p = po.Port.params_custom(6, 2048, 4096, Q54, 64, baseG, 32, po.GINX)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant == "cggi_u64_ntt32x64_skiptop"
+        Q, QH, N = p.Q, p.Q >> 1, 2048
+        B, d = baseG, p.digitsG
+        off = sum((B // 2) * B**i for i in range(d))
+        lo = max(B**d - off, 0)                                            # smallest centred value that wraps
+        acc = rng.integers(0, Q, (7, 2, N), dtype=np.uint64)
+        if lo < QH:
+            acc[0] = rng.integers(lo, QH, (2, N), dtype=np.uint64)         # all wrapped
+            acc[1, 0, 777] = QH - 1                                        # exactly one wrapped coefficient
+            acc[1, 1, 0] = lo
+            acc[2] = rng.integers(lo - 1000, lo + 1000, (2, N), dtype=np.uint64)
+            acc[3, :, ::64] = QH - 5                                       # one warp's worth of bitmap words
+        edge = np.array([0, 1, Q - 1, QH - 1, QH, QH + 1, min(max(lo, 1) - 1, Q - 1), min(lo, Q - 1)], dtype=np.uint64)
+        acc[4] = np.resize(edge, (2, N))
+        am = rng.integers(0, p.q, (7, p.n), dtype=np.uint64)
+        want = port.eval_acc(bk, am, p.q, acc)
+        assert np.array_equal(g.EvalAcc(am, p.q, acc), want)
+        g.set_option("force_generic", 1)
+        assert np.array_equal(g.EvalAcc(am, p.q, acc), want)
+    finally:
+        g.GPUClean()

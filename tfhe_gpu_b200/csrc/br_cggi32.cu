@@ -434,6 +434,27 @@ bool cggi32_skip_top_ok(const tfhe_b200_params& p) {
     return true;
 }
 
+// Weaker condition used by the 64-bit kernel, which repairs wrapped top digits on the fly: the offset value
+// D = d + sum_i (B/2) B^i must stay in [0, 2 B^digits), so that the masked digits reproduce D mod B^digits and the only
+// possible discrepancy is c - sum_l d_l B^l = B^digits, flagged by bit digits*gBits of D.
+bool cggi_skip_top_wrapfix_ok(const tfhe_b200_params& p) {
+    if (p.numDigitsToThrow != 0 || p.digitsG < 2)
+        return false;
+    u32 gbits = 0;
+    while ((1ULL << gbits) < p.baseG)
+        gbits++;
+    if ((1ULL << gbits) != p.baseG || gbits * p.digitsG > 62)
+        return false;
+    const __int128 B = p.baseG, QH = p.Q >> 1;
+    __int128 off = 0, pw = 1;
+    for (u32 i = 0; i < p.digitsG; i++) {
+        off += (B / 2) * pw;
+        pw *= B;
+    }
+    const __int128 dmax = QH - 1, dmin = QH - (__int128)p.Q;
+    return dmin + off >= 0 && dmax + off < 2 * pw;
+}
+
 static u32 bitrev_h(u32 x, u32 bits) {
     u32 r = 0;
     for (u32 i = 0; i < bits; i++) {

@@ -11,8 +11,11 @@
 //   * lazy Harvey/Shoup butterflies on 64-bit words (values < 24 Q < 2^59), inverse transform through the mirrored
 //     block so the forward twiddle table serves both directions;
 //   * pointwise stage accumulates in 128 bits with one Montgomery reduction per output;
-//   * closed-form signed digits, top-digit elimination when provably exact (cggi32_skip_top_ok; true for logQ = 12:
-//     2 forward + 2 inverse transforms per step instead of 4 + 2), fused accumulator init / extraction / transpose.
+//   * closed-form signed digits; top-digit elimination (logQ = 12: 2 forward + 2 inverse transforms per step instead of
+//     4 + 2; logQ = 17: 4 + 2 instead of 6 + 2).  For these rings the reference's top digit CAN wrap (B^d/2 - B/2 < Q/2),
+//     so the kernel records the wrapped coefficients of a step and corrects the evaluation-domain accumulator for them
+//     (cggi_skip_top_wrapfix_ok, wrap_fix below) -- still bit-exact;
+//   * fused accumulator init / extraction / transpose.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -34,6 +37,7 @@ struct CGGI64Args {
     const u64* tw32;     // [32][2] stride-32 stage twiddles: psi^bitrev(32 + u) and companion
     const u64* twU;      // [2][31][2] uniform pass-A twiddles: forward W[e+1], then NEGATED inverse Q - WI[e+1]
     u64 Q2, dig_off, dig_add, ninvM;
+    u64 kfix;            // B^d / N mod Q (plain): weight of a wrapped top digit in the evaluation-domain accumulator
     u32 zero;
 };
 
@@ -171,7 +175,9 @@ template <int DK, int G>
 struct K64 {
     static constexpr int D = 2 * DK;
     static constexpr int NT = G * 2 * TPN;
-    static constexpr size_t smem = (size_t)G * D * N * 8 + (size_t)NTW * TPN * 16 + 2 * NTW * 16 + 64;
+    static constexpr int WB = N / 32;   // words of a wrapped-coefficient bitmap
+    static constexpr size_t smem = (size_t)G * D * N * 8 + (size_t)NTW * TPN * 16 + 2 * NTW * 16 + 64 +
+                                   2 * (size_t)G * 2 * (WB + 2) * 4;
 };
 
 template <int DK, int G, bool SKIP>
@@ -183,6 +189,10 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
     ulonglong2* twS = reinterpret_cast<ulonglong2*>(Dsm + (size_t)G * D * N);    // [NTW][TPN]
     ulonglong2* twUf = twS + NTW * TPN;                                           // [NTW] uniform forward
     ulonglong2* twUi = twUf + NTW;                                                // [NTW] uniform inverse, negated
+    // wrapped-top-digit bookkeeping (SKIP only), double-buffered by step parity: bitmaps [2][G][2][WB], warp flags
+    // [2][G][2][2]
+    u32* wbits = reinterpret_cast<u32*>(twUi + NTW);
+    u32* wany = wbits + 2 * G * 2 * K::WB;
 
     const BRCommon& C = A.c;
     const u64 Q = A.mod.Q, Q2 = A.Q2, qinv = A.mod.qinv, oneM = A.mod.oneM;
@@ -276,6 +286,34 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
 
     for (u32 i = 0; i < n; i++) {
         // ---- phase 1 ---------------------------------------------------------------------------------------------
+        if (SKIP) {
+            // Top-digit elimination assumes c = sum_l d_l B^l.  The reference's top digit is truncated to its gBits
+            // window, so for the few centred values above B^d/2 - B/2 it comes out B too small and
+            // c = sum_l d_l B^l + B^d.  Those coefficients are recorded here (bit DK*gBits of the offset value) and the
+            // pointwise stage corrects the evaluation-domain accumulator for them (wrap_fix below).
+            u32 wm = 0;
+            const u32 wsh = gBits * DK;
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                i64 dv = (c[r] < QHalf) ? (i64)c[r] : (i64)c[r] - (i64)Q;
+                u64 Dv = (u64)(dv + (i64)A.dig_off);
+                wm |= (u32)((Dv >> wsh) & 1) << r;
+            }
+            const bool anyw = __any_sync(0xffffffffu, wm != 0);
+            const int par = i & 1;
+            if (anyw) {
+                // coefficient index T + 64 r = 32 * (2 r + T / 32) + T % 32: a warp's ballot IS the bitmap word
+                u32* wb = wbits + ((size_t)(par * G + g) * 2 + j) * K::WB + (T >> 5);
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    u32 word = __ballot_sync(0xffffffffu, (wm >> r) & 1);
+                    if ((T & 31) == 0)
+                        wb[2 * r] = word;
+                }
+            }
+            if ((T & 31) == 0)
+                wany[((par * G + g) * 2 + j) * 2 + (T >> 5)] = anyw;
+        }
 #pragma unroll 1
         for (int l = 0; l < (SKIP ? DK - 1 : DK); l++) {
             u64 v[32];
@@ -293,6 +331,52 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
         __syncthreads();
 
         // ---- phase 2: pointwise stage -------------------------------------------------------------------------------
+        // rare path (about 1 ciphertext-step in 130 for logQ = 17, 1 in 65000 for logQ = 12): for every wrapped
+        // coefficient k0 of ciphertext gg / component jj, NTT(X^k0)[slot] = psi^((2 bitrev(slot) + 1) k0), so the
+        // top-row operand becomes acc_eval - (B^d / N) * sum_k0 psi^(...).  Applied in place before the stage and
+        // undone after it (the stage adds delta on top), all CTA-uniform.
+        bool anyflag = false;
+        if (SKIP) {
+            const u32* fl = wany + (size_t)(i & 1) * G * 4;
+            u32 f = 0;
+#pragma unroll
+            for (int x = 0; x < G * 4; x++)
+                f |= fl[x];
+            anyflag = f != 0;
+        }
+        auto wrap_fix = [&](bool undo) {
+            const u32* fl = wany + (size_t)(i & 1) * G * 4;
+#pragma unroll 1
+            for (int gj = 0; gj < G * 2; gj++) {
+                if (!(fl[gj * 2] | fl[gj * 2 + 1]))
+                    continue;
+                const u32* wb = wbits + ((size_t)(i & 1) * G * 2 + gj) * K::WB;
+                u64* reg = Dsm + (size_t)(gj >> 1) * D * N + (size_t)(2 * (DK - 1) + (gj & 1)) * N;
+#pragma unroll 1
+                for (int k = tid; k < N; k += NT) {
+                    const u32 br = __brev((u32)k) >> (32 - LOGN);
+                    u64 sum = 0;
+#pragma unroll 1
+                    for (int wd = 0; wd < K::WB; wd++) {
+                        if (!fl[gj * 2 + (wd & 1)])
+                            continue;
+                        u32 bits = wb[wd];
+                        while (bits) {
+                            const u32 k0 = 32 * wd + (__ffs(bits) - 1);
+                            bits &= bits - 1;
+                            sum = csub(sum + __ldg(A.psi_pow + (((2 * br + 1) * k0) & (2 * N - 1))), Q);
+                        }
+                    }
+                    const u64 term = A.mod.mont_mul(sum, A.kfix);
+                    const u64 x = reg[pos64(k)];
+                    reg[pos64(k)] = undo ? csub(x + term, Q) : (x >= term ? x - term : x + Q - term);
+                }
+            }
+        };
+        if (SKIP && anyflag) {
+            wrap_fix(false);
+            __syncthreads();
+        }
         {
             constexpr int ITERS = N / NT;
             static_assert(N % NT == 0, "unsupported CTA shape");
@@ -374,6 +458,8 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
             }
         }
         __syncthreads();
+        if (SKIP && anyflag)
+            wrap_fix(true);   // next read of the top rows is the next step's pointwise stage, two barriers away
 
         // ---- phase 3: inverse transform of delta_j through the mirrored block, accumulate -------------------------
         {
@@ -530,6 +616,7 @@ cudaError_t launch_br_cggi64(const BRCommon& c, const CGGI64Tables& t, cudaStrea
     a.dig_add = t.mod.Q - B / 2;
     a.zero = 0;
     a.ninvM = to_mont<u64>(h_powmod((u64)N, t.mod.Q - 2, t.mod.Q), t.mod);
+    a.kfix = h_mulmod((u64)(pw % t.mod.Q), h_powmod((u64)N, t.mod.Q - 2, t.mod.Q), t.mod.Q);
     const int dk = (int)c.digitsKept;
     (void)group;
     if (dk == 1)

@@ -480,7 +480,9 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
     // TFHE_B200_NO_SKIPTOP=1 (debug) keeps the untransformed keys and the full set of forward transforms
     h->have_cggi64 = h->is64 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64");
     h->have_dm32 = !h->is64 && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
-    h->skip_top = (h->have_cggi32 || h->have_cggi64) && cggi32_skip_top_ok(p) && !getenv("TFHE_B200_NO_SKIPTOP");
+    h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) ||
+                   (h->have_cggi64 && (cggi32_skip_top_ok(p) || cggi_skip_top_wrapfix_ok(p)))) &&
+                  !getenv("TFHE_B200_NO_SKIPTOP");
     h->variant = h->is64 ? "generic_u64" : "generic_u32";
     if (p.method == TFHE_B200_METHOD_AP)
         h->variant += "_dm";

@@ -67,6 +67,7 @@ struct CGGI32Tables {
 };
 bool cggi32_supported(const tfhe_b200_params& p);
 bool cggi32_skip_top_ok(const tfhe_b200_params& p);
+bool cggi_skip_top_wrapfix_ok(const tfhe_b200_params& p);   // top digit may wrap but the 64-bit kernel can repair it
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group);
 bool dm32_supported(const tfhe_b200_params& p);
 cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s);
