@@ -31,7 +31,8 @@ constexpr int LOGN = 11, N = 2048, TPN = 64, NTW = 31;
 struct CGGI64Args {
     BRCommon c;
     ModCtx<u64> mod;
-    const u64* bk;       // [i][x(2D planes)][slot][2]: word w = (key*D + l')*2 + j lives in plane w/2, lane w%2
+    const u64* bk;       // [i][x(2D planes)][slot][2]: word w = (key*D + l')*2 + j lives in plane w/2, lane w%2;
+                         // each word split into 27-bit limbs b0 | b1 << 32 (Montgomery form)
     const u64* psi_pow;  // [2N] Montgomery form (global memory)
     const u64* twB;      // [NTW][TPN][2] per-thread pass-B twiddles (value, Shoup companion), already [x][T] order
     const u64* tw32;     // [32][2] stride-32 stage twiddles: psi^bitrev(32 + u) and companion
@@ -76,6 +77,76 @@ __device__ __forceinline__ u64 redc128(const A128& X, u64 Q, u64 qinv) {
     u64 r = X.hi - t;
     return X.hi < t ? r + Q : r;
 }
+
+// 64 x 64 -> 128-bit multiply-accumulate in 27-bit limbs (Karatsuba): x = x0 + 2^27 x1 (x < 24 Q < 2^59: x1 < 2^32),
+// b = b0 + 2^27 b1 (b < Q < 2^55: b1 < 2^28).  Three IMAD.WIDE per term and NO carry handling: with at most 8 terms the
+// column sums s0 = sum x0 b0, s2 = sum x1 b1, kk = sum (x0 + x1)(b0 + b1) stay below 2^64 (checked on the host:
+// cggi64_supported).  Key words arrive pre-split as b0 | b1 << 32 (bk_relayout_cggi64_kernel).
+constexpr u32 M27 = (1u << 27) - 1;
+// explicit 32 x 32 (+ 64) -> 64: written as C, NVVM widens the operands to 64 bits and ptxas re-derives IMAD.WIDE with
+// leftover adds of zero high halves
+__device__ __forceinline__ u64 mulwide(u32 a, u32 b) {
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ u64 madwide(u32 a, u32 b, u64 c) {
+    u64 r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void unpack(u64 x, u32& lo, u32& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
+}
+struct Limb {
+    u32 l0, l1, ls;
+    __device__ __forceinline__ explicit Limb(u64 x) {
+        u32 lo, hi;
+        unpack(x, lo, hi);
+        l0 = lo & M27;
+        l1 = __funnelshift_r(lo, hi, 27);
+        ls = l0 + l1;
+    }
+};
+struct L3 {
+    u64 s0, s2, kk;
+    // first term (no zero-initialised accumulators)
+    __device__ __forceinline__ L3(const Limb& x, u64 bpacked) {
+        u32 b0, b1;
+        unpack(bpacked, b0, b1);
+        s0 = mulwide(x.l0, b0);
+        s2 = mulwide(x.l1, b1);
+        kk = mulwide(x.ls, b0 + b1);
+    }
+    __device__ __forceinline__ L3(const Limb& x, const Limb& b) {
+        s0 = mulwide(x.l0, b.l0);
+        s2 = mulwide(x.l1, b.l1);
+        kk = mulwide(x.ls, b.ls);
+    }
+    __device__ __forceinline__ void mac(const Limb& x, u64 bpacked) {
+        u32 b0, b1;
+        unpack(bpacked, b0, b1);
+        s0 = madwide(x.l0, b0, s0);
+        s2 = madwide(x.l1, b1, s2);
+        kk = madwide(x.ls, b0 + b1, kk);
+    }
+    __device__ __forceinline__ void mac(const Limb& x, const Limb& b) {
+        s0 = madwide(x.l0, b.l0, s0);
+        s2 = madwide(x.l1, b.l1, s2);
+        kk = madwide(x.ls, b.ls, kk);
+    }
+    // s0 + 2^27 (kk - s0 - s2) + 2^54 s2 as a 128-bit value
+    __device__ __forceinline__ A128 value() const {
+        const u64 s1 = kk - s0 - s2;
+        A128 r;
+        r.lo = s0 + (s1 << 27);
+        r.hi = (s1 >> 37) + (r.lo < s0);
+        const u64 t = s2 << 54;
+        r.lo += t;
+        r.hi += (s2 >> 10) + (r.lo < t);
+        return r;
+    }
+};
 
 __device__ __forceinline__ void load_B(u64 (&v)[32], const u64* reg, int blk) {
     const ulonglong2* p = reinterpret_cast<const ulonglong2*>(reg) + 16 * blk;
@@ -421,25 +492,28 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
                 }
 #pragma unroll
                 for (int gg = 0; gg < G; gg++) {
-                    A128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+                    const Limb x0(xd[gg][0]);
+                    L3 a00(x0, bkv[(0 * D) * 2 + 0]), a01(x0, bkv[(0 * D) * 2 + 1]);
+                    L3 a10(x0, bkv[(1 * D) * 2 + 0]), a11(x0, bkv[(1 * D) * 2 + 1]);
 #pragma unroll
-                    for (int l = 0; l < D; l++) {
-                        const u64 x = xd[gg][l];
+                    for (int l = 1; l < D; l++) {
+                        const Limb x(xd[gg][l]);
                         a00.mac(x, bkv[(0 * D + l) * 2 + 0]);
                         a01.mac(x, bkv[(0 * D + l) * 2 + 1]);
                         a10.mac(x, bkv[(1 * D + l) * 2 + 0]);
                         a11.mac(x, bkv[(1 * D + l) * 2 + 1]);
                     }
-                    const u64 s00 = redc128(a00, Q, qinv), s01 = redc128(a01, Q, qinv);
-                    const u64 s10 = redc128(a10, Q, qinv), s11 = redc128(a11, Q, qinv);
+                    const Limb s00(redc128(a00.value(), Q, qinv)), s01(redc128(a01.value(), Q, qinv));
+                    const Limb s10(redc128(a10.value(), Q, qinv)), s11(redc128(a11.value(), Q, qinv));
                     u64 f1 = m1[gg], f2 = m2[gg];
                     f1 = f1 >= oneM ? f1 - oneM : f1 + Q - oneM;
                     f2 = f2 >= oneM ? f2 - oneM : f2 + Q - oneM;
-                    A128 t0{0, 0}, t1{0, 0};
-                    t0.mac(s00, f1); t0.mac(s10, f2);
-                    t1.mac(s01, f1); t1.mac(s11, f2);
-                    dl0[gg] = redc128(t0, Q, qinv);
-                    dl1[gg] = redc128(t1, Q, qinv);
+                    const Limb F1(f1), F2(f2);
+                    L3 t0(s00, F1), t1(s01, F1);
+                    t0.mac(s10, F2);
+                    t1.mac(s11, F2);
+                    dl0[gg] = redc128(t0.value(), Q, qinv);
+                    dl1[gg] = redc128(t1.value(), Q, qinv);
                     if (SKIP) {
                         m1[gg] = csub(xd[gg][2 * (DK - 1)] + dl0[gg], Q);
                         m2[gg] = csub(xd[gg][2 * (DK - 1) + 1] + dl1[gg], Q);
@@ -550,7 +624,8 @@ cudaError_t launch_t(const CGGI64Args& a, cudaStream_t s) {
 bool cggi64_supported(const tfhe_b200_params& p) {
     if (p.method != TFHE_B200_METHOD_GINX || p.N != 2048)
         return false;
-    if (p.Q < (1ULL << 31) || p.Q >= (1ULL << 55))
+    // Q < 2^54: lazy transform outputs (< 24 Q) must split into 27-bit limbs with x1 + x0 < 2^32 (see L3)
+    if (p.Q < (1ULL << 31) || p.Q >= (1ULL << 54))
         return false;
     const u32 dk = p.digitsG - p.numDigitsToThrow;
     return dk >= 1 && dk <= 4;

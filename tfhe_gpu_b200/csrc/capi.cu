@@ -327,7 +327,7 @@ __global__ void bk_relayout_cggi64_kernel(u64* dst, const u64* src, u32 n, u32 d
             const u64 t = M.mont_mul(vt, cM[l]);
             val = (l == top) ? t : M.sub(val, t);
         }
-        dst[idx] = val;
+        dst[idx] = (val & ((1ULL << 27) - 1)) | ((val >> 27) << 32);   // 27-bit limbs for the kernel's Karatsuba MAC
     }
 }
 
