@@ -385,8 +385,26 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
             if ((T & 31) == 0)
                 wany[((par * G + g) * 2 + j) * 2 + (T >> 5)] = anyw;
         }
+        // With top-digit elimination the accumulator exists in evaluation form (top rows), and phase 3 inverse-transforms
+        // THAT (not the step's delta), so the coefficient-form copy c[] is only needed here, for the digits: it does not
+        // stay in registers through the transforms.  With more than one digit it is parked in row j (the scratch of the
+        // LAST digit processed, l = 0) and re-read per digit; every thread reads back only what it wrote itself.
+        constexpr int NF = SKIP ? DK - 1 : DK;
+        if (SKIP && NF > 1) {
+            u64* park = myD + (size_t)j * N;
+#pragma unroll
+            for (int r = 0; r < 32; r++)
+                park[pos64(T + TPN * r)] = c[r];
+        }
 #pragma unroll 1
-        for (int l = 0; l < (SKIP ? DK - 1 : DK); l++) {
+        for (int li = 0; li < NF; li++) {
+            const int l = SKIP ? NF - 1 - li : li;
+            if (SKIP && NF > 1) {
+                const u64* park = myD + (size_t)j * N;
+#pragma unroll
+                for (int r = 0; r < 32; r++)
+                    c[r] = park[pos64(T + TPN * r)];
+            }
             u64 v[32];
             const u32 sh = gBits * (l + C.numThrow);
 #pragma unroll
@@ -522,9 +540,11 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
 #pragma unroll
                 for (int gg = 0; gg < G; gg++) {
                     u64* dreg = Dsm + (size_t)gg * D * N + pk;
-                    dreg[0] = dl0[gg];
-                    dreg[N] = dl1[gg];
-                    if (SKIP) {
+                    if (!SKIP) {
+                        dreg[0] = dl0[gg];
+                        dreg[N] = dl1[gg];
+                    }
+                    else {
                         dreg[(size_t)(2 * (DK - 1)) * N] = m1[gg];
                         dreg[(size_t)(2 * (DK - 1) + 1) * N] = m2[gg];
                     }
@@ -532,15 +552,18 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
             }
         }
         __syncthreads();
-        if (SKIP && anyflag)
-            wrap_fix(true);   // next read of the top rows is the next step's pointwise stage, two barriers away
+        if (SKIP && anyflag) {
+            wrap_fix(true);
+            __syncthreads();   // phase 3 reads the top rows
+        }
 
         // ---- phase 3: inverse transform of delta_j through the mirrored block, accumulate -------------------------
+        // (SKIP: inverse transform of the whole evaluation-domain accumulator, read from the top row, through row j)
         {
             u64 v[32];
             u64* reg = myD + (size_t)j * N;
             const int Tv = TPN - 1 - T;
-            load_B(v, reg, Tv);
+            load_B(v, SKIP ? myD + (size_t)(j + 2 * (DK - 1)) * N : reg, Tv);
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
                 inv_pass5(v, pass ? twUi : twS, pass ? 1 : TPN, pass ? 0 : T, pass == 0, Q, Q2);
@@ -557,7 +580,7 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
             }
 #pragma unroll
             for (int r = 0; r < 32; r++)
-                c[r] = csub(csub(c[r] + v[r], Q2), Q);
+                c[r] = SKIP ? csub(v[r], Q) : csub(csub(c[r] + v[r], Q2), Q);   // v < 2Q
         }
     }
 
