@@ -189,3 +189,23 @@ def test_functional_error_behaviour(keyset):
         g.CiphertextMulMatrix(ct, np.ones((3, 2), dtype=np.int64), q)
     with pytest.raises(TfheB200Error, match="unmatched with LUT size"):
         g.EvalFunc(ct, np.stack([arb, arb, arb]))
+
+
+@pytest.mark.parametrize("modulus", [1 << 17, 1 << 12, 2, 3, 12289, (1 << 29) - 3, (1 << 31) - 1, 1 << 32, (1 << 32) + 15,
+                                     1 << 35])
+def test_ciphertext_mul_matrix_moduli(keyset, rng, modulus):
+    """Every arithmetic path of the product: power-of-two and odd moduli on the 32-bit register-tiled kernel (with and
+    without intermediate reductions), moduli above 2^29.5 / 2^32 on the exact 128-bit kernel; ragged tile shapes,
+    entries of both signs and beyond the modulus, operands not reduced on input."""
+    ks = keyset("toy_func12")
+    n = ks.p.n
+    rows, cols = 150, 70                                                   # not multiples of the 16 / 64 / 128 tiles
+    ct = rng.integers(0, 1 << 40, (rows, n + 1), dtype=np.uint64)          # NOT reduced
+    ct[0] = modulus - 1
+    M = rng.integers(-(1 << 40), 1 << 40, (rows, cols), dtype=np.int64)
+    M[:, 0] = modulus - 1
+    ct[:, 0] = modulus - 1                                                 # worst-case accumulation: rows * (m-1)^2
+    got = ks.gpu().CiphertextMulMatrix(ct, M, modulus)
+    ref = (ct.astype(object).T @ M.astype(object)) % int(modulus)
+    assert np.array_equal(got.astype(object), ref.T)
+    assert np.array_equal(got, ks.port.mul_matrix(ct, M, modulus))

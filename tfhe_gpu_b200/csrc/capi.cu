@@ -994,17 +994,19 @@ extern "C" int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, c
     const u32 W = p.n + 1;
     auto run = [&]() -> int {
         CUDA_TRY(cudaSetDevice(d.id));
-        int r = arena_reserve(d, ((size_t)in * W + (size_t)in * out_cols + (size_t)out_cols * W) * 8 + 4096);
+        const size_t scratch_bytes = mul_matrix_scratch_bytes(in, out_cols, W, modulus);
+        int r = arena_reserve(d, ((size_t)in * W + (size_t)in * out_cols + (size_t)out_cols * W) * 8 + scratch_bytes + 4096);
         if (r) return r;
         u64* dct = arena_take<u64>(d, (size_t)in * W);
         i64* dM = arena_take<i64>(d, (size_t)in * out_cols);
         u64* dout = arena_take<u64>(d, (size_t)out_cols * W);
+        void* scratch = scratch_bytes ? (void*)arena_take<u32>(d, scratch_bytes / 4) : nullptr;
         CUDA_TRY(cudaEventRecord(d.ev[0], d.stream));
         r = copy_in(d, d, dct, ct, (size_t)in * W * 8, space);
         if (r) return r;
         r = copy_in(d, d, dM, matrix, (size_t)in * out_cols * 8, space);
         if (r) return r;
-        CUDA_TRY(launch_mul_matrix(dout, dct, dM, in, out_cols, W, modulus, d.stream));
+        CUDA_TRY(launch_mul_matrix(dout, dct, dM, in, out_cols, W, modulus, scratch, d.stream));
         r = copy_out(d, d, out, dout, (size_t)out_cols * W * 8, space);
         if (r) return r;
         CUDA_TRY(cudaEventRecord(d.ev[5], d.stream));
@@ -1012,7 +1014,7 @@ extern "C" int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, c
         if (stats) {
             memset(stats, 0, sizeof(*stats));
             cudaEventElapsedTime(&stats->total_ms, d.ev[0], d.ev[5]);
-            stats->kernel_launches = 1;
+            stats->kernel_launches = scratch ? 2 : 1;
         }
         return 0;
     };

@@ -413,8 +413,110 @@ __global__ void mul_matrix_kernel(u64* out, const u64* ct, const i64* M, int in,
     }
 }
 
+// Fast path for moduli that fit 32 bits (every CiphertextMulMatrix the reference's own examples run: q = 2^10..2^17,
+// GEMM.cpp:70-88): operands are reduced once into u32 planes, then a register-tiled integer GEMM accumulates
+// 32 x 32 -> 64-bit products (IMAD.WIDE) in 64-bit registers.  A power-of-two modulus needs no intermediate reduction
+// (wrap-around mod 2^64 is compatible); any other modulus is reduced every `chunk` terms, chunk * (m-1)^2 + m <= 2^64.
+__global__ void mm_reduce_kernel(u32* dct, u32* dM, const u64* ct, const i64* M, size_t nct, size_t nM, u64 modulus) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < nct; x += stride)
+        dct[x] = (u32)(ct[x] % modulus);
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < nM; x += stride) {
+        i64 v = M[x] % (i64)modulus;
+        dM[x] = (u32)(v < 0 ? v + (i64)modulus : v);
+    }
+}
+
+constexpr int MM_TI = 64, MM_TW = 128, MM_TK = 16;   // CTA tile: 64 output rows x 128 ciphertext words, 16 terms a stage
+
+__global__ void __launch_bounds__(256) mul_matrix32_kernel(u64* out, const u32* ct, const u32* M, int in, int outc,
+                                                             u32 words, u64 modulus, int pow2, int chunk) {
+    __shared__ __align__(16) u32 sM[MM_TK][MM_TI];
+    __shared__ __align__(16) u32 sC[MM_TK][MM_TW];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int w0 = blockIdx.x * MM_TW, i0 = blockIdx.y * MM_TI;
+    u64 acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++)
+            acc[a][b] = 0;
+    int since = 0;
+    for (int k0 = 0; k0 < in; k0 += MM_TK) {
+        // stage the two tiles (rows k0..k0+15): 16 x 64 matrix words, 16 x 128 ciphertext words
+        for (int x = tid; x < MM_TK * MM_TI; x += 256) {
+            const int k = k0 + x / MM_TI, i = i0 + x % MM_TI;
+            sM[x / MM_TI][x % MM_TI] = (k < in && i < outc) ? M[(size_t)k * outc + i] : 0;
+        }
+        for (int x = tid; x < MM_TK * MM_TW; x += 256) {
+            const int k = k0 + x / MM_TW, w = w0 + x % MM_TW;
+            sC[x / MM_TW][x % MM_TW] = (k < in && w < (int)words) ? ct[(size_t)k * words + w] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < MM_TK; k++) {
+            const uint4 m4 = *reinterpret_cast<const uint4*>(&sM[k][ty * 4]);
+            const uint4 c0 = *reinterpret_cast<const uint4*>(&sC[k][tx * 4]);
+            const uint4 c1 = *reinterpret_cast<const uint4*>(&sC[k][64 + tx * 4]);
+            const u32 mv[4] = {m4.x, m4.y, m4.z, m4.w};
+            const u32 cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 8; b++)
+                    acc[a][b] += (u64)mv[a] * cv[b];
+        }
+        __syncthreads();
+        since += MM_TK;
+        if (!pow2 && since + MM_TK > chunk) {
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 8; b++)
+                    acc[a][b] %= modulus;
+            since = 2;   // the carried residue (< m) counts as at most two terms
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int i = i0 + ty * 4 + a;
+        if (i >= outc)
+            continue;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const int w = w0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + b - 4);
+            if (w < (int)words)
+                out[(size_t)i * words + w] = pow2 ? (acc[a][b] & (modulus - 1)) : (acc[a][b] % modulus);
+        }
+    }
+}
+
+size_t mul_matrix_scratch_bytes(int in, int outc, u32 words, u64 modulus) {
+    if (modulus > (1ULL << 32))
+        return 0;
+    return ((size_t)in * words + (size_t)in * outc) * 4 + 64;
+}
+
 cudaError_t launch_mul_matrix(u64* out, const u64* ct, const i64* M, int in, int outc, u32 words, u64 modulus,
-                              cudaStream_t s) {
+                              void* scratch, cudaStream_t s) {
+    const bool pow2 = (modulus & (modulus - 1)) == 0;
+    int chunk = 0;
+    bool fast = scratch && modulus <= (1ULL << 32);
+    if (fast && !pow2) {
+        const unsigned __int128 sq = (unsigned __int128)(modulus - 1) * (modulus - 1);
+        const unsigned __int128 c = ((((unsigned __int128)1) << 64) - modulus) / (sq ? sq : 1);
+        chunk = c > (unsigned __int128)(1 << 30) ? (1 << 30) : (int)c;
+        if (chunk < 2 * MM_TK + 1)
+            fast = false;   // modulus above ~2^29.5: reductions would dominate; exact 128-bit kernel below
+    }
+    if (fast) {
+        u32* dct = reinterpret_cast<u32*>(scratch);
+        u32* dM = dct + (((size_t)in * words + 3) & ~(size_t)3);
+        mm_reduce_kernel<<<148 * 4, 256, 0, s>>>(dct, dM, ct, M, (size_t)in * words, (size_t)in * outc, modulus);
+        dim3 grid((words + MM_TW - 1) / MM_TW, (outc + MM_TI - 1) / MM_TI);
+        mul_matrix32_kernel<<<grid, 256, 0, s>>>(out, dct, dM, in, outc, words, modulus, pow2 ? 1 : 0, chunk);
+        return cudaGetLastError();
+    }
     dim3 grid((words + 31) / 32, (outc + 31) / 32), block(32, 8);
     mul_matrix_kernel<<<grid, block, 0, s>>>(out, ct, M, in, outc, words, modulus);
     return cudaGetLastError();
