@@ -8,7 +8,8 @@
 //     constant bank), one swizzled shared-memory transpose, the stride-32 stage done between neighbouring lanes with
 //     warp shuffles (each lane takes half of the butterflies), pass B (strides 16..1, per-thread twiddles read from a
 //     shared-memory table);
-//   * lazy Harvey/Shoup butterflies on 64-bit words (values < 24 Q < 2^59), inverse transform through the mirrored
+//   * lazy Harvey/Shoup butterflies on 64-bit words with an approximate quotient (shoup64; values < 45 Q < 2^60, one
+//     conditional subtraction at the end of the forward transform), inverse transform through the mirrored
 //     block so the forward twiddle table serves both directions;
 //   * pointwise stage accumulates in 128 bits with one Montgomery reduction per output;
 //   * closed-form signed digits; top-digit elimination (logQ = 12: 2 forward + 2 inverse transforms per step instead of
@@ -38,13 +39,55 @@ struct CGGI64Args {
     const u64* tw32;     // [32][2] stride-32 stage twiddles: psi^bitrev(32 + u) and companion
     const u64* twU;      // [2][31][2] uniform pass-A twiddles: forward W[e+1], then NEGATED inverse Q - WI[e+1]
     u64 Q2, dig_off, dig_add, ninvM;
+    u64 zero64;          // runtime 0 (see shoup64)
     u64 kfix;            // B^d / N mod Q (plain): weight of a wrapped top digit in the evaluation-domain accumulator
     u32 zero;
 };
 
-__device__ __forceinline__ u64 shoup64(u64 y, u64 w, u64 wp, u64 Q) {
-    u64 q = __umul64hi(y, wp);
-    return y * w - q * Q;   // [0, 2Q) for any 64-bit y
+// explicit 32 x 32 (+ 64) -> 64: written as C, NVVM widens the operands to 64 bits and ptxas re-derives IMAD.WIDE with
+// leftover adds of zero high halves
+__device__ __forceinline__ u64 mulwide(u32 a, u32 b) {
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ u64 madwide(u32 a, u32 b, u64 c) {
+    u64 r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ void unpack(u64 x, u32& lo, u32& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
+}
+__device__ __forceinline__ u64 pack(u32 lo, u32 hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+// Shoup multiplication y * w mod Q with an APPROXIMATE quotient, in explicit 32-bit pieces (14 multiplier-pipe issue
+// slots instead of the 16 + carry adds of __umul64hi + two 64-bit low products):
+//   q' = y1 p1 + hi32(y1 p0) + hi32(y0 p1)  in [q - 2, q],  q = floor(y wp / 2^64), wp = floor(w 2^64 / Q)
+//   t  = y w - q' Q (mod 2^64) = lo64(y0 w0 + q0 nQ0) + 2^32 (y0 w1 + y1 w0 + q0 nQ1 + q1 nQ0),   nQ = 2^64 - Q
+// For y < 2^60: t < (1 + 2^-4) Q + 2 Q < 3.07 Q, so lazy values use an offset of 4Q (QO) where the exact form used 2Q.
+// Z is a runtime 64-bit 0: it turns two-input adds into three-input IADD3 / IADD3.X (ALU pipe) where ptxas would
+// otherwise pick IMAD.IADD / IMAD.X / IMAD.MOV on the multiplier pipe, which is the one this kernel saturates.
+__device__ __forceinline__ u64 shoup64(u64 y, u64 w, u64 wp, u64 nQ, u64 Z) {
+    u32 y0, y1, w0, w1, p0, p1, nq0, nq1, a0, a1, b0, b1, q0, q1, l0, l1, z0, z1;
+    unpack(y, y0, y1);
+    unpack(w, w0, w1);
+    unpack(wp, p0, p1);
+    unpack(nQ, nq0, nq1);
+    unpack(Z, z0, z1);
+    unpack(mulwide(y1, p0), a0, a1);
+    unpack(mulwide(y0, p1), b0, b1);
+    // the runtime-zero addend keeps ptxas from folding one of the 32-bit terms into the multiply-add as a 64-bit
+    // register pair (two IMAD.MOVs); the two terms then go through one three-input IADD3 / IADD3.X pair
+    const u64 q = madwide(y1, p1, Z) + (u64)a1 + (u64)b1;
+    unpack(q, q0, q1);
+    const u32 hy = y0 * w1 + y1 * w0;
+    unpack(madwide(q0, nq0, mulwide(y0, w0)), l0, l1);
+    const u32 h = q1 * nq0 + (q0 * nq1 + hy);
+    return pack(l0, l1 + h + z0);
 }
 __device__ __forceinline__ u64 csub(u64 x, u64 m) {
     return x >= m ? x - m : x;
@@ -78,26 +121,11 @@ __device__ __forceinline__ u64 redc128(const A128& X, u64 Q, u64 qinv) {
     return X.hi < t ? r + Q : r;
 }
 
-// 64 x 64 -> 128-bit multiply-accumulate in 27-bit limbs (Karatsuba): x = x0 + 2^27 x1 (x < 24 Q < 2^59: x1 < 2^32),
+// 64 x 64 -> 128-bit multiply-accumulate in 27-bit limbs (Karatsuba): x = x0 + 2^27 x1 (x < 29 Q < 2^59: x1 < 2^32),
 // b = b0 + 2^27 b1 (b < Q < 2^55: b1 < 2^28).  Three IMAD.WIDE per term and NO carry handling: with at most 8 terms the
 // column sums s0 = sum x0 b0, s2 = sum x1 b1, kk = sum (x0 + x1)(b0 + b1) stay below 2^64 (checked on the host:
 // cggi64_supported).  Key words arrive pre-split as b0 | b1 << 32 (bk_relayout_cggi64_kernel).
 constexpr u32 M27 = (1u << 27) - 1;
-// explicit 32 x 32 (+ 64) -> 64: written as C, NVVM widens the operands to 64 bits and ptxas re-derives IMAD.WIDE with
-// leftover adds of zero high halves
-__device__ __forceinline__ u64 mulwide(u32 a, u32 b) {
-    u64 r;
-    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
-    return r;
-}
-__device__ __forceinline__ u64 madwide(u32 a, u32 b, u64 c) {
-    u64 r;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ void unpack(u64 x, u32& lo, u32& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
-}
 struct Limb {
     u32 l0, l1, ls;
     __device__ __forceinline__ explicit Limb(u64 x) {
@@ -169,7 +197,7 @@ __device__ __forceinline__ void store_B(const u64 (&v)[32], u64* reg, int blk) {
 // executed from a non-unrolled loop so the code exists once (the fully unrolled 64-bit transforms did not fit the
 // instruction cache: ncu showed `no_instruction` as the top stall).  Table entry e of a pass = twiddle (off(s) + x).
 __device__ __forceinline__ void fwd_pass5(u64 (&v)[32], const ulonglong2* __restrict__ tab, int stride, int lane_off,
-                                          u64 Q, u64 Q2) {
+                                          u64 nQ, u64 QO, u64 Z) {
 #pragma unroll
     for (int s = 4; s >= 0; s--) {
         const int off = (32 >> (s + 1)) - 1, cnt = 32 >> (s + 1);
@@ -182,17 +210,17 @@ __device__ __forceinline__ void fwd_pass5(u64 (&v)[32], const ulonglong2* __rest
             if (r & (1 << s))
                 continue;
             const int ti = r >> (s + 1);
-            u64 t = shoup64(v[r + (1 << s)], w[ti].x, w[ti].y, Q);
+            u64 t = shoup64(v[r + (1 << s)], w[ti].x, w[ti].y, nQ, Z);
             u64 x = v[r];
-            v[r] = x + t;
-            v[r + (1 << s)] = x - t + Q2;
+            v[r] = x + t + Z;
+            v[r + (1 << s)] = x - t + QO;
         }
     }
 }
 // Gentleman-Sande stages 2^s, s = 0..4, in the form v' = (V - U) * w: pass B' reads the FORWARD per-thread table
 // mirrored (psi^-bitrev(m+i) = -psi^bitrev(m + m-1-i)), pass A' reads a table of NEGATED inverse uniform twiddles.
 __device__ __forceinline__ void inv_pass5(u64 (&v)[32], const ulonglong2* __restrict__ tab, int stride, int lane_off,
-                                          bool mirror, u64 Q, u64 Q2) {
+                                          bool mirror, u64 nQ, u64 QO, u64 Z) {
 #pragma unroll
     for (int s = 0; s < 5; s++) {
         const int off = (32 >> (s + 1)) - 1, cnt = 32 >> (s + 1);
@@ -206,15 +234,15 @@ __device__ __forceinline__ void inv_pass5(u64 (&v)[32], const ulonglong2* __rest
                 continue;
             const int ti = r >> (s + 1);
             u64 U = v[r], V = v[r + (1 << s)];
-            v[r] = csub(U + V, Q2);
-            v[r + (1 << s)] = shoup64(V - U + Q2, w[ti].x, w[ti].y, Q);
+            v[r] = csub(U + V + Z, QO);
+            v[r + (1 << s)] = shoup64(V - U + QO, w[ti].x, w[ti].y, nQ, Z);
         }
     }
 }
 // stride 32: positions p (block 2u) and p + 32 (block 2u + 1) are held by neighbouring lanes.  Each lane computes half
 // of the 32 butterflies: the even lane those of its local slots 0..15, the odd lane those of its local slots 16..31.
 template <bool INV>
-__device__ __forceinline__ void stage32(u64 (&v)[32], bool odd_blk, u64 w, u64 wp, u64 Q, u64 Q2) {
+__device__ __forceinline__ void stage32(u64 (&v)[32], bool odd_blk, u64 w, u64 wp, u64 nQ, u64 QO, u64 Z) {
     // odd_blk: this lane holds the upper block (the "y" side) of the pair
 #pragma unroll
     for (int k = 0; k < 16; k++) {
@@ -226,14 +254,14 @@ __device__ __forceinline__ void stage32(u64 (&v)[32], bool odd_blk, u64 w, u64 w
         const u64 y = odd_blk ? own : recv;
         u64 nx, ny;
         if (!INV) {
-            u64 t = shoup64(y, w, wp, Q);
-            nx = x + t;
-            ny = x - t + Q2;
+            u64 t = shoup64(y, w, wp, nQ, Z);
+            nx = x + t + Z;
+            ny = x - t + QO;
         }
         else {
             // Gentleman-Sande with the mirrored (negated) forward twiddle: y' = (x - y) * (-w) = (y - x) * w
-            nx = csub(x + y, Q2);
-            ny = shoup64(y - x + Q2, w, wp, Q);
+            nx = csub(x + y + Z, QO);
+            ny = shoup64(y - x + QO, w, wp, nQ, Z);
         }
         const u64 keep = odd_blk ? ny : nx;
         const u64 ret = odd_blk ? nx : ny;
@@ -266,7 +294,8 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
     u32* wany = wbits + 2 * G * 2 * K::WB;
 
     const BRCommon& C = A.c;
-    const u64 Q = A.mod.Q, Q2 = A.Q2, qinv = A.mod.qinv, oneM = A.mod.oneM;
+    const u64 Q = A.mod.Q, Q2 = A.Q2, QO = 2 * A.Q2, nQ = 0 - A.mod.Q, qinv = A.mod.qinv, oneM = A.mod.oneM;
+    const u64 Z = A.zero64;
     const u32 n = C.n;
     const int tid = threadIdx.x;
     const int g = tid / (2 * TPN), j = (tid / TPN) & 1, T = tid % TPN;
@@ -327,7 +356,7 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
     auto forward = [&](u64 (&v)[32], u64* reg) {
 #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
-            fwd_pass5(v, pass ? twS : twUf, pass ? TPN : 1, pass ? T : 0, Q, Q2);
+            fwd_pass5(v, pass ? twS : twUf, pass ? TPN : 1, pass ? T : 0, nQ, QO, Z);
             if (pass == 0) {
 #pragma unroll
                 for (int r = 0; r < 32; r++)
@@ -335,9 +364,14 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
                 group_sync(bar_id);
                 load_B(v, reg, T);
                 group_sync(bar_id);
-                stage32<false>(v, odd_blk_f, w32, w32p, Q, Q2);
+                stage32<false>(v, odd_blk_f, w32, w32p, nQ, QO, Z);
             }
         }
+        // 11 lazy stages leave values below Q + 11 * 4Q = 45 Q; the pointwise stage's 27-bit limb split needs < 31 Q
+        const u64 Q16 = 4 * QO;
+#pragma unroll
+        for (int r = 0; r < 32; r++)
+            v[r] = csub(v[r], Q16);   // < max(16 Q, 29 Q)
     };
 
     if (SKIP) {
@@ -350,7 +384,7 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
         forward(v, reg);
 #pragma unroll
         for (int r = 0; r < 32; r++)
-            v[r] = A.mod.mont_mul(v[r], A.ninvM);   // lazy (< 24 Q) * (N^-1 R) * R^-1 -> canonical
+            v[r] = A.mod.mont_mul(v[r], A.ninvM);   // lazy (< 29 Q) * (N^-1 R) * R^-1 -> canonical
         store_B(v, reg, T);
         __syncthreads();
     }
@@ -566,9 +600,9 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
             load_B(v, SKIP ? myD + (size_t)(j + 2 * (DK - 1)) * N : reg, Tv);
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
-                inv_pass5(v, pass ? twUi : twS, pass ? 1 : TPN, pass ? 0 : T, pass == 0, Q, Q2);
+                inv_pass5(v, pass ? twUi : twS, pass ? 1 : TPN, pass ? 0 : T, pass == 0, nQ, QO, Z);
                 if (pass == 0) {
-                    stage32<true>(v, odd_blk_i, w32, w32p, Q, Q2);
+                    stage32<true>(v, odd_blk_i, w32, w32p, nQ, QO, Z);
                     group_sync(bar_id);
                     store_B(v, reg, Tv);
                     group_sync(bar_id);
@@ -580,7 +614,7 @@ __global__ void __launch_bounds__(K64<DK, G>::NT, 1) br_cggi64_kernel(const __gr
             }
 #pragma unroll
             for (int r = 0; r < 32; r++)
-                c[r] = SKIP ? csub(v[r], Q) : csub(csub(c[r] + v[r], Q2), Q);   // v < 2Q
+                c[r] = SKIP ? csub(csub(v[r], Q2), Q) : csub(csub(csub(c[r] + v[r], QO), Q2), Q);   // v < 4Q
         }
     }
 
@@ -647,7 +681,7 @@ cudaError_t launch_t(const CGGI64Args& a, cudaStream_t s) {
 bool cggi64_supported(const tfhe_b200_params& p) {
     if (p.method != TFHE_B200_METHOD_GINX || p.N != 2048)
         return false;
-    // Q < 2^54: lazy transform outputs (< 24 Q) must split into 27-bit limbs with x1 + x0 < 2^32 (see L3)
+    // Q < 2^54: lazy transform outputs (< 29 Q) must split into 27-bit limbs with x1 + x0 < 2^32 (see L3)
     if (p.Q < (1ULL << 31) || p.Q >= (1ULL << 54))
         return false;
     const u32 dk = p.digitsG - p.numDigitsToThrow;
@@ -713,6 +747,7 @@ cudaError_t launch_br_cggi64(const BRCommon& c, const CGGI64Tables& t, cudaStrea
     a.dig_off = (u64)off;
     a.dig_add = t.mod.Q - B / 2;
     a.zero = 0;
+    a.zero64 = 0;
     a.ninvM = to_mont<u64>(h_powmod((u64)N, t.mod.Q - 2, t.mod.Q), t.mod);
     a.kfix = h_mulmod((u64)(pw % t.mod.Q), h_powmod((u64)N, t.mod.Q - 2, t.mod.Q), t.mod.Q);
     const int dk = (int)c.digitsKept;
