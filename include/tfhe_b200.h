@@ -115,6 +115,27 @@ int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, const uint64
 /* BinFHEContext::EvalBinGate(gate, vector, vector); ct modulus = ct_mod (normally q). */
 int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch, const uint64_t* ct1, const uint64_t* ct2,
                             uint64_t ct_mod, uint64_t* out, int space, tfhe_b200_stats* stats);
+
+/* --------------------------------------------------------------------------------------------------------
+ * SURVEY.md section 8(f) rank 1 -- gate-graph submission: a whole netlist of binary gates over a batch in ONE call,
+ * every intermediate ciphertext device-resident.  Replaces the host loop a reference user writes around
+ * BinFHEContext::EvalBinGate / EvalNOT (one std::vector<LWECiphertext> round trip per gate; the glue of
+ * lib/binfhe-base-scheme.cpp:598-677 and the AND/AND/OR expansion of XOR at :617-640 run on the host there).
+ * Semantics: identical, bit for bit, to evaluating the nodes one by one in order with EvalBinGate / EvalNOT.
+ *   wires 0 .. n_inputs-1 are the inputs, wire n_inputs + g is the output of node g; nodes are in topological
+ *   order (in0, in1 < n_inputs + g); gate is a TFHE_B200_* binary gate or TFHE_B200_NOT (in1 ignored).
+ *   inputs: [n_inputs][batch][n+1]; out: [n_outputs][batch][n+1] = the wires listed in output_wires.
+ * Independent nodes of the same kind and depth are bootstrapped by ONE launch over (nodes x batch) ciphertexts, so a
+ * small batch still fills the GPU.  Like every batched call the batch is sharded over the handle's GPUs. */
+enum { TFHE_B200_NOT = 8 };
+typedef struct tfhe_b200_gate_node {
+    int32_t gate;
+    int32_t in0;
+    int32_t in1;
+} tfhe_b200_gate_node;
+int tfhe_b200_eval_circuit(tfhe_b200_handle* h, int batch, int n_inputs, const uint64_t* inputs, uint64_t ct_mod,
+                           int n_nodes, const tfhe_b200_gate_node* nodes, int n_outputs, const int32_t* output_wires,
+                           uint64_t* out, int space, tfhe_b200_stats* stats);
 /* BinFHEScheme::BootstrapFunc(vector) (lib/binfhe-base-scheme.cpp:1194-1211, 1260-1277): table[x] = f(x, ct_mod,
  * fmod) for x < ct_mod; per_ct != 0 => one table per ciphertext ([batch][ct_mod]).  Output modulus fmod. */
 int tfhe_b200_bootstrap_func(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod,

@@ -27,6 +27,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 GATES = {"OR": 0, "AND": 1, "NOR": 2, "NAND": 3, "XOR_FAST": 4, "XNOR_FAST": 5, "XOR": 6, "XNOR": 7}
+NOT_GATE = 8   # TFHE_B200_NOT (netlists only)
 AP, GINX = 1, 2
 HOST, DEVICE = 0, 1
 
@@ -86,6 +87,7 @@ EXPORTS = [
     "tfhe_b200_ksk_words", "tfhe_b200_kernel_variant", "tfhe_b200_set_option", "tfhe_b200_eval_acc",
     "tfhe_b200_mkmswitch", "tfhe_b200_mul_matrix", "tfhe_b200_eval_bin_gate", "tfhe_b200_bootstrap_func",
     "tfhe_b200_eval_func", "tfhe_b200_eval_floor", "tfhe_b200_eval_sign", "tfhe_b200_eval_decomp",
+    "tfhe_b200_eval_circuit",
 ]
 
 
@@ -236,6 +238,26 @@ class BinFHEContextB200:
             raise TfheB200Error(-1, "EvalBinGate: `out` must be a contiguous uint64 array")
         self._call("tfhe_b200_eval_bin_gate", self._handle(), g, a.shape[0], a.ptr, b.ptr,
                    C.c_uint64(ct_mod or self.params.q), o.ptr, a.space, self._st())
+        return out
+
+    def EvalCircuit(self, inputs, nodes, outputs, ct_mod=None):
+        """Gate-graph submission (tfhe_b200_eval_circuit): `inputs` [n_inputs][batch][n+1]; `nodes` a list of
+        (gate, in0, in1) with gate a name from GATES or "NOT" (in1 ignored), wires numbered inputs first then node
+        outputs; `outputs` the wires to return -> [len(outputs)][batch][n+1].  Bit-identical to evaluating the nodes
+        one by one with EvalBinGate / EvalNOT; intermediates never leave the device."""
+        a = _Buf(inputs)
+        if len(a.shape) != 3 or a.shape[0] == 0 or a.shape[1] == 0:
+            raise TfheB200Error(-1, "ERROR: EvalCircuit: input vector is empty")
+        arr = np.zeros((len(nodes), 3), dtype=np.int32)
+        for i, (g, x, y) in enumerate(nodes):
+            arr[i] = (NOT_GATE if g == "NOT" else (GATES[g] if isinstance(g, str) else int(g)), x, x if y is None else y)
+        ow = np.ascontiguousarray(outputs, dtype=np.int32)
+        if ow.size == 0:
+            raise TfheB200Error(-1, "EvalCircuit: no output wires")
+        out = a.empty_like_out((int(ow.size), a.shape[1], a.shape[2]))
+        self._call("tfhe_b200_eval_circuit", self._handle(), a.shape[1], a.shape[0], a.ptr,
+                   C.c_uint64(ct_mod or self.params.q), len(nodes), C.c_void_p(arr.ctypes.data), int(ow.size),
+                   C.c_void_p(ow.ctypes.data), _Buf(out).ptr, a.space, self._st())
         return out
 
     def BootstrapFunc(self, ct, ct_mod, table, fmod):

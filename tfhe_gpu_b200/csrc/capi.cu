@@ -4,6 +4,7 @@
 // (binfhe-base-scheme.cpp:598-1277) as a sequence of device kernels over device-resident ciphertext batches:
 // nothing returns to the host between the bootstraps of one call (the reference round-trips through
 // std::vector<LWECiphertext> twice per bootstrap, bootstrapping.cu:1616-1667,1877-1905).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1063,6 +1064,179 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
             CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
         }
         return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
+    });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gate-graph submission.  The netlist is lowered on the host to primitive nodes
+// (XOR / XNOR -> NOT, NOT, AND, AND, OR [, NOT], exactly the expansion gate_dev performs, binfhe-base-scheme.cpp:617-640),
+// levelised, and every (level, gate kind) group is bootstrapped by one launch over group x shard ciphertexts.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct PrimNode {
+    int gate;      // TFHE_B200_OR .. TFHE_B200_XNOR_FAST, or TFHE_B200_NOT
+    int in0, in1;  // wire ids (primitive numbering)
+    int level;     // bootstrap depth
+};
+}  // namespace
+
+extern "C" int tfhe_b200_eval_circuit(tfhe_b200_handle* h, int batch, int n_inputs, const uint64_t* inputs,
+                                      uint64_t ct_mod, int n_nodes, const tfhe_b200_gate_node* nodes, int n_outputs,
+                                      const int32_t* output_wires, uint64_t* out, int space, tfhe_b200_stats* stats) {
+    if (!h)
+        FAIL(TFHE_B200_EINVAL, "EvalCircuit: GPUSetup has not been called");
+    if (batch <= 0 || n_inputs <= 0 || !inputs)
+        FAIL(TFHE_B200_EINVAL, "ERROR: EvalCircuit: input vector is empty");
+    if (n_nodes < 0 || (n_nodes > 0 && !nodes) || n_outputs <= 0 || !output_wires || !out)
+        FAIL(TFHE_B200_EINVAL, "EvalCircuit: bad netlist or output description");
+    const tfhe_b200_params& p = h->p;
+    if (ct_mod == 0 || (2ULL * p.N) % ct_mod)
+        FAIL(TFHE_B200_EINVAL, "EvalCircuit: ciphertext modulus must divide 2N");
+    // ---- lower to primitive nodes; wire_of[user wire] = primitive wire --------------------------------------------
+    std::vector<PrimNode> prim;
+    std::vector<int> wire_of(n_inputs + n_nodes), level_of_wire;
+    level_of_wire.assign(n_inputs, 0);
+    for (int i = 0; i < n_inputs; i++)
+        wire_of[i] = i;
+    auto add = [&](int gate, int a, int b) -> int {
+        PrimNode nd;
+        nd.gate = gate; nd.in0 = a; nd.in1 = b;
+        nd.level = gate == TFHE_B200_NOT ? level_of_wire[a] : 1 + std::max(level_of_wire[a], level_of_wire[b]);
+        prim.push_back(nd);
+        level_of_wire.push_back(nd.level);
+        return n_inputs + (int)prim.size() - 1;
+    };
+    for (int g = 0; g < n_nodes; g++) {
+        const tfhe_b200_gate_node& nd = nodes[g];
+        const int lim = n_inputs + g;
+        if (nd.in0 < 0 || nd.in0 >= lim)
+            FAIL(TFHE_B200_EINVAL, "EvalCircuit: node input is not an earlier wire");
+        const int a = wire_of[nd.in0];
+        if (nd.gate == TFHE_B200_NOT) {
+            wire_of[lim] = add(TFHE_B200_NOT, a, a);
+            continue;
+        }
+        if (nd.gate < 0 || nd.gate > TFHE_B200_XNOR)
+            FAIL(TFHE_B200_EINVAL, "EvalCircuit: unknown gate");
+        if (nd.in1 < 0 || nd.in1 >= lim)
+            FAIL(TFHE_B200_EINVAL, "EvalCircuit: node input is not an earlier wire");
+        if (nd.in0 == nd.in1)
+            FAIL(TFHE_B200_EINVAL, "Input ciphertexts should be independant");
+        const int b = wire_of[nd.in1];
+        if (nd.gate == TFHE_B200_XOR || nd.gate == TFHE_B200_XNOR) {
+            const int n1 = add(TFHE_B200_NOT, a, a), n2 = add(TFHE_B200_NOT, b, b);
+            const int a1 = add(TFHE_B200_AND, a, n2), a2 = add(TFHE_B200_AND, n1, b);
+            int o = add(TFHE_B200_OR, a1, a2);
+            if (nd.gate == TFHE_B200_XNOR)
+                o = add(TFHE_B200_NOT, o, o);
+            wire_of[lim] = o;
+        }
+        else
+            wire_of[lim] = add(nd.gate, a, b);
+    }
+    for (int o = 0; o < n_outputs; o++)
+        if (output_wires[o] < 0 || output_wires[o] >= n_inputs + n_nodes)
+            FAIL(TFHE_B200_EINVAL, "EvalCircuit: output wire out of range");
+    const int n_prim = (int)prim.size();
+    int max_level = 0, n_boot_nodes = 0;
+    for (const PrimNode& nd : prim) {
+        max_level = std::max(max_level, nd.level);
+        n_boot_nodes += nd.gate != TFHE_B200_NOT;
+    }
+    // execution order: per level, the bootstrapped nodes grouped by gate kind, then that level's NOT nodes (index order)
+    struct Group { int gate; std::vector<int> ids; };
+    std::vector<std::vector<Group>> plan(max_level + 1);
+    std::vector<std::vector<int>> nots(max_level + 1);
+    size_t max_group = 1;
+    for (int id = 0; id < n_prim; id++) {
+        const PrimNode& nd = prim[id];
+        if (nd.gate == TFHE_B200_NOT) {
+            nots[nd.level].push_back(id);
+            continue;
+        }
+        auto& lv = plan[nd.level];
+        Group* grp = nullptr;
+        for (Group& g : lv)
+            if (g.gate == nd.gate)
+                grp = &g;
+        if (!grp) {
+            lv.push_back(Group{nd.gate, {}});
+            grp = &lv.back();
+        }
+        grp->ids.push_back(id);
+    }
+    Dev& d0 = h->devs[0];
+    const int nd_gpus = (int)h->devs.size();
+    const int shard_max = (batch + nd_gpus - 1) / nd_gpus;
+    // at most ~32768 ciphertexts per launch keeps the scratch bounded
+    const size_t group_cap = std::max<size_t>(1, 32768 / (size_t)std::max(1, shard_max));
+    for (auto& lv : plan)
+        for (Group& g : lv)
+            max_group = std::max(max_group, std::min(g.ids.size(), group_cap));
+    static const u64 mult[6] = {5, 7, 1, 3, 5, 1};  // rgsw-cryptoparameters.h:130-137
+    return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
+        const u32 W = p.n + 1, N = p.N;
+        const size_t S = (size_t)count * W;
+        const size_t n_wires = (size_t)n_inputs + n_prim;
+        int r = arena_reserve(d, ((n_wires + max_group) * S + max_group * (size_t)count * (N + 1)) * 8 + 16384);
+        if (r) return r;
+        u64* wires = arena_take<u64>(d, n_wires * S);
+        u64* prep = arena_take<u64>(d, max_group * S);
+        u64* ext = arena_take<u64>(d, max_group * (size_t)count * (N + 1));
+        for (int i = 0; i < n_inputs; i++) {
+            r = copy_in(d, d0, wires + (size_t)i * S, inputs + ((size_t)i * batch + start) * W, S * 8, space);
+            if (r) return r;
+        }
+        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        const int batch_ = count;   // AFFINE uses `batch`
+        int depth = 0;
+        for (int lvl = 0; lvl <= max_level; lvl++) {
+            for (const Group& g : plan[lvl]) {
+                for (size_t off = 0; off < g.ids.size(); off += group_cap) {
+                    const size_t k = std::min(group_cap, g.ids.size() - off);
+                    // prepared ciphertexts of the chunk's k nodes side by side -> one blind rotation + one key switch
+                    for (size_t x = 0; x < k; x++) {
+                        const PrimNode& nd = prim[g.ids[off + x]];
+                        const u64* c1 = wires + (size_t)nd.in0 * S;
+                        const u64* c2 = wires + (size_t)nd.in1 * S;
+                        const int batch = batch_;
+                        if (g.gate == TFHE_B200_XOR_FAST || g.gate == TFHE_B200_XNOR_FAST)
+                            AFFINE(prep + x * S, c1, c2, 1, -1, 1, 0, ct_mod, 0);
+                        else
+                            AFFINE(prep + x * S, c1, c2, 1, 1, 0, 0, ct_mod, 0);
+                    }
+                    AccDesc a;
+                    a.mode = ACC_GATE; a.gate_q1 = mult[g.gate] * (p.q >> 3); a.ext_add_b = p.Q / 8 + 1;
+                    // the key switch writes [k*count][W]; reuse `prep` as the landing block once the rotation has
+                    // consumed it (blind_rotate reads prep, mkmswitch reads ext and writes prep)
+                    r = bootstrap_dev(h, d, (int)(k * count), prep, ct_mod, a, ct_mod, ext, prep, launches);
+                    if (r) return r;
+                    for (size_t x = 0; x < k; x++)
+                        CUDA_TRY(cudaMemcpyAsync(wires + ((size_t)n_inputs + g.ids[off + x]) * S, prep + x * S, S * 8,
+                                                 cudaMemcpyDeviceToDevice, d.stream));
+                }
+                depth = lvl;
+            }
+            for (int id : nots[lvl]) {
+                const PrimNode& nd = prim[id];
+                const int batch = batch_;
+                AFFINE(wires + ((size_t)n_inputs + id) * S, wires + (size_t)nd.in0 * S, nullptr, -1, 0, 0, ct_mod >> 2,
+                       ct_mod, 0);   // EvalNOT (binfhe-base-scheme.cpp:741-745)
+            }
+        }
+        (void)depth;
+        *nboot = n_boot_nodes;   // bootstraps per batch element
+        if (d.id == d0.id) {
+            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        }
+        for (int o = 0; o < n_outputs; o++) {
+            r = copy_out(d, d0, out + ((size_t)o * batch + start) * W, wires + (size_t)wire_of[output_wires[o]] * S,
+                         S * 8, space);
+            if (r) return r;
+        }
+        return 0;
     });
 }
 
