@@ -189,6 +189,42 @@ public:
                 ret[s].push_back(make(o.data() + (s * maxd + k) * W, mods[k]));
         return ret;
     }
+    // SURVEY section 8(f) rank 1 (no reference counterpart: replaces a host loop of EvalBinGate / EvalNOT calls).
+    // inputs[w] = the batch on input wire w; nodes in topological order, wire ids = inputs first, then node outputs.
+    struct GateNode {
+        int gate;   // lbcrypto::BINGATE value (OR, AND, NOR, NAND, XOR_FAST, XNOR_FAST, XOR, XNOR) or kNot
+        int in0, in1;
+    };
+    static constexpr int kNot = TFHE_B200_NOT;
+    std::vector<std::vector<CT>> EvalCircuit(const std::vector<std::vector<CT>>& inputs, const std::vector<GateNode>& nodes,
+                                             const std::vector<int>& outputs) const {
+        using namespace lbcrypto;
+        if (inputs.empty() || inputs[0].empty())
+            OPENFHE_THROW(openfhe_error, "ERROR: EvalCircuit: input vector is empty");
+        const size_t batch = inputs[0].size(), W = m_p.n + 1;
+        std::vector<uint64_t> in(inputs.size() * batch * W);
+        for (size_t w = 0; w < inputs.size(); w++) {
+            if (inputs[w].size() != batch)
+                OPENFHE_THROW(openfhe_error, "ERROR: EvalCircuit: input ciphertexts size unmatched");
+            auto a = flatten(inputs[w]);
+            std::copy(a.begin(), a.end(), in.begin() + w * batch * W);
+        }
+        std::vector<tfhe_b200_gate_node> nd(nodes.size());
+        for (size_t g = 0; g < nodes.size(); g++)
+            nd[g] = tfhe_b200_gate_node{nodes[g].gate, nodes[g].in0, nodes[g].in1};
+        std::vector<int32_t> ow(outputs.begin(), outputs.end());
+        std::vector<uint64_t> o(ow.size() * batch * W);
+        const uint64_t mod = inputs[0][0]->GetModulus().ConvertToInt();
+        check(tfhe_b200_eval_circuit(m_h, (int)batch, (int)inputs.size(), in.data(), mod, (int)nd.size(), nd.data(),
+                                     (int)ow.size(), ow.data(), o.data(), TFHE_B200_HOST, nullptr),
+              "EvalCircuit");
+        std::vector<std::vector<CT>> ret(ow.size());
+        for (size_t k = 0; k < ow.size(); k++) {
+            std::vector<uint64_t> slice(o.begin() + k * batch * W, o.begin() + (k + 1) * batch * W);
+            ret[k] = unflatten(slice, batch, mod);
+        }
+        return ret;
+    }
     // binfhecontext.cpp:319-321
     std::vector<CT> CiphertextMulMatrix(const std::vector<CT>& ct, const std::vector<std::vector<int64_t>>& matrix,
                                         uint64_t modulus) const {

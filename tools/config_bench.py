@@ -165,8 +165,65 @@ def cfg4():
     return out
 
 
+def adder_netlist(bits):
+    nodes, wire = [], 2 * bits
+
+    def add(g, x, y=None):
+        nonlocal wire
+        nodes.append((g, x, y))
+        wire += 1
+        return wire - 1
+
+    sums, carry = [], None
+    for i in range(bits):
+        a, b = i, bits + i
+        x = add("XOR_FAST", a, b)
+        if carry is None:
+            sums.append(x)
+            carry = add("AND", a, b)
+        else:
+            sums.append(add("XOR_FAST", x, carry))
+            carry = add("NAND", add("NAND", a, b), add("NAND", x, carry))
+    return nodes, sums + [carry]
+
+
+def circuit():
+    """Section 8(f) rank 1: 16-bit ripple-carry adders and a wide one-level netlist, STD128 CGGI, batch 64 and 1024,
+    one EvalCircuit submission vs the same nodes as separate EvalBinGate calls on device tensors."""
+    p = po.Port.params_named(po.STD128, po.GINX)
+    ctx, info = setup(p)
+    rng = np.random.default_rng(5)
+    out = {"params": "STD128 CGGI", **info}
+    try:
+        for batch in (64, 1024):
+            for name, (nodes, outs, n_in) in {
+                "adder16": (*adder_netlist(16), 32),
+                "wide_64_nands": ([("NAND", i, i + 1) for i in range(64)], list(range(65, 129)), 65),
+            }.items():
+                ins = torch.from_numpy(rng.integers(0, p.q, (n_in, batch, p.n + 1), dtype=np.int64)).cuda()
+                dt = timed(lambda: ctx.EvalCircuit(ins, nodes, outs))
+                st = ctx.last_stats
+                boots = st.bootstraps
+                e = {"batch": batch, "nodes": len(nodes), "bootstraps_per_element": boots, "ms": round(dt * 1e3, 2),
+                     "gates_per_s": round(boots * batch / dt, 1), "kernel_launches": st.kernel_launches}
+
+                def one_by_one():
+                    wires = [ins[i] for i in range(n_in)]
+                    for g, a, b in nodes:
+                        wires.append(ctx.EvalBinGate(g, wires[a], wires[b]))
+                    return wires
+
+                dt2 = timed(one_by_one, reps=2, warm=1)
+                e["gate_by_gate_ms"] = round(dt2 * 1e3, 2)
+                e["gate_by_gate_gates_per_s"] = round(boots * batch / dt2, 1)
+                out[f"{name}_batch{batch}"] = e
+    finally:
+        ctx.GPUClean()
+    return out
+
+
 if __name__ == "__main__":
-    table = {"cfg0": cfg0, "cfg1": cfg1, "cfg2": cfg2, "cfg2b": cfg2b, "cfg3": cfg3, "cfg4": cfg4}
+    table = {"cfg0": cfg0, "cfg1": cfg1, "cfg2": cfg2, "cfg2b": cfg2b, "cfg3": cfg3, "cfg4": cfg4, "circuit": circuit}
     want = sys.argv[1:] or list(table)
     res = {"note": __doc__.split("\n\n")[0], "gpu": torch.cuda.get_device_name(0), "imad_peak_used": IMAD_PEAK}
     for k in want:
