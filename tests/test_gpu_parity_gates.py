@@ -136,3 +136,23 @@ def test_error_behaviour(keyset):
     x = np.zeros((2, n + 1), dtype=np.uint64)
     with pytest.raises(TfheB200Error, match="independant"):
         g.EvalBinGate("NAND", x, x)
+
+
+def test_host_buffer_pipeline_matches_single_shot(keyset, rng, monkeypatch):
+    """Host-buffer calls with >= 4096 ciphertexts go through in chunks (upload / bootstrap / download overlapped on three
+    streams); the result must equal the one-shot path and the oracle, for a ragged chunking and a composite gate."""
+    ks = keyset("toy_ginx")
+    q, n = ks.p.q, ks.p.n
+    batch = 2 * 4096 + 37
+    c1 = rng.integers(0, q, (batch, n + 1), dtype=np.uint64)
+    c2 = rng.integers(0, q, (batch, n + 1), dtype=np.uint64)
+    g = ks.gpu()
+    for gate in ("NAND", "XOR"):
+        piped = g.EvalBinGate(gate, c1, c2)
+        monkeypatch.setenv("TFHE_B200_NO_PIPELINE", "1")
+        single = g.EvalBinGate(gate, c1, c2)
+        monkeypatch.delenv("TFHE_B200_NO_PIPELINE")
+        assert np.array_equal(piped, single), gate
+        idx = np.r_[0:3, 4094:4099, batch - 3:batch]
+        want = ks.port.eval_bin_gate(ks.bk, ks.ksk, po.GATES[gate], c1[idx], c2[idx], q)
+        assert np.array_equal(piped[idx], want), gate

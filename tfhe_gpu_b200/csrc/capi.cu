@@ -51,7 +51,9 @@ struct Dev {
     int id = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t xfer_in = nullptr, xfer_out = nullptr;   // host<->device copies of the pipelined host-buffer path
     cudaEvent_t ev[6] = {};
+    cudaEvent_t pev[17] = {};                             // per-chunk hand-over events (no timing)
     // key material / tables
     void* bk_generic = nullptr;
     u32* bk_cggi32 = nullptr;
@@ -411,8 +413,15 @@ static int free_dev(Dev& d) {
     for (auto& e : d.ev)
         if (e)
             cudaEventDestroy(e);
+    for (auto& e : d.pev)
+        if (e)
+            cudaEventDestroy(e);
     if (d.stream)
         cudaStreamDestroy(d.stream);
+    if (d.xfer_in)
+        cudaStreamDestroy(d.xfer_in);
+    if (d.xfer_out)
+        cudaStreamDestroy(d.xfer_out);
     d = Dev();
     return 0;
 }
@@ -499,8 +508,12 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
             CUDA_TRY(cudaGetDeviceProperties(&prop, d.id));
             d.sm_count = prop.multiProcessorCount;
             CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_in, cudaStreamNonBlocking));
+            CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_out, cudaStreamNonBlocking));
             for (auto& e : d.ev)
                 CUDA_TRY(cudaEventCreate(&e));
+            for (auto& e : d.pev)
+                CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             int r = h->is64 ? build_tables<u64>(h, d, h->m64) : build_tables<u32>(h, d, h->m32);
             if (r)
                 return r;
@@ -1050,6 +1063,53 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
         u64* o = arena_take<u64>(d, S);
         u64* tmp = arena_take<u64>(d, 4 * S);
         u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
+        if (space == TFHE_B200_HOST && count >= 4096 && !getenv("TFHE_B200_NO_PIPELINE")) {
+            // Host buffers: the shard goes through in up to 4 chunks so that the upload of chunk k+1 and the download
+            // of chunk k-1 ride under the bootstraps of chunk k (three streams, hand-over by events).  The reference
+            // copies everything in, computes, copies everything out (bootstrapping.cu:1562-1853).
+            // chunk boundaries on whole waves of CTAs (sm_count x 4 ciphertexts), or the partial last wave of every
+            // chunk would cost more than the overlap gains
+            const int unit = d.sm_count * 4;
+            const int waves = (count + unit - 1) / unit;
+            const int wpc = (waves + 3) / 4;
+            const int nch = (waves + wpc - 1) / wpc;
+            auto chunk = [&](int k, int* off, int* cnt) {
+                *off = k * wpc * unit;
+                *cnt = std::min(wpc * unit, count - *off);
+            };
+            if (d.id == d0.id) CUDA_TRY(cudaStreamWaitEvent(d.xfer_in, d.ev[0], 0));
+            for (int k = 0; k < nch; k++) {
+                int off, cnt;
+                chunk(k, &off, &cnt);
+                const size_t o8 = (size_t)off * W, b8 = (size_t)cnt * W * 8;
+                CUDA_TRY(cudaMemcpyAsync(c1 + o8, ct1 + (size_t)(start + off) * W, b8, cudaMemcpyHostToDevice, d.xfer_in));
+                CUDA_TRY(cudaMemcpyAsync(c2 + o8, ct2 + (size_t)(start + off) * W, b8, cudaMemcpyHostToDevice, d.xfer_in));
+                CUDA_TRY(cudaEventRecord(d.pev[k], d.xfer_in));
+            }
+            if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+            for (int k = 0; k < nch; k++) {
+                int off, cnt, nb = 0;
+                chunk(k, &off, &cnt);
+                const size_t o8 = (size_t)off * W;
+                CUDA_TRY(cudaStreamWaitEvent(d.stream, d.pev[k], 0));
+                r = gate_dev(h, d, gate, cnt, c1 + o8, c2 + o8, ct_mod, o + o8, tmp, ext, launches, &nb);
+                if (r) return r;
+                *nboot = nb;
+                CUDA_TRY(cudaEventRecord(d.pev[8 + k], d.stream));
+                CUDA_TRY(cudaStreamWaitEvent(d.xfer_out, d.pev[8 + k], 0));
+                CUDA_TRY(cudaMemcpyAsync(out + (size_t)(start + off) * W, o + o8, (size_t)cnt * W * 8,
+                                         cudaMemcpyDeviceToHost, d.xfer_out));
+            }
+            if (d.id == d0.id) {
+                if (gate == TFHE_B200_XOR || gate == TFHE_B200_XNOR)
+                    CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+                CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
+                CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+            }
+            CUDA_TRY(cudaEventRecord(d.pev[16], d.xfer_out));
+            CUDA_TRY(cudaStreamWaitEvent(d.stream, d.pev[16], 0));   // the caller's synchronisation covers the downloads
+            return 0;
+        }
         r = copy_in(d, d0, c1, ct1 + (size_t)start * W, S * 8, space);
         if (r) return r;
         r = copy_in(d, d0, c2, ct2 + (size_t)start * W, S * 8, space);
