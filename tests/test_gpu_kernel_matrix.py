@@ -81,7 +81,7 @@ def test_top_digit_elimination_extreme_coefficients(rng):
     port = po.Port(p)
     sk, bk, ksk, g = _ctx(p, port)
     try:
-        assert g.kernel_variant.endswith("skiptop")
+        assert "skiptop" in g.kernel_variant
         Q, QH = p.Q, p.Q >> 1
         edge = np.array([0, 1, Q - 1, QH - 1, QH, QH + 1, QH - 64, QH + 64], dtype=np.uint64)
         acc = np.resize(edge, (4, 2, 1024)).copy()

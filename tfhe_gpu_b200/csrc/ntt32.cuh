@@ -6,7 +6,7 @@
 namespace tfhe_b200 {
 
 __device__ __forceinline__ u32 mulhi_w(u32 a, u32 b) {
-    // high half through IMAD.WIDE (full rate) instead of IMAD.HI (half rate)
+    // high half through IMAD.WIDE (same issue cost as IMAD.HI on B200, measured)
     u32 hi, lo;
     asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%1, %0}, p; }" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
     (void)lo;
@@ -14,8 +14,8 @@ __device__ __forceinline__ u32 mulhi_w(u32 a, u32 b) {
 }
 __device__ __forceinline__ u32 shoup_mul(u32 y, u32 w, u32 wp, u32 Q) {
     // y*w mod Q up to one extra Q: result in [0, 2Q) for any 32-bit y.
-    // The quotient estimate is the high half of a full-rate IMAD.WIDE (no addend): measured 129 /clk/SM on B200 vs
-    // 62 /clk/SM for IMAD.HI (profiles/r01_imad_peak.json), so the butterfly costs 3 fma-heavy slots instead of 4.
+    // The quotient estimate is the high half of an IMAD.WIDE; on B200 IMAD.WIDE and IMAD.HI both issue at half the
+    // IMAD rate (profiles/r01_imad_peak.json), so a butterfly costs 4 fma-heavy issue slots: 2 + 1 + 1.
     u32 q, lo;
     asm("{ .reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%1, %0}, p; }" : "=r"(q), "=r"(lo) : "r"(y), "r"(wp));
     (void)lo;
