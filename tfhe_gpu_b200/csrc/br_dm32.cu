@@ -153,105 +153,96 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
     }
     __syncthreads();
 
+    // The ciphertexts of a CTA share nothing but the tables: from here on every (ciphertext) pair of warps runs on its
+    // own, synchronised by a named barrier, and a ciphertext whose refresh digit is zero skips the step entirely.
+    const int lt = tid % (2 * TPN);                 // thread within the ciphertext
+    const int bar_id = 1 + g;
+    auto ct_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(2 * TPN) : "memory"); };
+    constexpr int MIT = N / (2 * TPN);              // pointwise iterations per thread (slots lt + 2*TPN*it)
+    u32* top0 = myD + (size_t)(2 * (DK - 1)) * RS;  // evaluation-domain accumulator rows (a, b)
+
     for (u32 s = 0; s < steps; s++) {
-        const bool act = kidx[g * steps + s] >= 0;   // uniform over the (ciphertext, component) thread group
+        const int row = kidx[g * steps + s];        // uniform over the ciphertext's threads
+        if (row < 0)
+            continue;
+        // key words of the first pointwise iteration: requested now, consumed after the forward transforms
+        const uint4* kp = reinterpret_cast<const uint4*>(A.bk) + (size_t)row * P * N + lt;
+        uint4 cur[P];
+#pragma unroll
+        for (int x = 0; x < P; x++)
+            cur[x] = __ldg(kp + (size_t)x * N);
         // ---- phase 1: digits 0..DK-2 of component j -> forward NTT -------------------------------------------------
-        if (act) {
 #pragma unroll 1
-            for (int l = 0; l < DK - 1; l++) {
-                u32 v[32];
-                const u32 sh = gBits * l;
+        for (int l = 0; l < DK - 1; l++) {
+            u32 v[32];
+            const u32 sh = gBits * l;
 #pragma unroll
-                for (int r = 0; r < 32; r++) {
-                    int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
-                    u32 Dv = (u32)(dv + (int)A.dig_off);
-                    v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
-                }
-                fwd_passA(v, A, Q, Q2);
-                u32* reg = myD + (size_t)(j + 2 * l) * RS;
+            for (int r = 0; r < 32; r++) {
+                int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
+                u32 Dv = (u32)(dv + (int)A.dig_off);
+                v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
+            }
+            fwd_passA(v, A, Q, Q2);
+            u32* reg = myD + (size_t)(j + 2 * l) * RS;
 #pragma unroll
-                for (int r = 0; r < 32; r++)
-                    reg[pos_of(T + TPN * r)] = v[r];
-                __syncwarp();
-                load_B(v, reg, T);
-                __syncwarp();
-                fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
-                store_B(v, reg, T);
+            for (int r = 0; r < 32; r++)
+                reg[pos_of(T + TPN * r)] = v[r];
+            __syncwarp();
+            load_B(v, reg, T);
+            __syncwarp();
+            fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+            store_B(v, reg, T);
+        }
+        ct_sync();
+
+        // ---- phase 2: pointwise product with the ciphertext's own key row; the result REPLACES the accumulator -----
+        // (ciphertext-major: the two warps of the ciphertext cover its N slots, next iteration's key words in flight)
+#pragma unroll 1
+        for (int it = 0; it < MIT; it++) {
+            uint4 nxt[P];
+            if (it + 1 < MIT) {
+#pragma unroll
+                for (int x = 0; x < P; x++)
+                    nxt[x] = __ldg(kp + (size_t)x * N + (size_t)(it + 1) * 2 * TPN);
+            }
+            const u32 pk = pos_of(lt + it * 2 * TPN);
+            u32 xd[D];
+#pragma unroll
+            for (int l = 0; l < D; l++)
+                xd[l] = myD[(size_t)l * RS + pk];
+            u64 s0 = 0, s1 = 0;
+#pragma unroll
+            for (int x = 0; x < P; x++) {
+                const u32 kw[4] = {cur[x].x, cur[x].y, cur[x].z, cur[x].w};   // words (2x, 0), (2x, 1), (2x+1, 0), (2x+1, 1)
+                s0 += (u64)xd[2 * x] * kw[0];
+                s1 += (u64)xd[2 * x] * kw[1];
+                s0 += (u64)xd[2 * x + 1] * kw[2];
+                s1 += (u64)xd[2 * x + 1] * kw[3];
+            }
+            // sums < D * 22Q * Q < 2^62: reduce in two steps (lazy, then canonical)
+            auto redc2 = [&](u64 x) -> u32 {
+                u32 lo = (u32)x, hi = (u32)(x >> 32);
+                u32 t = mulhi_w(lo * qinv, Q);
+                u32 r = hi - t + Q;                       // < 2^31 + Q, == x R^-1 (mod Q)
+                r = cond_sub(r, 8 * Q); r = cond_sub(r, 4 * Q); r = cond_sub(r, Q2); r = cond_sub(r, Q);
+                return r;
+            };
+            top0[pk] = redc2(s0);        // the new evaluation-domain accumulator; phase 3 transforms it back
+            top0[RS + pk] = redc2(s1);
+            if (it + 1 < MIT) {
+#pragma unroll
+                for (int x = 0; x < P; x++)
+                    cur[x] = nxt[x];
             }
         }
-        __syncthreads();
+        ct_sync();
 
-        // ---- phase 2: pointwise product with the ciphertext's own key row; result replaces the accumulator ---------
+        // ---- phase 3: c = INTT(result), read from the accumulator row, through row j as scratch ---------------------
         {
-            constexpr int ITERS = N / NT;
-            static_assert(N % NT == 0, "unsupported CTA shape");
-#pragma unroll 1
-            for (int it = 0; it < ITERS; it++) {
-                const int k = tid + it * NT;
-                const u32 pk = pos_of(k);
-                u32 bkv[G][2 * D];
-                int rows[G];
-#pragma unroll
-                for (int gg = 0; gg < G; gg++) {
-                    rows[gg] = kidx[gg * steps + s];
-                    if (rows[gg] >= 0) {
-                        const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (size_t)rows[gg] * P * N + k;
-#pragma unroll
-                        for (int x = 0; x < P; x++) {
-                            uint4 w = __ldg(p4 + (size_t)x * N);
-                            bkv[gg][4 * x] = w.x; bkv[gg][4 * x + 1] = w.y; bkv[gg][4 * x + 2] = w.z; bkv[gg][4 * x + 3] = w.w;
-                        }
-                    }
-                }
-                // loads of all active ciphertexts first, arithmetic, then stores (see br_cggi32.cu)
-                u32 xd[G][D], d0[G], d1[G];
-#pragma unroll
-                for (int gg = 0; gg < G; gg++) {
-                    const u32* dreg = Dsm + (size_t)gg * D * RS + pk;
-#pragma unroll
-                    for (int l = 0; l < D; l++)
-                        xd[gg][l] = dreg[(size_t)l * RS];
-                }
-#pragma unroll
-                for (int gg = 0; gg < G; gg++) {
-                    u64 s0 = 0, s1 = 0;
-#pragma unroll
-                    for (int l = 0; l < D; l++) {
-                        const u32 x = xd[gg][l];
-                        s0 += (u64)x * bkv[gg][l * 2 + 0];
-                        s1 += (u64)x * bkv[gg][l * 2 + 1];
-                    }
-                    // sums < D * 22Q * Q < 2^62: reduce in two steps (lazy, then canonical)
-                    auto redc2 = [&](u64 x) -> u32 {
-                        u32 lo = (u32)x, hi = (u32)(x >> 32);
-                        u32 t = mulhi_w(lo * qinv, Q);
-                        u32 r = hi - t + Q;                       // < 2^31 + Q, == x R^-1 (mod Q)
-                        r = cond_sub(r, 8 * Q); r = cond_sub(r, 4 * Q); r = cond_sub(r, Q2); r = cond_sub(r, Q);
-                        return r;
-                    };
-                    d0[gg] = redc2(s0);
-                    d1[gg] = redc2(s1);
-                }
-#pragma unroll
-                for (int gg = 0; gg < G; gg++) {
-                    if (rows[gg] < 0)
-                        continue;
-                    u32* dreg = Dsm + (size_t)gg * D * RS + pk;
-                    dreg[0] = d0[gg];                             // delta for the inverse transform (regions 0, 1)
-                    dreg[RS] = d1[gg];
-                    dreg[(size_t)(2 * (DK - 1)) * RS] = d0[gg];   // and the new evaluation-domain accumulator
-                    dreg[(size_t)(2 * (DK - 1) + 1) * RS] = d1[gg];
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 3: c = INTT(result) (REPLACE) ---------------------------------------------------------------------
-        if (act) {
             u32 v[32];
             u32* reg = myD + (size_t)j * RS;
             const int Tv = TPN - 1 - T;
-            load_B(v, reg, Tv);
+            load_B(v, top0 + (size_t)j * RS, Tv);
             inv_passB<PB>(v, tw, twp, Q, Q2, A.zero);
             __syncwarp();
             store_B(v, reg, Tv);
