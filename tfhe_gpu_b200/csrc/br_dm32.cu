@@ -319,7 +319,7 @@ cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_
     a.dig_add = t.mod.Q - B / 2;
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
-    constexpr int G = 4;
+    constexpr int G = 4;   // 5 ciphertexts per CTA (168 registers, small spills) measured 43.7 k gates/s against 52.8 k
     using K = KCfg<10, 4, G>;
     const size_t smem = (size_t)G * K::D * K::RS * 4 + (size_t)G * c.n * c.digitsR * 4 + 64;
     if (smem > 227 * 1024)
