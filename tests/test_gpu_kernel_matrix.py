@@ -125,3 +125,24 @@ def test_cggi64_wrapped_top_digit_repair(baseG, rng):
         assert np.array_equal(g.EvalAcc(am, p.q, acc), want)
     finally:
         g.GPUClean()
+
+
+def test_cggi32_tma_key_ring_variant(rng, monkeypatch):
+    """Opt-in variant of the headline kernel that streams the RGSW key through TMA bulk copies into a shared-memory ring
+    (full / empty mbarriers): same bits as the register-staged default and as the oracle."""
+    p = po.Port.params_custom(20, 1024, 1024, Q27, 128, 1 << 7, 32, po.GINX)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        q, n = p.q, p.n
+        c1 = rng.integers(0, q, (9, n + 1), dtype=np.uint64)              # ragged last CTA
+        c2 = rng.integers(0, q, (9, n + 1), dtype=np.uint64)
+        want = port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, q)
+        default = g.EvalBinGate("NAND", c1, c2)
+        monkeypatch.setenv("TFHE_B200_TMA", "1")
+        tma = g.EvalBinGate("NAND", c1, c2)
+        monkeypatch.delenv("TFHE_B200_TMA")
+        assert np.array_equal(default, want)
+        assert np.array_equal(tma, want)
+    finally:
+        g.GPUClean()

@@ -41,7 +41,40 @@ struct CGGI32Args {
     u32 zero;            // always 0: third IADD3 operand that keeps ptxas from turning adds into IMAD.IADD (fma-heavy pipe)
 };
 
-template <int LOGN, int DK, int G, bool SKIP>
+// ---- TMA bulk copies + mbarriers (key streaming of the TMA variant) ----------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void* p) {
+    return (u32)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// TMA = true (opt-in variant, see launch_t): the RGSW key words of a pointwise iteration (D planes x NT slots x 16 B =
+// 32 KB for the headline shape) are streamed by TMA bulk copies into a two-stage shared-memory ring, two iterations
+// ahead (full / empty mbarriers, one producer thread), instead of register-staged __ldg prefetches.
+template <int LOGN, int DK, int G, bool SKIP, bool TMA = false>
 __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
     using K = KCfg<LOGN, DK, G>;
     constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS, NT = K::NT;
@@ -49,6 +82,20 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
     u32* Dsm = reinterpret_cast<u32*>(smem_raw);                      // [G][D][RS]
     u32* psiM = Dsm + (size_t)G * D * RS;                             // [2N]
     unsigned short* es = reinterpret_cast<unsigned short*>(psiM + 2 * N);  // [G][n] rotation exponents
+    // TMA variant: key ring [2][D][NT] uint4 and 4 mbarriers (full[2], empty[2]) behind the exponents, 128-byte aligned
+    uint4* ring = reinterpret_cast<uint4*>(smem_raw + K::ring_offset((int)A.c.n));
+    const u32 bar0 = smem_u32(ring + 2 * D * NT);
+    constexpr u32 STAGE_BYTES = D * NT * 16;
+    constexpr int MIT = (N + NT - 1) / NT;
+    const u32 total_fills = A.c.n * MIT;
+    auto issue_fill = [&](u32 f) {   // chunk f = (step f / MIT, iteration f % MIT) -> stage f & 1
+        const u32 st = f & 1, fb = bar0 + 8 * st;
+        const uint4* src = reinterpret_cast<const uint4*>(A.bk) + (size_t)(f / MIT) * D * N + (f % MIT) * NT;
+        mbar_expect_tx(fb, STAGE_BYTES);
+#pragma unroll
+        for (int x = 0; x < D; x++)
+            tma_bulk_g2s(smem_u32(ring + (st * D + x) * NT), src + (size_t)x * N, NT * 16, fb);
+    };
 
     const BRCommon& C = A.c;
     const u32 Q = A.mod.Q, Q2 = A.Q2, qinv = A.mod.qinv, oneM = A.mod.oneM;
@@ -122,16 +169,28 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
             c[r] = val;
         }
     }
+    if (TMA && tid == 0) {
+        mbar_init(bar0, 1);              // full[0], full[1]: one arrive (the producer's expect_tx) + the bytes
+        mbar_init(bar0 + 8, 1);
+        mbar_init(bar0 + 16, NT / 32);   // empty[0], empty[1]: one arrive per warp
+        mbar_init(bar0 + 24, NT / 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
-    u32 bk_pre[4 * D];   // key slice of (step, slot tid), requested one step ahead
-    {
+    u32 bk_pre[TMA ? 1 : 4 * D];   // key slice of (step, slot tid), requested one step ahead (register-staged variant)
+    if (!TMA) {
         const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + tid;
 #pragma unroll
         for (int x = 0; x < D; x++) {
             uint4 w = __ldg(p4 + (size_t)x * N);
             bk_pre[4 * x] = w.x; bk_pre[4 * x + 1] = w.y; bk_pre[4 * x + 2] = w.z; bk_pre[4 * x + 3] = w.w;
         }
+    }
+    else if (tid == 0) {
+        issue_fill(0);
+        if (total_fills > 1)
+            issue_fill(1);
     }
     u32* myD = Dsm + (size_t)g * D * RS;
     const u32 QHalf = Q >> 1;
@@ -228,14 +287,32 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
         {
             constexpr int ITERS = (N + NT - 1) / NT;
             u32 bkv[4 * D];
+            if (!TMA) {
 #pragma unroll
-            for (int x = 0; x < 4 * D; x++)
-                bkv[x] = bk_pre[x];
+                for (int x = 0; x < 4 * D; x++)
+                    bkv[x] = bk_pre[x];
+            }
 #pragma unroll
             for (int it = 0; it < ITERS; it++) {
                 const int k = tid + it * NT;
-                u32 bkn[4 * D];
-                if (it + 1 < ITERS) {
+                u32 bkn[TMA ? 1 : 4 * D];
+                if (TMA) {
+                    const u32 f = i * ITERS + it, st = f & 1, par = (f >> 1) & 1;
+                    mbar_wait(bar0 + 8 * st, par);                 // the bytes of chunk f have landed
+#pragma unroll
+                    for (int x = 0; x < D; x++) {
+                        const uint4 w = ring[(st * D + x) * NT + tid];
+                        bkv[4 * x] = w.x; bkv[4 * x + 1] = w.y; bkv[4 * x + 2] = w.z; bkv[4 * x + 3] = w.w;
+                    }
+                    __syncwarp();
+                    if ((tid & 31) == 0)
+                        mbar_arrive(bar0 + 16 + 8 * st);           // this warp no longer needs the stage
+                    if (tid == 0 && f + 2 < total_fills) {
+                        mbar_wait(bar0 + 16 + 8 * st, par);        // ... nor does any other warp: refill it
+                        issue_fill(f + 2);
+                    }
+                }
+                if (!TMA && it + 1 < ITERS) {
                     const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (size_t)i * D * N + (k + NT);
 #pragma unroll
                     for (int x = 0; x < D; x++) {
@@ -311,14 +388,14 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                         }
                     }
                 }
-                if (it + 1 < ITERS) {
+                if (!TMA && it + 1 < ITERS) {
 #pragma unroll
                     for (int x = 0; x < 4 * D; x++)
                         bkv[x] = bkn[x];
                 }
             }
             // request the first slot of the next step now
-            if (i + 1 < n) {
+            if (!TMA && i + 1 < n) {
                 const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (size_t)(i + 1) * D * N + tid;
 #pragma unroll
                 for (int x = 0; x < D; x++) {
@@ -500,24 +577,31 @@ void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::
         }
 }
 
-template <int LOGN, int DK, int G, bool SKIP>
+template <int LOGN, int DK, int G, bool SKIP, bool TMA>
 static cudaError_t launch_t2(const CGGI32Args& a, cudaStream_t s) {
     using K = KCfg<LOGN, DK, G>;
-    const size_t smem = K::smem_bytes((int)a.c.n);
+    const size_t smem = TMA ? K::ring_offset((int)a.c.n) + (size_t)2 * K::D * K::NT * 16 + 64 : K::smem_bytes((int)a.c.n);
     if (smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G, SKIP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G, SKIP, TMA>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
     const int grid = (a.c.batch + G - 1) / G;
-    br_cggi32_kernel<LOGN, DK, G, SKIP><<<grid, K::NT, smem, s>>>(a);
+    br_cggi32_kernel<LOGN, DK, G, SKIP, TMA><<<grid, K::NT, smem, s>>>(a);
     return cudaGetLastError();
 }
 
 template <int LOGN, int DK, int G>
 static cudaError_t launch_t(const CGGI32Args& a, cudaStream_t s, bool skip) {
-    return skip ? launch_t2<LOGN, DK, G, true>(a, s) : launch_t2<LOGN, DK, G, false>(a, s);
+    // TMA key streaming exists for the headline shape (N = 1024, four digits, four ciphertexts per CTA, top digit
+    // eliminated) and is OPT-IN (TFHE_B200_TMA=1): measured 173.5 ms per 16384 bootstraps against 162.8 ms for the
+    // register-staged loads on the same box.  The key is L2-resident and the register prefetch already hides its
+    // latency a whole phase ahead; the ring adds 8 LDS.128 per thread-iteration, the mbarrier waits and a bubble at the
+    // head of every iteration (the multiply-accumulates cannot start before the ring reads return).
+    if (LOGN == 10 && DK == 4 && G == 4 && skip && getenv("TFHE_B200_TMA"))
+        return launch_t2<LOGN, DK, G, true, (LOGN == 10 && DK == 4 && G == 4)>(a, s);
+    return skip ? launch_t2<LOGN, DK, G, true, false>(a, s) : launch_t2<LOGN, DK, G, false, false>(a, s);
 }
 
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group) {

@@ -41,6 +41,10 @@ struct KCfg {
     static constexpr size_t smem_bytes(int n) {
         return (size_t)G * D * RS * 4 + (size_t)2 * N * 4 + (size_t)G * ((n + 1) / 2 * 2) * 2 + 64;
     }
+    // TMA variant of br_cggi32: the key ring starts behind the rotation exponents, 128-byte aligned
+    static constexpr size_t ring_offset(int n) {
+        return ((size_t)G * D * RS * 4 + (size_t)2 * N * 4 + (size_t)G * (size_t)n * 2 + 127) & ~(size_t)127;
+    }
 };
 
 // ---- register-resident NTT passes -----------------------------------------------------------------------------
