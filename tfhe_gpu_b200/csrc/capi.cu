@@ -128,8 +128,11 @@ static int arena_reserve(Dev& d, size_t bytes) {
 template <typename T>
 static T* arena_take(Dev& d, size_t count) {
     size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
-    if (d.ws.off + bytes > d.ws.cap)
-        return nullptr;
+    if (d.ws.off + bytes > d.ws.cap) {
+        // a reservation computed too small is a programming error in this file: stop instead of handing a kernel a null
+        fprintf(stderr, "tfhe_b200: workspace arena overrun (%zu + %zu > %zu)\n", d.ws.off, bytes, d.ws.cap);
+        abort();
+    }
     T* p = reinterpret_cast<T*>(d.ws.base + d.ws.off);
     d.ws.off += bytes;
     return p;
