@@ -67,6 +67,9 @@ struct Dev {
     u64* twB64 = nullptr;
     u64* tw32_64 = nullptr;
     u64* twU64 = nullptr;
+    u64* twCw = nullptr;   // wide 64-bit kernel tables
+    u64* twBw = nullptr;
+    u64* twUw = nullptr;
     void* ksk = nullptr;
     Arena ws;
 };
@@ -80,6 +83,7 @@ struct tfhe_b200_handle {
     bool skip_top = false;
     bool have_dm32 = false;
     bool have_cggi64 = false;
+    bool have_cggi64w = false;   // wide variant usable (skip-top path of a supported ring)
     std::vector<u64> twA64_host;
     int force_generic = 0;
     int group = 0;  // ciphertexts per CTA of the cggi32 kernel (0 = default)
@@ -389,7 +393,7 @@ extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
     if (h->have_dm32 && !h->force_generic)
         return "dm_u32_ntt32_skiptop";
     if (h->have_cggi64 && !h->force_generic)
-        return h->skip_top ? "cggi_u64_ntt32x64_skiptop" : "cggi_u64_ntt32x64";
+        return h->have_cggi64w ? "cggi_u64_ntt16x128_skiptop" : (h->skip_top ? "cggi_u64_ntt32x64_skiptop" : "cggi_u64_ntt32x64");
     return h->variant.c_str();
 }
 extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value) {
@@ -409,7 +413,7 @@ static int free_dev(Dev& d) {
     cudaSetDevice(d.id);
     if (d.stream)
         cudaStreamSynchronize(d.stream);
-    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twU64, d.twB, d.ksk, d.ws.base};
+    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twU64, d.twCw, d.twBw, d.twUw, d.twB, d.ksk, d.ws.base};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -496,6 +500,7 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
     h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) ||
                    (h->have_cggi64 && (cggi32_skip_top_ok(p) || cggi_skip_top_wrapfix_ok(p)))) &&
                   !getenv("TFHE_B200_NO_SKIPTOP");
+    h->have_cggi64w = h->have_cggi64 && h->skip_top && cggi64w_supported(p) && !getenv("TFHE_B200_NO_C64W");
     h->variant = h->is64 ? "generic_u64" : "generic_u32";
     if (p.method == TFHE_B200_METHOD_AP)
         h->variant += "_dm";
@@ -535,6 +540,16 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 CUDA_TRY(cudaMemcpy(d.tw32_64, tw32.data(), tw32.size() * 8, cudaMemcpyHostToDevice));
                 CUDA_TRY(cudaMalloc((void**)&d.twU64, h->twA64_host.size() * 8));
                 CUDA_TRY(cudaMemcpy(d.twU64, h->twA64_host.data(), h->twA64_host.size() * 8, cudaMemcpyHostToDevice));
+            }
+            if (h->have_cggi64w) {
+                std::vector<u64> tU, tB, tC;
+                cggi64w_build_tables(p, tU, tB, tC);
+                CUDA_TRY(cudaMalloc((void**)&d.twUw, tU.size() * 8));
+                CUDA_TRY(cudaMalloc((void**)&d.twBw, tB.size() * 8));
+                CUDA_TRY(cudaMalloc((void**)&d.twCw, tC.size() * 8));
+                CUDA_TRY(cudaMemcpy(d.twUw, tU.data(), tU.size() * 8, cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(d.twBw, tB.data(), tB.size() * 8, cudaMemcpyHostToDevice));
+                CUDA_TRY(cudaMemcpy(d.twCw, tC.data(), tC.size() * 8, cudaMemcpyHostToDevice));
             }
             return 0;
         };
@@ -699,6 +714,11 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB;
         t.skip_top = true;
         CUDA_TRY(launch_br_dm32(c, t, d.stream));
+    }
+    else if (h->have_cggi64w && !h->force_generic && !getenv("TFHE_B200_C64_NARROW")) {
+        CGGI64WTables t;
+        t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twC = d.twCw; t.twB = d.twBw; t.twU = d.twUw;
+        CUDA_TRY(launch_br_cggi64w(c, t, d.stream));
     }
     else if (h->have_cggi64 && !h->force_generic) {
         CGGI64Tables t;

@@ -87,6 +87,19 @@ bool cggi64_supported(const tfhe_b200_params& p);
 void cggi64_build_tables(const tfhe_b200_params& p, std::vector<u64>& twA, std::vector<u64>& twB, std::vector<u64>& tw32);
 cudaError_t launch_br_cggi64(const BRCommon& c, const CGGI64Tables& t, cudaStream_t s, int group);
 
+// wide variant (128 threads x 16 coefficients per polynomial, br_cggi64w.cu): top-digit-elimination path only
+struct CGGI64WTables {
+    ModCtx<u64> mod;
+    const u64* bk;        // same re-laid-out key as CGGI64Tables (skip-top transform applied)
+    const u64* psi_pow;
+    const u64* twC;       // device [15][128][2]
+    const u64* twB;       // device [16][8][2]
+    const u64* twU;       // device [2][15][2]
+};
+bool cggi64w_supported(const tfhe_b200_params& p);
+void cggi64w_build_tables(const tfhe_b200_params& p, std::vector<u64>& twU, std::vector<u64>& twB, std::vector<u64>& twC);
+cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s);
+
 // LWE-side kernels (lwe_kernels.cu)
 struct KSArgs {
     u32 N, n, baseKS, dKS, row_stride;  // row_stride in entries (padded to 16 B)
