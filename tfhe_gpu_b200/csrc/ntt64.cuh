@@ -6,6 +6,10 @@
 
 namespace tfhe_b200 {
 
+// runtime zero (never written): a third addend that keeps ptxas from turning 32-bit adds into IMAD.IADD on the
+// multiplier pipe (7.8 % of its issue slots in the ncu profile of br_cggi64w before this)
+static __constant__ u32 kZero32;
+
 // explicit 32 x 32 (+ 64) -> 64: written as C, NVVM widens the operands to 64 bits and ptxas re-derives IMAD.WIDE with
 // leftover adds of zero high halves
 __device__ __forceinline__ u64 mulwide(u32 a, u32 b) {
@@ -49,7 +53,7 @@ __device__ __forceinline__ u64 shoup64(u64 y, u64 w, u64 wp, u64 nQ, u64 Z) {
     const u32 hy = y0 * w1 + y1 * w0;
     unpack(madwide(q0, nq0, mulwide(y0, w0)), l0, l1);
     const u32 h = q1 * nq0 + (q0 * nq1 + hy);
-    return pack(l0, l1 + h + z0);
+    return pack(l0, l1 + h + kZero32);
 }
 __device__ __forceinline__ u64 csub(u64 x, u64 m) {
     return x >= m ? x - m : x;
@@ -85,7 +89,7 @@ struct Limb {
         unpack(x, lo, hi);
         l0 = lo & M27;
         l1 = __funnelshift_r(lo, hi, 27);
-        ls = l0 + l1;
+        ls = l0 + l1 + kZero32;
     }
 };
 struct L3 {
@@ -96,7 +100,7 @@ struct L3 {
         unpack(bpacked, b0, b1);
         s0 = mulwide(x.l0, b0);
         s2 = mulwide(x.l1, b1);
-        kk = mulwide(x.ls, b0 + b1);
+        kk = mulwide(x.ls, b0 + b1 + kZero32);
     }
     __device__ __forceinline__ L3(const Limb& x, const Limb& b) {
         s0 = mulwide(x.l0, b.l0);
@@ -108,7 +112,7 @@ struct L3 {
         unpack(bpacked, b0, b1);
         s0 = madwide(x.l0, b0, s0);
         s2 = madwide(x.l1, b1, s2);
-        kk = madwide(x.ls, b0 + b1, kk);
+        kk = madwide(x.ls, b0 + b1 + kZero32, kk);
     }
     __device__ __forceinline__ void mac(const Limb& x, const Limb& b) {
         s0 = madwide(x.l0, b.l0, s0);
