@@ -62,11 +62,46 @@ __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG
 #pragma unroll
             for (int v = 0; v < VW; v++)
                 acc[s][v] = 0;
-        for (u32 r = rg; r < rows; r += RG) {
+        // up to four gathered rows per trip: all their loads are issued before the first add (the gather is latency / L2
+        // bound; one row per trip left only S loads in flight per thread)
+        auto row_ptr = [&](u32 r) {
             u32 i = r / dKS, j = r - i * dKS;
             u32 a0 = dig[r];
             size_t row = ((size_t)i * A.baseKS + a0) * dKS + j;
-            const KVec<TK, VW>* rp = tab + row * CV;
+            return tab + row * CV;
+        };
+        // rows per trip: 4 measured 20.1 ms per 2048 ciphertexts of the 54-bit table (1 row: 29.1 ms; 8 rows with a
+        // 255-register budget: 38.8 ms, occupancy lost)
+        constexpr int U = S <= 3 ? 4 : (S == 4 ? 2 : 1);
+        u32 r = rg;
+        for (; r + (U - 1) * RG < rows; r += U * RG) {
+            const KVec<TK, VW>* rp[U];
+#pragma unroll
+            for (int q = 0; q < U; q++)
+                rp[q] = row_ptr(r + q * RG);
+            KVec<TK, VW> x[U][S];
+#pragma unroll
+            for (int q = 0; q < U; q++)
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    u32 cv = tc + s * TC;
+                    if (cv < CV)
+                        x[q][s] = rp[q][cv];
+                }
+#pragma unroll
+            for (int q = 0; q < U; q++)
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    u32 cv = tc + s * TC;
+                    if (cv < CV) {
+#pragma unroll
+                        for (int v = 0; v < VW; v++)
+                            acc[s][v] += (u64)x[q][s].v[v];
+                    }
+                }
+        }
+        for (; r < rows; r += RG) {
+            const KVec<TK, VW>* rp = row_ptr(r);
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 u32 cv = tc + s * TC;
