@@ -91,6 +91,19 @@ const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h);
 int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value);
 
 /* --------------------------------------------------------------------------------------------------------
+ * SURVEY.md section 8(f) rank 3 -- evaluation-key generation on the GPU (reference: BinFHEContext::BTKeyGen ->
+ * BinFHEScheme::KeyGen, lib/binfhe-base-scheme.cpp:38-57; lib/lwe-pke.cpp:218-295; lib/rgsw-acc-cggi.cpp:43-75,213-240;
+ * lib/rgsw-acc-dm.cpp:44-76,153-209).  The keys are written to DEVICE memory in the element order tfhe_b200_setup
+ * expects (pass them on with key_space = TFHE_B200_DEVICE), so a 4.8 GB key-switching key never exists on the host.
+ *   sk_lwe : the n ternary LWE secret coefficients in {-1, 0, 1};  sk_ring : the N ternary ring secret coefficients
+ *   bk_dev : tfhe_b200_bk_words(params) u64 on `device`;  ksk_dev : tfhe_b200_ksk_words(params) u64 on `device`
+ * Randomness: Philox4x32-10 streams keyed by `seed`, unbiased uniform residues, discrete Gaussian errors (sigma 3.19).
+ * Key generation is randomised: results are not comparable bit for bit with the reference (tests check decryption
+ * correctness under these keys and the noise distribution of the key material). */
+int tfhe_b200_keygen(const tfhe_b200_params* params, const int8_t* sk_lwe, const int8_t* sk_ring, uint64_t seed,
+                     int device, uint64_t* bk_dev, uint64_t* ksk_dev);
+
+/* --------------------------------------------------------------------------------------------------------
  * Operator-level entry points (what the reference's host code calls).
  * -------------------------------------------------------------------------------------------------------- */
 /* GPUFFTBootstrap::EvalAcc_CUDA (include/bootstrapping.cuh:111-124, lib/bootstrapping.cu:1139-1853).

@@ -20,4 +20,5 @@ from .context import (  # noqa: F401
     GATES,
     lib_path,
     load_library,
+    gpu_keygen,
 )

@@ -87,7 +87,7 @@ EXPORTS = [
     "tfhe_b200_ksk_words", "tfhe_b200_kernel_variant", "tfhe_b200_set_option", "tfhe_b200_eval_acc",
     "tfhe_b200_mkmswitch", "tfhe_b200_mul_matrix", "tfhe_b200_eval_bin_gate", "tfhe_b200_bootstrap_func",
     "tfhe_b200_eval_func", "tfhe_b200_eval_floor", "tfhe_b200_eval_sign", "tfhe_b200_eval_decomp",
-    "tfhe_b200_eval_circuit",
+    "tfhe_b200_eval_circuit", "tfhe_b200_keygen",
 ]
 
 
@@ -144,6 +144,29 @@ class _Buf:
 
             return torch.empty(shape, dtype=self.obj.dtype, device=self.obj.device)
         return np.empty(shape, dtype=np.uint64)
+
+
+def gpu_keygen(params, sk_lwe, sk_ring, seed, device=0):
+    """tfhe_b200_keygen: evaluation keys generated on the GPU.  `sk_lwe` / `sk_ring` are
+    the ternary secrets as signed values in {-1, 0, 1}.  Returns (bk, ksk) as int64 CUDA tensors in the layout
+    GPUSetup takes -- the keys never exist on the host."""
+    import torch
+
+    L = load_library()
+    p = params if isinstance(params, Params) else Params.from_dict(
+        params.as_dict() if hasattr(params, "as_dict") else params)
+    s1 = np.ascontiguousarray(sk_lwe, dtype=np.int8)
+    s2 = np.ascontiguousarray(sk_ring, dtype=np.int8)
+    if s1.shape != (p.n,) or s2.shape != (p.N,):
+        raise TfheB200Error(-1, "KeyGen: secret key lengths must be n and N")
+    dev = torch.device("cuda", device)
+    bk = torch.empty(int(L.tfhe_b200_bk_words(C.byref(p))), dtype=torch.int64, device=dev)
+    ksk = torch.empty(int(L.tfhe_b200_ksk_words(C.byref(p))), dtype=torch.int64, device=dev)
+    rc = L.tfhe_b200_keygen(C.byref(p), C.c_void_p(s1.ctypes.data), C.c_void_p(s2.ctypes.data), C.c_uint64(seed),
+                            device, C.c_void_p(bk.data_ptr()), C.c_void_p(ksk.data_ptr()))
+    if rc != 0:
+        raise TfheB200Error(rc, L.tfhe_b200_last_error().decode())
+    return bk, ksk
 
 
 class BinFHEContextB200:

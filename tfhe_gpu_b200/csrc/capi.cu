@@ -937,6 +937,33 @@ static int check_call(tfhe_b200_handle* h, int batch, const void* a, const void*
 // ---------------------------------------------------------------------------------------------------------
 // operator-level entry points
 // ---------------------------------------------------------------------------------------------------------
+extern "C" int tfhe_b200_keygen(const tfhe_b200_params* params, const int8_t* sk_lwe, const int8_t* sk_ring,
+                                uint64_t seed, int device, uint64_t* bk_dev, uint64_t* ksk_dev) {
+    if (!params || !sk_lwe || !sk_ring || !bk_dev || !ksk_dev)
+        FAIL(TFHE_B200_EINVAL, "KeyGen: null argument");
+    const tfhe_b200_params& p = *params;
+    if (p.n == 0 || p.N == 0 || (p.N & (p.N - 1)) || p.Q < 3 || p.Q >= (1ULL << 62) || p.qKS < 2 || p.baseKS < 2 ||
+        p.baseG < 2 || p.digitsG == 0 || p.dKS == 0)
+        FAIL(TFHE_B200_EINVAL, "KeyGen: inconsistent parameters");
+    if (p.method != TFHE_B200_METHOD_GINX && p.method != TFHE_B200_METHOD_AP)
+        FAIL(TFHE_B200_ENOTSUP, "KeyGen: unknown bootstrapping method");
+    for (uint32_t i = 0; i < p.n; i++)
+        if (sk_lwe[i] < -1 || sk_lwe[i] > 1)
+            FAIL(TFHE_B200_EINVAL, "ERROR: only ternary secret key distributions are supported.");
+    for (uint32_t i = 0; i < p.N; i++)
+        if (sk_ring[i] < -1 || sk_ring[i] > 1)
+            FAIL(TFHE_B200_EINVAL, "ERROR: only ternary secret key distributions are supported.");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        FAIL(TFHE_B200_ENODEV, "KeyGen: no CUDA device (this engine has no CPU fallback)");
+    if (device < 0 || device >= ndev)
+        FAIL(TFHE_B200_EINVAL, "KeyGen: bad device index");
+    int rc = keygen_device(p, (const signed char*)sk_lwe, (const signed char*)sk_ring, seed, device, bk_dev, ksk_dev);
+    if (rc)
+        g_err = keygen_last_error();
+    return rc;
+}
+
 extern "C" int tfhe_b200_eval_acc(tfhe_b200_handle* h, int batch, const uint64_t* a, uint64_t ct_mod, uint64_t* acc,
                                   int space, tfhe_b200_stats* stats) {
     int rc = check_call(h, batch, a, acc, "EvalAcc");

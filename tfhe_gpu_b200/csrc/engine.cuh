@@ -100,6 +100,11 @@ bool cggi64w_supported(const tfhe_b200_params& p);
 void cggi64w_build_tables(const tfhe_b200_params& p, std::vector<u64>& twU, std::vector<u64>& twB, std::vector<u64>& twC);
 cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s);
 
+// GPU key generation (keygen.cu)
+int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const signed char* sk_ring, u64 seed, int device,
+                  u64* bk_dev, u64* ksk_dev);
+const char* keygen_last_error();
+
 // LWE-side kernels (lwe_kernels.cu)
 struct KSArgs {
     u32 N, n, baseKS, dKS, row_stride;  // row_stride in entries (padded to 16 B)
