@@ -46,10 +46,11 @@ def test_gates_decrypt_under_gpu_generated_keys(pset, method, gate):
         ctx.GPUClean()
 
 
-def test_functional_bootstrapping_under_gpu_generated_keys():
+@pytest.mark.parametrize("pset", [po.TOY, po.STD128])
+def test_functional_bootstrapping_under_gpu_generated_keys(pset):
     from tfhe_gpu_b200 import BinFHEContextB200, gpu_keygen
 
-    p = po.Port.params_func(po.TOY, True, 12)
+    p = po.Port.params_func(pset, True, 12)
     port = po.Port(p)
     sk, skN = _secrets(p, 5)
     bk, ksk = gpu_keygen(p.as_dict(), sk, skN, seed=7)

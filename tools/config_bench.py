@@ -222,8 +222,35 @@ def circuit():
     return out
 
 
+def keygen():
+    """Section 8(f) rank 3: evaluation keys generated on the GPU, straight into device memory, then GPUSetup from device."""
+    from tfhe_gpu_b200 import gpu_keygen
+
+    out = {}
+    for name, p in (("STD128_CGGI", po.Port.params_named(po.STD128, po.GINX)),
+                    ("STD128_AP", po.Port.params_named(po.STD128, po.AP)),
+                    ("STD128_logQ17", po.Port.params_func(po.STD128, False, 17))):
+        r = np.random.default_rng(1)
+        sk, skN = r.integers(-1, 2, p.n).astype(np.int8), r.integers(-1, 2, p.N).astype(np.int8)
+        gpu_keygen(p.as_dict(), sk, skN, 1)                      # warm-up (context, allocator)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        bk, ksk = gpu_keygen(p.as_dict(), sk, skN, 2)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        t = time.perf_counter()
+        ctx = BinFHEContextB200().GPUSetup(p.as_dict(), bk, ksk, numGPUs=1)
+        ts = time.perf_counter() - t
+        ctx.GPUClean()
+        out[name] = {"gpu_keygen_s": round(dt, 3), "gpu_setup_from_device_s": round(ts, 3),
+                     "bk_gb": round(bk.numel() * 8 / 1e9, 2), "ksk_gb": round(ksk.numel() * 8 / 1e9, 2)}
+        del bk, ksk
+        torch.cuda.empty_cache()
+    return out
+
+
 if __name__ == "__main__":
-    table = {"cfg0": cfg0, "cfg1": cfg1, "cfg2": cfg2, "cfg2b": cfg2b, "cfg3": cfg3, "cfg4": cfg4, "circuit": circuit}
+    table = {"cfg0": cfg0, "cfg1": cfg1, "cfg2": cfg2, "cfg2b": cfg2b, "cfg3": cfg3, "cfg4": cfg4, "circuit": circuit, "keygen": keygen}
     want = sys.argv[1:] or list(table)
     res = {"note": __doc__.split("\n\n")[0], "gpu": torch.cuda.get_device_name(0), "imad_peak_used": IMAD_PEAK}
     for k in want:
