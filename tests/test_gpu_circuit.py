@@ -120,3 +120,32 @@ def test_circuit_errors(keyset):
         g.EvalCircuit(ins, [("AND", 0, 1)], [3])
     with pytest.raises(TfheB200Error, match="empty"):
         g.EvalCircuit(np.zeros((0, 2, ks.p.n + 1), dtype=np.uint64), [], [0])
+
+
+def test_deep_chain_like_the_reference_long_running_tests(keyset, rng):
+    """UnitTestFHEWDeep.cpp:42-316 chains thousands of NOT / AND / OR / XOR on one ciphertext and asserts every decrypt.
+    Here: a 600-node dependent chain over a batch, submitted as ONE netlist, every wire returned and decrypted."""
+    ks = keyset("toy_ginx")
+    q, batch = ks.p.q, 6
+    bits = [[int(x) for x in rng.integers(0, 2, batch)] for _ in range(3)]
+    ins = np.stack([ks.port.encrypt_batch(ks.sk, b, 4, q, 300 + i) for i, b in enumerate(bits)])
+    kinds = ["NAND", "NOT", "OR", "XOR_FAST", "AND", "NOT", "XOR", "NOR", "XNOR_FAST"]
+    fn = {"NAND": lambda a, b: 1 - (a & b), "OR": lambda a, b: a | b, "XOR_FAST": lambda a, b: a ^ b,
+          "AND": lambda a, b: a & b, "XOR": lambda a, b: a ^ b, "NOR": lambda a, b: 1 - (a | b),
+          "XNOR_FAST": lambda a, b: 1 - (a ^ b)}
+    nodes, plain = [], [list(b) for b in bits]
+    cur = 0
+    for k in range(600):
+        g = kinds[k % len(kinds)]
+        other = 1 + (k % 2)                                   # alternate the two side inputs
+        if g == "NOT":
+            nodes.append(("NOT", cur, None))
+            plain.append([1 - v for v in plain[cur]])
+        else:
+            nodes.append((g, cur, other))
+            plain.append([fn[g](a, b) for a, b in zip(plain[cur], plain[other])])
+        cur = 3 + k
+    outs = list(range(3, 3 + len(nodes)))
+    got = ks.gpu().EvalCircuit(ins, nodes, outs)
+    for k, w in enumerate(outs):
+        assert ks.port.decrypt_batch(ks.sk, got[k], q, 4) == plain[w], f"node {k} ({nodes[k][0]})"

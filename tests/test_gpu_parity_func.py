@@ -209,3 +209,29 @@ def test_ciphertext_mul_matrix_moduli(keyset, rng, modulus):
     ref = (ct.astype(object).T @ M.astype(object)) % int(modulus)
     assert np.array_equal(got.astype(object), ref.T)
     assert np.array_equal(got, ks.port.mul_matrix(ct, M, modulus))
+
+
+def test_large_precision_logq29(keyset):
+    """UnitTestFunc.cpp:150-265 runs EvalSign / EvalDecomp at logQ = 29 (space-optimised: one key, baseG = 2^14, four
+    digits -> the 4-digit instantiation of the 64-bit kernel): sign, digits and floor against the oracle, digits pinned
+    by decryption."""
+    ks = keyset("toy_sign29")
+    Qin, P, msgs, ct = _big_inputs(ks, 29, 6)
+    g = ks.gpu()
+    want = ks.port.eval_sign(ks.bk, ks.ksk, ct, Qin)
+    got = g.EvalSign(ct, Qin)
+    assert np.array_equal(got, want)
+    assert ks.port.decrypt_batch(ks.sk, got, ks.p.q, 2) == [int(m >= P // 2) for m in msgs]
+    wd, wm = ks.port.eval_decomp(ks.bk, ks.ksk, ct, Qin)
+    gd, gm = g.EvalDecomp(ct, Qin)
+    assert gm == wm and np.array_equal(gd, wd)
+    assert np.array_equal(g.EvalFloor(ct, Qin), ks.port.eval_floor(ks.bk, ks.ksk, ct, Qin))
+    # the digits recompose the message (base 16 digits, the last one under the shrunken modulus)
+    beta, q = ks.p.beta, ks.p.q
+    for j, m in enumerate(msgs):
+        total, scale = 0, 1
+        for k, mod in enumerate(gm):
+            pk = (q if mod == q else int(mod)) // (2 * beta)
+            total += ks.port.decrypt_batch(ks.sk, np.ascontiguousarray(gd[j:j + 1, k, :]), int(mod), pk)[0] * scale
+            scale *= pk
+        assert total % P == m
