@@ -91,6 +91,22 @@ const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h);
 int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value);
 
 /* --------------------------------------------------------------------------------------------------------
+ * SURVEY.md section 8(f) rank 4 -- dynamic gadget base ("timeOptimization") for EvalSign / EvalDecomp.
+ * BinFHEContext::BTKeyGen with timeOptimization fills m_BTKey_map with one RingGSWBTKey (BK and KSK) per gadget base
+ * in {2^14, 2^18, 2^27} (lib/binfhecontext.cpp:222-247, include/rgsw-cryptoparameters.h:105-120); the scalar EvalSign /
+ * EvalDecomp start with the context's own base and switch to 2^18 once the ciphertext modulus is <= 2^26 and to 2^27
+ * once it is <= 2^17 (lib/binfhe-base-scheme.cpp:342-360, 411-428).  The reference's GPU path refuses such contexts
+ * (lib/binfhecontext.cpp:350-353); here the extra key sets are loaded beside the one given to tfhe_b200_setup and
+ * tfhe_b200_eval_sign / tfhe_b200_eval_decomp follow the same switching rule -- exactly when, like the reference
+ * (`EKs.size() == 3`), three key sets are loaded.  Every other entry point keeps using the setup key.
+ *   baseG: gadget base of this key set; digitsG = ceil(log Q / log baseG) as Change_BaseG computes it
+ *   bk / ksk: same element order as tfhe_b200_setup, sized for (baseG, digitsG) */
+int tfhe_b200_add_key_set(tfhe_b200_handle* h, uint32_t baseG, const uint64_t* bk, size_t bk_words,
+                          const uint64_t* ksk, size_t ksk_words, int key_space);
+/* number of key sets loaded (1 after tfhe_b200_setup) */
+int tfhe_b200_num_key_sets(const tfhe_b200_handle* h);
+
+/* --------------------------------------------------------------------------------------------------------
  * SURVEY.md section 8(f) rank 3 -- evaluation-key generation on the GPU (reference: BinFHEContext::BTKeyGen ->
  * BinFHEScheme::KeyGen, lib/binfhe-base-scheme.cpp:38-57; lib/lwe-pke.cpp:218-295; lib/rgsw-acc-cggi.cpp:43-75,213-240;
  * lib/rgsw-acc-dm.cpp:44-76,153-209).  The keys are written to DEVICE memory in the element order tfhe_b200_setup

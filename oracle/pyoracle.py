@@ -246,6 +246,35 @@ class Port:
         assert nd > 0
         return out[:, :nd].copy(), [int(m) for m in mods[:nd]]
 
+    @staticmethod
+    def _key_arrays(ports, bks, ksks):
+        nk = len(ports)
+        cs = (C.c_void_p * nk)(*[pt.h for pt in ports])
+        b = (C.c_void_p * nk)(*[x.ctypes.data for x in bks])
+        k = (C.c_void_p * nk)(*[x.ctypes.data for x in ksks])
+        return nk, cs, b, k
+
+    @staticmethod
+    def eval_sign_dyn(ports, bks, ksks, ct, mod):
+        """Dynamic gadget base: ports[0] is the context's own key set (tfo_eval_sign_dyn)."""
+        ct = _u64(ct)
+        out = np.zeros_like(ct)
+        nk, cs, b, k = Port._key_arrays(ports, bks, ksks)
+        rc = ports[0].L.tfo_eval_sign_dyn(C.c_int(nk), cs, b, k, C.c_int(ct.shape[0]), _p(ct), C.c_uint64(mod), _p(out))
+        assert rc == 0
+        return out
+
+    @staticmethod
+    def eval_decomp_dyn(ports, bks, ksks, ct, mod, max_digits=8):
+        ct = _u64(ct)
+        out = np.zeros((ct.shape[0], max_digits, ports[0].n + 1), dtype=np.uint64)
+        mods = np.zeros(max_digits, dtype=np.uint64)
+        nk, cs, b, k = Port._key_arrays(ports, bks, ksks)
+        nd = ports[0].L.tfo_eval_decomp_dyn(C.c_int(nk), cs, b, k, C.c_int(ct.shape[0]), _p(ct), C.c_uint64(mod),
+                                            C.c_int(max_digits), _p(out), _p(mods))
+        assert nd > 0
+        return out[:, :nd].copy(), [int(m) for m in mods[:nd]]
+
     def mul_matrix(self, ct, M, modulus):
         ct = _u64(ct)
         M = np.ascontiguousarray(M, dtype=np.int64)
@@ -299,6 +328,37 @@ class Ref:
     @staticmethod
     def custom(n, N, q, Q, baseKS, baseG, baseR, method, so=None):
         return Ref(2, [n, N, q, Q, baseKS, baseG, baseR, method], so)
+
+    @staticmethod
+    def func_dynamic(pset, arb, logQ, N=0, so=None):
+        """GenerateBinFHEContext(set, arbFunc, logQ, N, GINX, timeOptimization=true): BTKeyGen fills the three-key map."""
+        return Ref(3, [pset, int(arb), logQ, N, 0, 0], so)
+
+    def key_map_bases(self):
+        out = np.zeros(8, dtype=np.uint64)
+        cnt = self._chk(self.L.ref_key_map_bases(self.h, _p(out), C.c_int(8)))
+        return [int(x) for x in out[:cnt]]
+
+    def export_key_map(self):
+        """{baseG: (Params, bk, ksk)} for every key set of m_BTKey_map; leaves the context on its own base."""
+        own = int(self.p.baseG)
+        res = {}
+        try:
+            for base in self.key_map_bases():
+                self._chk(self.L.ref_select_key(self.h, C.c_uint64(base)))
+                out = np.zeros(16, dtype=np.uint64)
+                self._chk(self.L.ref_ctx_params(self.h, _p(out)))
+                p = Params()
+                (p.n, p.N, p.q, p.Q, p.qKS, p.baseKS, p.dKS, p.baseG, p.digitsG, p.numDigitsToThrow, p.baseR,
+                 p.digitsR, p.method, p.psi, p.beta) = [int(x) for x in out[:15]]
+                bk = np.zeros(self.L.ref_bk_words(self.h), dtype=np.uint64)
+                ksk = np.zeros(self.L.ref_ksk_words(self.h), dtype=np.uint64)
+                self._chk(self.L.ref_export_bk(self.h, _p(bk)))
+                self._chk(self.L.ref_export_ksk(self.h, _p(ksk)))
+                res[base] = (p, bk, ksk)
+        finally:
+            self._chk(self.L.ref_select_key(self.h, C.c_uint64(own)))
+        return res
 
     def _chk(self, rc):
         if rc < 0:

@@ -70,8 +70,8 @@ void* ref_ctx_create(int kind, const u64* a) {
     auto* c = new RefCtx();
     if (kind == 0)
         c->cc.GenerateBinFHEContext((BINFHE_PARAMSET)a[0], (BINFHE_METHOD)a[1]);
-    else if (kind == 1)
-        c->cc.GenerateBinFHEContext((BINFHE_PARAMSET)a[0], a[1] != 0, (uint32_t)a[2], (int64_t)a[3], GINX, false,
+    else if (kind == 1 || kind == 3)  // kind 3: timeOptimization = true (three-key map, dynamic gadget base)
+        c->cc.GenerateBinFHEContext((BINFHE_PARAMSET)a[0], a[1] != 0, (uint32_t)a[2], (int64_t)a[3], GINX, kind == 3,
                                     (uint32_t)a[4], (uint32_t)a[5]);
     else
         c->cc.GenerateBinFHEContext((uint32_t)a[0], (uint32_t)a[1], NativeInteger(a[2]), NativeInteger(a[3]), 3.19,
@@ -118,6 +118,33 @@ int ref_keygen(void* h) {
     c->sk   = c->cc.KeyGen();
     c->cc.BTKeyGen(c->sk);
     c->has_keys = true;
+    return 0;
+    REF_CATCH(-1)
+}
+
+// timeOptimization contexts: gadget bases of m_BTKey_map (binfhecontext.cpp:222-247); returns their count
+int ref_key_map_bases(void* h, u64* out, int max) {
+    REF_TRY
+    auto* c  = (RefCtx*)h;
+    auto map = c->cc.GetBTKeyMap();
+    int k    = 0;
+    for (auto& kv : *map)
+        if (k < max)
+            out[k++] = kv.first;
+    return (int)map->size();
+    REF_CATCH(-1)
+}
+// make the key set of `baseG` the context's current one (BTKeyLoad + Change_BaseG), so that ref_ctx_params /
+// ref_export_bk / ref_export_ksk describe it; select the original base again before evaluating
+int ref_select_key(void* h, u64 baseG) {
+    REF_TRY
+    auto* c  = (RefCtx*)h;
+    auto map = c->cc.GetBTKeyMap();
+    auto it  = map->find((uint32_t)baseG);
+    if (it == map->end())
+        throw std::runtime_error("no such key in the map");
+    c->cc.GetParams()->GetRingGSWParams()->Change_BaseG((uint32_t)baseG);
+    c->cc.BTKeyLoad(it->second);
     return 0;
     REF_CATCH(-1)
 }
@@ -318,7 +345,9 @@ int ref_eval_sign(void* h, int batch, const u64* ct, u64 mod, u64* out) {
     auto* c    = (RefCtx*)h;
     uint32_t n = c->cc.GetParams()->GetLWEParams()->Getn();
     int bad    = 0;
-#pragma omp parallel for schedule(dynamic)
+    // with the three-key map EvalSign calls Change_BaseG on the shared RingGSWCryptoParams: not thread-safe
+    const bool par = c->cc.GetBTKeyMap()->size() < 3;
+#pragma omp parallel for schedule(dynamic) if (par)
     for (int s = 0; s < batch; s++) {
         try {
             auto r = c->cc.EvalSign(make_ct(ct + (size_t)s * (n + 1), n, mod));
@@ -339,7 +368,8 @@ int ref_eval_decomp(void* h, int batch, const u64* ct, u64 mod, int max_digits, 
     auto* c    = (RefCtx*)h;
     uint32_t n = c->cc.GetParams()->GetLWEParams()->Getn();
     int bad = 0, nd = 0;
-#pragma omp parallel for schedule(dynamic)
+    const bool par = c->cc.GetBTKeyMap()->size() < 3;
+#pragma omp parallel for schedule(dynamic) if (par)
     for (int s = 0; s < batch; s++) {
         try {
             auto r = c->cc.EvalDecomp(make_ct(ct + (size_t)s * (n + 1), n, mod));

@@ -998,57 +998,96 @@ int tfo_eval_floor(const tfo_ctx* c, const u64* bk, const u64* ksk, int batch, c
     return rc;
 }
 
-/* binfhe-base-scheme.cpp:314-372 (scalar, single-key map) / :989-1037 (batched) */
-int tfo_eval_sign(const tfo_ctx* c, const u64* bk, const u64* ksk, int batch, const u64* ct, u64 mod, u64* out) {
-    const tfo_params* p = &c->p;
+/* gadget base the scalar EvalSign / EvalDecomp switch to once the modulus has shrunk to `mod`
+ * (binfhe-base-scheme.cpp:342-349, 411-418); 0 = keep the current base */
+static uint32_t dynamic_base(u64 mod) {
+    uint32_t binLog = (uint32_t)ceil(log2((double)mod));
+    if (binLog <= 17)
+        return 1u << 27;
+    if (binLog <= 26)
+        return 1u << 18;
+    return 0;
+}
+
+/* key set for gadget base `base` among the nk loaded ones; -1 = "No key [..] found in the map" */
+static int find_key(int nk, const tfo_ctx* const* cs, uint32_t base) {
+    for (int k = 0; k < nk; k++)
+        if (cs[k]->p.baseG == base)
+            return k;
+    return -1;
+}
+
+/* binfhe-base-scheme.cpp:314-372 (scalar EvalSign over the key map) / :989-1037 (batched, single key).
+ * cs[0] / bks[0] / ksks[0] is the context's own key set (curBase); with nk == 3 the gadget base follows the
+ * shrinking modulus ("if (EKs.size() == 3)"), otherwise the first key set is used throughout. */
+int tfo_eval_sign_dyn(int nk, const tfo_ctx* const* cs, const u64* const* bks, const u64* const* ksks, int batch,
+                      const u64* ct, u64 mod, u64* out) {
+    const tfo_params* p = &cs[0]->p;
     u64 n = p->n, beta = p->beta, q = p->q;
     size_t W = n + 1, tot = (size_t)batch * W;
-    if (batch <= 0)
+    if (batch <= 0 || nk <= 0)
         return -1;
     u64* cur = (u64*)malloc(sizeof(u64) * tot);
     u64* nxt = (u64*)malloc(sizeof(u64) * tot);
     memcpy(cur, ct, sizeof(u64) * tot);
-    int rc = 0;
-    while (mod > q) {
-        rc |= tfo_eval_floor(c, bk, ksk, batch, cur, mod, 0, nxt);
+    int rc = 0, k = 0;
+    while (mod > q && rc == 0) {
+        rc |= tfo_eval_floor(cs[k], bks[k], ksks[k], batch, cur, mod, 0, nxt);
         u64 newmod = mod / q * 2 * beta;
         tfo_mod_switch(batch, W, nxt, mod, newmod, cur);
         mod = newmod;
+        if (nk == 3) {
+            uint32_t base = dynamic_base(mod);
+            if (base && (k = find_key(nk, cs, base)) < 0)
+                rc = -1;
+        }
     }
-    for (int b = 0; b < batch; b++)
-        cur[b * W + n] = addmod(cur[b * W + n], beta, mod);
-    u64* f3 = (u64*)malloc(sizeof(u64) * mod);
-    for (u64 x = 0; x < mod; x++)
-        f3[x] = (x < mod / 2) ? q / 4 : q - q / 4;
-    rc |= tfo_bootstrap_func(c, bk, ksk, batch, cur, mod, f3, 0, q, out);
-    for (int b = 0; b < batch; b++)
-        out[b * W + n] = submod(out[b * W + n], q >> 2, q);
-    free(cur); free(nxt); free(f3);
+    if (rc == 0) {
+        for (int b = 0; b < batch; b++)
+            cur[b * W + n] = addmod(cur[b * W + n], beta, mod);
+        u64* f3 = (u64*)malloc(sizeof(u64) * mod);
+        for (u64 x = 0; x < mod; x++)
+            f3[x] = (x < mod / 2) ? q / 4 : q - q / 4;
+        rc |= tfo_bootstrap_func(cs[k], bks[k], ksks[k], batch, cur, mod, f3, 0, q, out);
+        for (int b = 0; b < batch; b++)
+            out[b * W + n] = submod(out[b * W + n], q >> 2, q);
+        free(f3);
+    }
+    free(cur); free(nxt);
     return rc;
 }
 
-/* binfhe-base-scheme.cpp:375-434 (scalar) / :1039-1085 (batched) */
-int tfo_eval_decomp(const tfo_ctx* c, const u64* bk, const u64* ksk, int batch, const u64* ct, u64 mod,
-                    int max_digits, u64* out, u64* out_mods) {
-    const tfo_params* p = &c->p;
+int tfo_eval_sign(const tfo_ctx* c, const u64* bk, const u64* ksk, int batch, const u64* ct, u64 mod, u64* out) {
+    return tfo_eval_sign_dyn(1, &c, &bk, &ksk, batch, ct, mod, out);
+}
+
+/* binfhe-base-scheme.cpp:375-434 (scalar EvalDecomp over the key map) / :1039-1085 (batched, single key) */
+int tfo_eval_decomp_dyn(int nk, const tfo_ctx* const* cs, const u64* const* bks, const u64* const* ksks, int batch,
+                        const u64* ct, u64 mod, int max_digits, u64* out, u64* out_mods) {
+    const tfo_params* p = &cs[0]->p;
     u64 n = p->n, beta = p->beta, q = p->q;
     size_t W = n + 1, tot = (size_t)batch * W;
-    if (batch <= 0 || mod <= q)
+    if (batch <= 0 || nk <= 0 || mod <= q)
         return -1;
     u64* cur = (u64*)malloc(sizeof(u64) * tot);
     u64* nxt = (u64*)malloc(sizeof(u64) * tot);
     memcpy(cur, ct, sizeof(u64) * tot);
-    int nd = 0, rc = 0;
-    while (mod > q) {
+    int nd = 0, rc = 0, k = 0;
+    while (mod > q && rc == 0) {
         if (nd >= max_digits) { rc = -1; break; }
         for (int b = 0; b < batch; b++)
             for (size_t i = 0; i < W; i++)
                 out[((size_t)b * max_digits + nd) * W + i] = cur[b * W + i] % q;
         out_mods[nd++] = q;
-        rc |= tfo_eval_floor(c, bk, ksk, batch, cur, mod, 0, nxt);
+        rc |= tfo_eval_floor(cs[k], bks[k], ksks[k], batch, cur, mod, 0, nxt);
         u64 newmod = mod / q * 2 * beta;
         tfo_mod_switch(batch, W, nxt, mod, newmod, cur);
         mod = newmod;
+        if (nk == 3) {
+            uint32_t base = dynamic_base(mod);
+            if (base && (k = find_key(nk, cs, base)) < 0)
+                rc = -1;
+        }
     }
     if (nd >= max_digits)
         rc = -1;
@@ -1059,6 +1098,11 @@ int tfo_eval_decomp(const tfo_ctx* c, const u64* bk, const u64* ksk, int batch, 
     }
     free(cur); free(nxt);
     return rc ? -1 : nd;
+}
+
+int tfo_eval_decomp(const tfo_ctx* c, const u64* bk, const u64* ksk, int batch, const u64* ct, u64 mod,
+                    int max_digits, u64* out, u64* out_mods) {
+    return tfo_eval_decomp_dyn(1, &c, &bk, &ksk, batch, ct, mod, max_digits, out, out_mods);
 }
 
 /* lwe-operation.cu:50-141, exact-integer restatement */

@@ -92,6 +92,15 @@ int tfo_eval_sign(const tfo_ctx* c, const uint64_t* bk, const uint64_t* ksk, int
 /* out [batch][max_digits][n+1]; returns number of digits (or -1) and their moduli in out_mods */
 int tfo_eval_decomp(const tfo_ctx* c, const uint64_t* bk, const uint64_t* ksk, int batch, const uint64_t* ct,
                     uint64_t mod, int max_digits, uint64_t* out, uint64_t* out_mods);
+/* dynamic gadget base ("timeOptimization", binfhecontext.cpp:222-247): nk key sets, each with its own context
+ * (same ring, different baseG / digitsG), BK and KSK; set 0 is the context's own.  With nk == 3 the scalar
+ * EvalSign / EvalDecomp rule applies (binfhe-base-scheme.cpp:342-360, 411-428): after each floor + modulus switch,
+ * base 2^27 once the modulus is <= 2^17, 2^18 once it is <= 2^26. */
+int tfo_eval_sign_dyn(int nk, const tfo_ctx* const* cs, const uint64_t* const* bks, const uint64_t* const* ksks,
+                      int batch, const uint64_t* ct, uint64_t mod, uint64_t* out);
+int tfo_eval_decomp_dyn(int nk, const tfo_ctx* const* cs, const uint64_t* const* bks, const uint64_t* const* ksks,
+                        int batch, const uint64_t* ct, uint64_t mod, int max_digits, uint64_t* out,
+                        uint64_t* out_mods);
 /* out[i] = sum_k ct[k] * M[k][i] mod modulus; ct [in][n+1], M [in][outc] int64 row-major, out [outc][n+1]
  * (lwe-operation.cu:50-141; exact integer semantics, Euclidean residue for negative entries) */
 int tfo_mul_matrix(const tfo_ctx* c, int in, int outc, const uint64_t* ct, const int64_t* M, uint64_t modulus,

@@ -102,3 +102,28 @@ def test_fused_cpp_adapter_on_reference_objects():
         assert np.array_equal(r.fused_eval_func(ct2, q, per), r.eval_func(ct2, q, per))
     finally:
         r.fused_destroy()
+
+
+def test_fused_cpp_adapter_time_optimization_context():
+    """A timeOptimization context (three-key map, binfhecontext.cpp:222-247): the reference's own GPUSetup throws for
+    it (binfhecontext.cpp:350-353); the adapter loads all three key sets and the batched EvalSign / EvalDecomp equal
+    the reference's scalar CPU path, which switches gadget base as the modulus shrinks
+    (binfhe-base-scheme.cpp:342-360, 411-428)."""
+    r = po.Ref.func_dynamic(po.TOY, False, 29, so=po.DROPIN_SO)
+    r.keygen()
+    with pytest.raises(RuntimeError):
+        r.gpu_setup(1)                                       # the reference API refuses the context
+    r.fused_create(1)
+    try:
+        Qin, q = 1 << 29, r.p.q
+        P = Qin // q * (q // (2 * r.p.beta))
+        msgs = [P // 2 + i - 2 for i in range(4)]
+        ct = r.encrypt_batch(msgs, P, Qin)
+        got = r.fused_eval_sign(ct, Qin)
+        assert np.array_equal(got, r.eval_sign(ct, Qin))
+        assert r.decrypt_batch(got, q, 2) == [int(m >= P // 2) for m in msgs]
+        a, am = r.fused_eval_decomp(ct, Qin)
+        b, bm = r.eval_decomp(ct, Qin)
+        assert am == bm and np.array_equal(a, b)
+    finally:
+        r.fused_destroy()

@@ -72,3 +72,29 @@ def test_sign_and_decomp_logq17():
     w, wm = ref.eval_decomp(ct, Qin)
     g, gm = port.eval_decomp(bk, ksk, ct, Qin)
     assert gm == wm and np.array_equal(g, w)
+
+
+def test_dynamic_gadget_base_sign_and_decomp_logq29():
+    """timeOptimization: BTKeyGen fills the three-key map (bases 2^14, 2^18, 2^27; binfhecontext.cpp:222-247) and the
+    scalar EvalSign / EvalDecomp switch key set as the modulus shrinks 2^29 -> 2^25 -> 2^21 -> 2^17 -> 2^13 -> 2^9
+    (binfhe-base-scheme.cpp:342-360, 411-428): logQ = 29 walks through all three."""
+    ref = po.Ref.func_dynamic(po.TOY, False, 29)
+    ref.keygen()
+    assert sorted(ref.key_map_bases()) == [1 << 14, 1 << 18, 1 << 27] and ref.p.baseG == 1 << 14
+    km = ref.export_key_map()
+    assert {b: km[b][0].digitsG for b in km} == {1 << 14: 4, 1 << 18: 3, 1 << 27: 2}
+    order = [ref.p.baseG] + [b for b in sorted(km) if b != ref.p.baseG]   # the context's own set first
+    ports = [po.Port(km[b][0]) for b in order]
+    bks, ksks = [km[b][1] for b in order], [km[b][2] for b in order]
+    Qin, q = 1 << 29, ref.p.q
+    P = Qin // q * (q // (2 * ref.p.beta))
+    msgs = [P // 2 + i - 2 for i in range(4)] + [3, P - 5]
+    ct = ref.encrypt_batch(msgs, P, Qin)
+    want = ref.eval_sign(ct, Qin)
+    assert ref.decrypt_batch(want, q, 2) == [int(m >= P // 2) for m in msgs]
+    assert np.array_equal(po.Port.eval_sign_dyn(ports, bks, ksks, ct, Qin), want)
+    # the single-key evaluation is a different computation (other keys, other digit counts)
+    assert not np.array_equal(ports[0].eval_sign(bks[0], ksks[0], ct, Qin), want)
+    w, wm = ref.eval_decomp(ct, Qin)
+    g, gm = po.Port.eval_decomp_dyn(ports, bks, ksks, ct, Qin)
+    assert gm == wm and np.array_equal(g, w)

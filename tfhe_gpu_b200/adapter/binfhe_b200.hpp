@@ -51,50 +51,26 @@ public:
         p.method = (uint32_t)R->GetMethod();
         p.psi = R->GetPolyParams()->GetRootOfUnity().ConvertToInt();
         p.beta = cc.GetBeta().ConvertToInt();
-        const uint64_t N = p.N, n = p.n;
-        std::vector<uint64_t> bk(tfhe_b200_bk_words(&p)), ksk(tfhe_b200_ksk_words(&p));
-        if (p.method == TFHE_B200_METHOD_GINX) {
-            const uint64_t d = 2 * (p.digitsG - p.numDigitsToThrow);
-#pragma omp parallel for collapse(2)
-            for (uint64_t key = 0; key < 2; key++)
-                for (uint64_t i = 0; i < n; i++) {
-                    const auto& ev = (*BSkey)[0][key][i]->GetElements();
-                    for (uint64_t l = 0; l < d; l++)
-                        for (uint64_t j = 0; j < 2; j++) {
-                            uint64_t* dst = bk.data() + ((((key * n + i) * d + l) * 2 + j) * N);
-                            for (uint64_t k = 0; k < N; k++)
-                                dst[k] = ev[l][j][k].ConvertToInt();
-                        }
-                }
-        }
-        else {
-            const uint64_t d = 2 * p.digitsG, bR = p.baseR, dR = p.digitsR;
-#pragma omp parallel for
-            for (uint64_t i = 0; i < n; i++)
-                for (uint64_t a0 = 1; a0 < bR; a0++)
-                    for (uint64_t k = 0; k < dR; k++) {
-                        const auto& ev = (*BSkey)[i][a0][k]->GetElements();
-                        for (uint64_t l = 0; l < d; l++)
-                            for (uint64_t j = 0; j < 2; j++) {
-                                uint64_t* dst = bk.data() + ((((((i * bR + a0) * dR + k) * d + l) * 2 + j)) * N);
-                                for (uint64_t x = 0; x < N; x++)
-                                    dst[x] = ev[l][j][x].ConvertToInt();
-                            }
-                    }
-        }
-        const auto& A = KSkey->GetElementsA();
-        const auto& B = KSkey->GetElementsB();
-#pragma omp parallel for
-        for (uint64_t i = 0; i < N; i++)
-            for (uint64_t a0 = 0; a0 < p.baseKS; a0++)
-                for (uint64_t j = 0; j < p.dKS; j++) {
-                    uint64_t* dst = ksk.data() + (((i * p.baseKS + a0) * p.dKS + j) * (n + 1));
-                    for (uint64_t k = 0; k < n; k++)
-                        dst[k] = A[i][a0][j][k].ConvertToInt();
-                    dst[n] = B[i][a0][j].ConvertToInt();
-                }
+        std::vector<uint64_t> bk, ksk;
+        flatten_keys(p, BSkey, KSkey, bk, ksk);
         check(tfhe_b200_setup(&p, bk.data(), bk.size(), ksk.data(), ksk.size(), TFHE_B200_HOST, 0, numGPUs, &m_h),
               "GPUSetup");
+        // timeOptimization contexts (BTKeyGen filled m_BTKey_map with the 2^14 / 2^18 / 2^27 key sets,
+        // binfhecontext.cpp:222-247): the reference's GPUSetup throws here (binfhecontext.cpp:350-353); we load the other
+        // sets so that EvalSign / EvalDecomp switch base as the scalar CPU path does (binfhe-base-scheme.cpp:342-360)
+        auto keyMap = cc.GetBTKeyMap();
+        if (keyMap->size() == 3 && p.method == TFHE_B200_METHOD_GINX) {
+            for (const auto& kv : *keyMap) {
+                if (kv.first == p.baseG)
+                    continue;
+                tfhe_b200_params p2 = p;
+                p2.baseG = kv.first;
+                p2.digitsG = (uint32_t)std::ceil(log((double)p.Q) / log((double)kv.first));
+                flatten_keys(p2, kv.second.BSkey, kv.second.KSkey, bk, ksk);
+                check(tfhe_b200_add_key_set(m_h, p2.baseG, bk.data(), bk.size(), ksk.data(), ksk.size(), TFHE_B200_HOST),
+                      "GPUSetup");
+            }
+        }
     }
     ~BatchedBinFHE() {
         if (m_h)
@@ -253,6 +229,54 @@ public:
     tfhe_b200_handle* handle() const { return m_h; }
 
 private:
+    // BK / KSK in the element order tfhe_b200_setup documents (the flattening of bootstrapping.cu:933-975)
+    static void flatten_keys(const tfhe_b200_params& p, const lbcrypto::RingGSWACCKey& BSkey,
+                             const lbcrypto::LWESwitchingKey& KSkey, std::vector<uint64_t>& bk,
+                             std::vector<uint64_t>& ksk) {
+        const uint64_t N = p.N, n = p.n;
+        bk.assign(tfhe_b200_bk_words(&p), 0);
+        ksk.assign(tfhe_b200_ksk_words(&p), 0);
+        if (p.method == TFHE_B200_METHOD_GINX) {
+            const uint64_t d = 2 * (p.digitsG - p.numDigitsToThrow);
+#pragma omp parallel for collapse(2)
+            for (uint64_t key = 0; key < 2; key++)
+                for (uint64_t i = 0; i < n; i++) {
+                    const auto& ev = (*BSkey)[0][key][i]->GetElements();
+                    for (uint64_t l = 0; l < d; l++)
+                        for (uint64_t j = 0; j < 2; j++) {
+                            uint64_t* dst = bk.data() + ((((key * n + i) * d + l) * 2 + j) * N);
+                            for (uint64_t k = 0; k < N; k++)
+                                dst[k] = ev[l][j][k].ConvertToInt();
+                        }
+                }
+        }
+        else {
+            const uint64_t d = 2 * p.digitsG, bR = p.baseR, dR = p.digitsR;
+#pragma omp parallel for
+            for (uint64_t i = 0; i < n; i++)
+                for (uint64_t a0 = 1; a0 < bR; a0++)
+                    for (uint64_t k = 0; k < dR; k++) {
+                        const auto& ev = (*BSkey)[i][a0][k]->GetElements();
+                        for (uint64_t l = 0; l < d; l++)
+                            for (uint64_t j = 0; j < 2; j++) {
+                                uint64_t* dst = bk.data() + ((((((i * bR + a0) * dR + k) * d + l) * 2 + j)) * N);
+                                for (uint64_t x = 0; x < N; x++)
+                                    dst[x] = ev[l][j][x].ConvertToInt();
+                            }
+                    }
+        }
+        const auto& A = KSkey->GetElementsA();
+        const auto& B = KSkey->GetElementsB();
+#pragma omp parallel for
+        for (uint64_t i = 0; i < N; i++)
+            for (uint64_t a0 = 0; a0 < p.baseKS; a0++)
+                for (uint64_t j = 0; j < p.dKS; j++) {
+                    uint64_t* dst = ksk.data() + (((i * p.baseKS + a0) * p.dKS + j) * (n + 1));
+                    for (uint64_t k = 0; k < n; k++)
+                        dst[k] = A[i][a0][j][k].ConvertToInt();
+                    dst[n] = B[i][a0][j].ConvertToInt();
+                }
+    }
     tfhe_b200_handle* m_h = nullptr;
     tfhe_b200_params m_p;
 

@@ -87,7 +87,7 @@ EXPORTS = [
     "tfhe_b200_ksk_words", "tfhe_b200_kernel_variant", "tfhe_b200_set_option", "tfhe_b200_eval_acc",
     "tfhe_b200_mkmswitch", "tfhe_b200_mul_matrix", "tfhe_b200_eval_bin_gate", "tfhe_b200_bootstrap_func",
     "tfhe_b200_eval_func", "tfhe_b200_eval_floor", "tfhe_b200_eval_sign", "tfhe_b200_eval_decomp",
-    "tfhe_b200_eval_circuit", "tfhe_b200_keygen",
+    "tfhe_b200_eval_circuit", "tfhe_b200_keygen", "tfhe_b200_add_key_set", "tfhe_b200_num_key_sets",
 ]
 
 
@@ -113,6 +113,9 @@ def load_library():
     L.tfhe_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.tfhe_b200_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                   C.c_int, C.c_void_p]
+    L.tfhe_b200_add_key_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                        C.c_int]
+    L.tfhe_b200_num_key_sets.argtypes = [C.c_void_p]
     _LIB = L
     return L
 
@@ -198,6 +201,21 @@ class BinFHEContextB200:
             raise TfheB200Error(rc, L.tfhe_b200_last_error().decode())
         self._h, self.params = h, p
         return self
+
+    def AddKeySet(self, baseG, bk, ksk):
+        """Load the key set of another gadget base of a timeOptimization context (m_BTKey_map, binfhecontext.cpp:222-247);
+        with three sets loaded EvalSign / EvalDecomp switch base like the reference's scalar path
+        (binfhe-base-scheme.cpp:342-360, 411-428)."""
+        b, k = _Buf(bk), _Buf(ksk)
+        if b.space != k.space:
+            raise TfheB200Error(-1, "AddKeySet: bk and ksk must live in the same memory space")
+        self._call("tfhe_b200_add_key_set", self._handle(), C.c_uint32(int(baseG)), b.ptr,
+                   C.c_size_t(int(np.prod(b.shape))), k.ptr, C.c_size_t(int(np.prod(k.shape))), b.space)
+        return self
+
+    @property
+    def num_key_sets(self):
+        return load_library().tfhe_b200_num_key_sets(self._h) if self._h else 0
 
     def GPUClean(self):
         """binfhecontext.cpp:362-365."""

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -97,6 +98,10 @@ struct tfhe_b200_handle {
     std::vector<u32> twA_host;
     std::string variant;
     std::mutex mu;
+    // additional bootstrapping-key sets (own BK + KSK) for other gadget bases, keyed by baseG;
+    // complete child handles on the same devices that borrow this handle's streams (binfhecontext.h:437 m_BTKey_map)
+    std::map<u32, tfhe_b200_handle*> key_map;
+    bool borrowed_streams = false;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -406,11 +411,15 @@ extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_
         h->group = (int)value;
     else
         FAIL(TFHE_B200_EINVAL, "set_option: unknown key " + k);
+    for (auto& kv : h->key_map)
+        tfhe_b200_set_option(kv.second, key, value);
     return 0;
 }
 
-static int free_dev(Dev& d) {
+static int free_dev(Dev& d, bool borrowed_streams = false) {
     cudaSetDevice(d.id);
+    if (borrowed_streams)
+        d.stream = d.xfer_in = d.xfer_out = nullptr;
     if (d.stream)
         cudaStreamSynchronize(d.stream);
     void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twU64, d.twCw, d.twBw, d.twUw, d.twB, d.ksk, d.ws.base};
@@ -437,7 +446,15 @@ extern "C" int tfhe_b200_clean(tfhe_b200_handle* h) {
     if (!h)
         return 0;  // GPUClean without GPUSetup is a no-op
     for (auto& d : h->devs)
-        free_dev(d);
+        if (d.stream && !h->borrowed_streams) {
+            cudaSetDevice(d.id);
+            cudaStreamSynchronize(d.stream);
+        }
+    for (auto& kv : h->key_map)
+        tfhe_b200_clean(kv.second);
+    h->key_map.clear();
+    for (auto& d : h->devs)
+        free_dev(d, h->borrowed_streams);
     delete h;
     return 0;
 }
@@ -673,6 +690,50 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
     }
     *out = h;
     return 0;
+}
+
+// SURVEY 8(f) rank 4 -- BinFHEContext::BTKeyGen with timeOptimization fills m_BTKey_map with one RingGSWBTKey (BK and
+// KSK) per gadget base in {2^14, 2^18, 2^27} (binfhecontext.cpp:222-247, rgsw-cryptoparameters.h:105-120); the scalar
+// EvalSign / EvalDecomp switch between them as the ciphertext modulus shrinks (binfhe-base-scheme.cpp:342-360,411-428).
+extern "C" int tfhe_b200_add_key_set(tfhe_b200_handle* h, uint32_t baseG, const uint64_t* bk, size_t bk_words,
+                                     const uint64_t* ksk, size_t ksk_words, int key_space) {
+    if (!h)
+        FAIL(TFHE_B200_EINVAL, "add_key_set: GPUSetup has not been called");
+    if (h->borrowed_streams)
+        FAIL(TFHE_B200_EINVAL, "add_key_set: not a top-level handle");
+    if (h->p.method != TFHE_B200_METHOD_GINX)
+        FAIL(TFHE_B200_ENOTSUP, "add_key_set: the key map exists for CGGI/GINX functional parameter sets only");
+    if (baseG < 2 || (baseG & (baseG - 1)))
+        FAIL(TFHE_B200_EINVAL, "add_key_set: gadget base must be a power of two");
+    tfhe_b200_params p = h->p;
+    p.baseG = baseG;
+    // RingGSWCryptoParams::Change_BaseG (rgsw-cryptoparameters.h:276-282)
+    p.digitsG = (uint32_t)std::ceil(std::log((double)p.Q) / std::log((double)baseG));
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (baseG == h->p.baseG || h->key_map.count(baseG))
+        FAIL(TFHE_B200_EINVAL, "add_key_set: a key set for this gadget base is already loaded");
+    tfhe_b200_handle* c = nullptr;
+    int rc = tfhe_b200_setup(&p, bk, bk_words, ksk, ksk_words, key_space, h->devs[0].id, (int)h->devs.size(), &c);
+    if (rc)
+        return rc;
+    // the child only ever runs inside the parent's calls: same streams, so stream order covers every dependency
+    for (size_t k = 0; k < c->devs.size(); k++) {
+        Dev& d = c->devs[k];
+        cudaSetDevice(d.id);
+        cudaStreamDestroy(d.stream);
+        cudaStreamDestroy(d.xfer_in);
+        cudaStreamDestroy(d.xfer_out);
+        d.stream = h->devs[k].stream;
+        d.xfer_in = h->devs[k].xfer_in;
+        d.xfer_out = h->devs[k].xfer_out;
+    }
+    c->borrowed_streams = true;
+    c->force_generic = h->force_generic;
+    h->key_map[baseG] = c;
+    return 0;
+}
+extern "C" int tfhe_b200_num_key_sets(const tfhe_b200_handle* h) {
+    return h ? 1 + (int)h->key_map.size() : 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1539,6 +1600,16 @@ extern "C" int tfhe_b200_eval_floor(tfhe_b200_handle* h, int batch, const uint64
 }
 
 // shared body of EvalSign (binfhe-base-scheme.cpp:989-1037) and EvalDecomp (:1039-1085)
+// gadget base the reference selects for a ciphertext modulus (0 = keep the current one)
+static u32 dynamic_base(u64 mod) {
+    const u32 binLog = (u32)std::ceil(std::log2((double)mod));
+    if (binLog <= 17)
+        return 1u << 27;
+    if (binLog <= 26)
+        return 1u << 18;
+    return 0;
+}
+
 static int sign_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint64_t ct_mod, bool decomp, int max_digits,
                        uint64_t* out, uint64_t* out_mods, int space, tfhe_b200_stats* stats, int* ndigits) {
     const tfhe_b200_params& p = h->p;
@@ -1570,6 +1641,16 @@ static int sign_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint6
         for (int k = 0; k < nd; k++)
             out_mods[k] = k < nd - 1 ? q : mfin;
     }
+    // "if (EKs.size() == 3)": the reference switches gadget base only when the full three-key map is present; every base
+    // the modulus chain asks for must then be loaded ("ERROR: No key [..] found in the map")
+    const bool dynamic = h->key_map.size() == 2;
+    if (dynamic) {
+        for (size_t k = 1; k < mods.size(); k++) {
+            const u32 base = dynamic_base(mods[k]);
+            if (base && base != p.baseG && !h->key_map.count(base))
+                FAIL(TFHE_B200_EINVAL, "ERROR: No key [" + std::to_string(base) + "] found in the map");
+        }
+    }
     Dev& d0 = h->devs[0];
     return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
         const int batch = count;
@@ -1589,18 +1670,27 @@ static int sign_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint6
         if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
         u64 mod = ct_mod;
         int digit = 0;
+        // current key set (curEK of binfhe-base-scheme.cpp:327-333); the child handle's Dev of the same index carries
+        // that set's key tables and borrows this Dev's streams
+        const size_t dev_index = (size_t)(&d - &h->devs[0]);
+        tfhe_b200_handle* kh = h;
         while (mod > q) {
             if (decomp) {
                 CUDA_TRY(launch_copy_mod(o + (size_t)digit * W, (size_t)max_digits * W, cur, W, q, count, W, d.stream));
                 (*launches)++;
                 digit++;
             }
-            r = floor_dev(h, d, count, cur, mod, 0, nxt, tmp, ext, tab, launches, nboot);
+            r = floor_dev(kh, kh->devs[dev_index], count, cur, mod, 0, nxt, tmp, ext, tab, launches, nboot);
             if (r) return r;
             u64 newmod = mod / q * 2 * beta;
             CUDA_TRY(launch_mod_switch(cur, nxt, mod, newmod, S, d.stream));   // lwe-pke.cpp:204-215
             (*launches)++;
             mod = newmod;
+            if (dynamic) {  // binfhe-base-scheme.cpp:342-360 / :411-428
+                const u32 base = dynamic_base(mod);
+                if (base)
+                    kh = base == h->p.baseG ? h : h->key_map.find(base)->second;
+            }
         }
         if (decomp) {
             CUDA_TRY(launch_copy_mod(o + (size_t)digit * W, (size_t)max_digits * W, cur, W, 0, count, W, d.stream));
@@ -1616,7 +1706,7 @@ static int sign_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint6
             CUDA_TRY(cudaStreamSynchronize(d.stream));
             AccDesc a;
             a.mode = ACC_TABLE; a.table = tab; a.fmod = q;
-            r = bootstrap_dev(h, d, count, cur, mod, a, q, ext, nxt, launches);
+            r = bootstrap_dev(kh, kh->devs[dev_index], count, cur, mod, a, q, ext, nxt, launches);
             if (r) return r;
             (*nboot)++;
             AFFINE(o, nxt, nullptr, 1, 0, 0, q - (q >> 2), q, 0);
