@@ -249,8 +249,46 @@ def keygen():
     return out
 
 
+def dynamic():
+    """Section 8(f) rank 4: EvalSign / EvalDecomp at logQ = 29 (STD128, n = 1305), one key set (baseG = 2^14, the
+    batched reference semantics) against the three-key map of a timeOptimization context (2^14 -> 2^18 -> 2^27 as the
+    modulus shrinks).  Keys for the three gadget bases are generated on the GPU under the same secret."""
+    import math
+
+    from tfhe_gpu_b200 import gpu_keygen
+
+    p = po.Port.params_func(po.STD128, False, 29)
+    r = np.random.default_rng(1)
+    sk, skN = r.integers(-1, 2, p.n).astype(np.int8), r.integers(-1, 2, p.N).astype(np.int8)
+    bk, ksk = gpu_keygen(p.as_dict(), sk, skN, 2)
+    ctx = BinFHEContextB200().GPUSetup(p.as_dict(), bk, ksk, numGPUs=1)
+    out = {"params": "STD128 large precision, logQ = 29 (N = 2048, 54-bit Q, baseG 2^14 / 2^18 / 2^27)",
+           "kernel_own_base": ctx.kernel_variant}
+    rng = np.random.default_rng(6)
+    batch, Qbig = 512, 1 << 29
+    try:
+        ct = rand_ct(rng, batch, p.n, Qbig)
+        for label in ("single_key", "three_key_map"):
+            if label == "three_key_map":
+                for base in (1 << 18, 1 << 27):
+                    d = p.as_dict()
+                    d["baseG"], d["digitsG"] = base, math.ceil(math.log(p.Q) / math.log(base))
+                    bk2, ksk2 = gpu_keygen(d, sk, skN, 3 + base)
+                    ctx.AddKeySet(base, bk2, ksk2)
+                    del bk2, ksk2
+            for op, fn in (("EvalSign", lambda: ctx.EvalSign(ct, Qbig)), ("EvalDecomp", lambda: ctx.EvalDecomp(ct, Qbig))):
+                dt = timed(fn)
+                st = ctx.last_stats
+                out[f"{op}_{label}"] = {"batch": batch, "ms": round(dt * 1e3, 2), "ops_per_s": round(batch / dt, 1),
+                                        "bootstraps_per_op": st.bootstraps,
+                                        "bootstraps_per_s": round(st.bootstraps * batch / dt, 1)}
+    finally:
+        ctx.GPUClean()
+    return out
+
+
 if __name__ == "__main__":
-    table = {"cfg0": cfg0, "cfg1": cfg1, "cfg2": cfg2, "cfg2b": cfg2b, "cfg3": cfg3, "cfg4": cfg4, "circuit": circuit, "keygen": keygen}
+    table = {"dynamic": dynamic, "cfg0": cfg0, "cfg1": cfg1, "cfg2": cfg2, "cfg2b": cfg2b, "cfg3": cfg3, "cfg4": cfg4, "circuit": circuit, "keygen": keygen}
     want = sys.argv[1:] or list(table)
     res = {"note": __doc__.split("\n\n")[0], "gpu": torch.cuda.get_device_name(0), "imad_peak_used": IMAD_PEAK}
     for k in want:
