@@ -77,7 +77,8 @@ class Stats(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libtfhe_b200.so")
+    # TFHE_B200_LIB: developer knob to load an experimental build of the same library (kernel A/B measurements)
+    return os.environ.get("TFHE_B200_LIB") or os.path.join(_HERE, "libtfhe_b200.so")
 
 
 _LIB = None

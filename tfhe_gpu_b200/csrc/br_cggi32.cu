@@ -243,7 +243,11 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
     // =========================================================================================================
     for (u32 i = 0; i < n; i++) {
         // ---- phase 1: decompose + forward NTT of the DK digit polynomials of component j ---------------------
+#ifdef CGGI32_UNROLL_L
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int l = 0; l < (SKIP ? DK - 1 : DK); l++) {
             u32 v[32];
             const u32 sh = gBits * (l + C.numThrow);
@@ -326,7 +330,10 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                 // arithmetic (independent streams the scheduler can interleave), then the stores.  Written per ciphertext
                 // the store of one and the loads of the next cannot be reordered (possible aliasing), which serialises the
                 // long multiply-accumulate / reduction chains (ncu: `wait` was half of this phase's samples).
-                constexpr int GB = (G % 2 == 0) ? 2 : 1;   // 4 at a time measured slower (register pressure)
+                #ifndef CGGI32_GB
+#define CGGI32_GB 2
+#endif
+                constexpr int GB = (G % CGGI32_GB == 0) ? CGGI32_GB : ((G % 2 == 0) ? 2 : 1);   // 4 at a time measured slower
                 auto redc_lazy = [&](u64 x) -> u32 {   // x < 2^63 -> < 2^31 + Q, congruent x R^-1 (mod Q)
                     u32 lo = (u32)x, hi = (u32)(x >> 32);
                     u32 t = mulhi_w(lo * qinv, Q);
@@ -380,11 +387,13 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
 #pragma unroll
                     for (int b = 0; b < GB; b++) {
                         u32* wreg = Dsm + (size_t)(g0 + b) * D * RS + pk;
-                        wreg[0] = dl0[b];
-                        wreg[RS] = dl1[b];
-                        if (SKIP) {
+                        if (SKIP) {   // phase 3 transforms the updated acc_eval itself; delta is not needed on its own
                             wreg[(size_t)(2 * (DK - 1)) * RS] = m1[b];
                             wreg[(size_t)(2 * (DK - 1) + 1) * RS] = m2[b];
+                        }
+                        else {
+                            wreg[0] = dl0[b];
+                            wreg[RS] = dl1[b];
                         }
                     }
                 }
@@ -406,13 +415,17 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
         }
         __syncthreads();
 
-        // ---- phase 3: inverse NTT of delta_j (mirrored block), accumulate into c ------------------------------
+        // ---- phase 3: inverse NTT (mirrored block) ------------------------------------------------------------
+        // plain path: of delta_j, accumulated into c.  SKIP path: of the evaluation-domain accumulator itself,
+        // c = INTT(acc_eval) (identical mod Q because the transform is linear), read from its own region and
+        // transposed through the free digit region j, so acc_eval survives for the next step and c is dead between
+        // the digit extraction and this point (32 registers less through phases 1 and 2).
         {
             u32 v[32];
             u32* reg = myD + (size_t)j * RS;
             const int Tv = TPN - 1 - T;
             {
-                const uint4* p4 = reinterpret_cast<const uint4*>(reg + 36 * Tv);
+                const uint4* p4 = reinterpret_cast<const uint4*>((SKIP ? myD + (size_t)(2 * (DK - 1) + j) * RS : reg) + 36 * Tv);
 #pragma unroll
                 for (int x = 0; x < 8; x++) {
                     uint4 w = p4[x];
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
             inv_passA(v, A, Q, Q2);
 #pragma unroll
             for (int r = 0; r < 32; r++)
-                c[r] = cond_sub(cond_sub(c[r] + v[r], Q2), Q);   // c < Q, v < 2Q
+                c[r] = SKIP ? cond_sub(v[r], Q) : cond_sub(cond_sub(c[r] + v[r], Q2), Q);   // c < Q, v < 2Q
         }
         // no CTA barrier needed here: phase 1 of the next step writes regions that phase 2 finished reading
         // (barrier above) and region j, which only this thread group read in phase 3 (__syncwarp above).
