@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 # algorithmic work per STD128 CGGI bootstrap
 IMAD32_PER_BOOTSTRAP = 129.0e6          # 3 IMAD32 per modular multiplication, 42.99 M modmults
 KS_BYTES_PER_BOOTSTRAP = 2_101_248      # N*dKS*(n+1)*2 B gathered from the u16 key-switching table
-DRAM_TRAFFIC_PER_LAUNCH_16384 = 1.475e9 + 0.139e9      # br_cggi32 (profiles/r01_prof_cggi32_summary.md, r01c)
+DRAM_TRAFFIC_PER_LAUNCH_16384 = 1.507e9 + 0.202e9      # br_cggi32 (profiles/r01_prof_cggi32_summary.md, r01e)
 KS_TABLE_BYTES = 1024 * 2 * 128 * 513 * 2   # N * dKS * baseKS * (n+1) u16 entries
 KS_DRAM_TRAFFIC_PER_LAUNCH_16384 = 5.30e9 + 0.07e9     # mkmswitch_packed16 (same file, prof_mkms_r01b)
 IMAD_PEAK_FALLBACK = 18.5e12            # profiles/r01_imad_peak.json (sustained, power-capped), this pool's B200
