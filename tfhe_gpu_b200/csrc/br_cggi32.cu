@@ -618,7 +618,6 @@ static cudaError_t launch_t(const CGGI32Args& a, cudaStream_t s, bool skip) {
 }
 
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group) {
-    (void)sm_count;
     CGGI32Args a;
     a.c = c;
     a.mod = t.mod;
@@ -642,6 +641,12 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
 #define CASE(LOGN, DK, GG) \
     if (c.logN == LOGN && dk == DK && group == GG) return launch_t<LOGN, DK, GG>(a, s, t.skip_top);
     if (c.logN == 10) {
+        // Throughput shape: 4 ciphertexts per CTA share every key word.  A batch that leaves SMs idle that way is
+        // latency-bound instead and runs as CTAs of 2 ciphertexts (4 warps): a rotation step finishes sooner because
+        // fewer warps compete for the SM's multiplier pipe.  Measured per bootstrap at batch <= 296 on one B200: 5.77 ms
+        // (4 per CTA), 4.47 ms (2 per CTA), 5.1 ms (1 per CTA: one warp per scheduler, latency-bound -- not instantiated).
+        if (group == 0 && dk == 4 && c.batch <= 2 * sm_count)
+            group = 2;
         if (group == 0) group = (dk <= 4) ? 4 : 2;
         CASE(10, 4, 4) CASE(10, 4, 2)
         CASE(10, 3, 4)
