@@ -74,10 +74,20 @@ __device__ __forceinline__ void tma_bulk_g2s(u32 dst, const void* src, u32 bytes
 // TMA = true (opt-in variant, see launch_t): the RGSW key words of a pointwise iteration (D planes x NT slots x 16 B =
 // 32 KB for the headline shape) are streamed by TMA bulk copies into a two-stage shared-memory ring, two iterations
 // ahead (full / empty mbarriers, one producer thread), instead of register-staged __ldg prefetches.
-template <int LOGN, int DK, int G, bool SKIP, bool TMA = false>
-__global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
+//
+// LAT = true (latency layout, one ciphertext per CTA, top digit eliminated): 2*DK warps; warps 0 .. 2*(DK-1)-1 own one
+// DIGIT polynomial each instead of one accumulator component.  The DK-1 warps of a component each run the inverse
+// transform redundantly (through their own digit region), extract their own digit and do ONE forward transform; the
+// last pair of warps only helps in the pointwise stage.  The critical path of a rotation step is 1 inverse + 1 forward
+// transform + N / (64 DK) pointwise iterations instead of 1 + (DK-1) + N/64.  Chosen for batches of at most one
+// ciphertext per SM.
+template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false>
+__global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
+    br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
     using K = KCfg<LOGN, DK, G>;
-    constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS, NT = K::NT;
+    constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS;
+    constexpr int NT = LAT ? 2 * DK * TPN : K::NT;
+    static_assert(!LAT || (G == 1 && SKIP && !TMA && DK >= 2), "latency layout: one ciphertext per CTA, skip-top path");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32* Dsm = reinterpret_cast<u32*>(smem_raw);                      // [G][D][RS]
     u32* psiM = Dsm + (size_t)G * D * RS;                             // [2N]
@@ -101,8 +111,10 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
     const u32 Q = A.mod.Q, Q2 = A.Q2, qinv = A.mod.qinv, oneM = A.mod.oneM;
     const u32 n = C.n;
     const int tid = threadIdx.x;
-    const int g = tid / (2 * TPN);         // ciphertext slot within the CTA
+    const int g = LAT ? 0 : tid / (2 * TPN);   // ciphertext slot within the CTA
     const int j = (tid / TPN) & 1;         // accumulator component (0 = a, 1 = b)
+    const int lw = LAT ? tid / (2 * TPN) : 0;  // latency layout: the digit polynomial this warp transforms
+    const bool helper = LAT && lw == DK - 1;   // latency layout: pointwise-only warps
     const int T = tid % TPN;               // thread index within the NTT
     const int ct = blockIdx.x * G + g;
     const bool live = ct < C.batch;
@@ -203,6 +215,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
         // with BK'_l = BK_l - B^(l-top) BK_top and BK'_top = B^-top BK_top (done once at setup).  NTT(c) is simply the
         // evaluation-domain accumulator, maintained as acc_eval += delta in the pointwise stage and kept in the
         // shared-memory region the top digit would have used: 2 of the 2*DK forward transforms per step disappear.
+        if (!LAT || lw == 0) {
         u32 v[32];
 #pragma unroll
         for (int r = 0; r < 32; r++)
@@ -237,6 +250,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
             for (int x = 0; x < 8; x++)
                 p4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
         }
+        }
         __syncthreads();
     }
 
@@ -248,7 +262,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
 #else
 #pragma unroll 1
 #endif
-        for (int l = 0; l < (SKIP ? DK - 1 : DK); l++) {
+        for (int l = (LAT ? lw : 0); l < (LAT ? (helper ? lw : lw + 1) : (SKIP ? DK - 1 : DK)); l++) {
             u32 v[32];
             const u32 sh = gBits * (l + C.numThrow);
 #pragma unroll
@@ -316,7 +330,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                         issue_fill(f + 2);
                     }
                 }
-                if (!TMA && it + 1 < ITERS) {
+                if (!TMA && it + 1 < ITERS && (!LAT || k + NT < N)) {
                     const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (size_t)i * D * N + (k + NT);
 #pragma unroll
                     for (int x = 0; x < D; x++) {
@@ -345,6 +359,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
                     u32 r = hi - t;
                     return hi < t ? r + Q : r;
                 };
+                if (!LAT || k < N)
 #pragma unroll
                 for (int g0 = 0; g0 < G; g0 += GB) {
                     u32 xd[GB][D], m1[GB], m2[GB], dl0[GB], dl1[GB];
@@ -420,9 +435,9 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
         // c = INTT(acc_eval) (identical mod Q because the transform is linear), read from its own region and
         // transposed through the free digit region j, so acc_eval survives for the next step and c is dead between
         // the digit extraction and this point (32 registers less through phases 1 and 2).
-        {
+        if (!helper) {
             u32 v[32];
-            u32* reg = myD + (size_t)j * RS;
+            u32* reg = myD + (size_t)(LAT ? j + 2 * lw : j) * RS;   // scratch: this warp's own digit region
             const int Tv = TPN - 1 - T;
             {
                 const uint4* p4 = reinterpret_cast<const uint4*>((SKIP ? myD + (size_t)(2 * (DK - 1) + j) * RS : reg) + 36 * Tv);
@@ -455,7 +470,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_cggi32_kernel(con
     }
 
     // ---- extraction: a'(X) = a(X^-1), b = acc_b[0] (+ Q8 for gates) ---------------------------------------------
-    if (live) {
+    if (live && (!LAT || lw == 0)) {
         if (C.write_acc) {
             u64* dst = C.acc_io + (size_t)ct * 2 * N;
 #pragma unroll
@@ -605,6 +620,19 @@ static cudaError_t launch_t2(const CGGI32Args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// latency layout: one ciphertext per CTA, 2*DK warps
+template <int LOGN, int DK>
+static cudaError_t launch_lat(const CGGI32Args& a, cudaStream_t s) {
+    using K = KCfg<LOGN, DK, 1>;
+    const size_t smem = K::smem_bytes((int)a.c.n);
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, 1, true, false, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    br_cggi32_kernel<LOGN, DK, 1, true, false, true><<<a.c.batch, 2 * DK * K::TPN, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 template <int LOGN, int DK, int G>
 static cudaError_t launch_t(const CGGI32Args& a, cudaStream_t s, bool skip) {
     // TMA key streaming exists for the headline shape (N = 1024, four digits, four ciphertexts per CTA, top digit
@@ -645,6 +673,9 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
         // latency-bound instead and runs as CTAs of 2 ciphertexts (4 warps): a rotation step finishes sooner because
         // fewer warps compete for the SM's multiplier pipe.  Measured per bootstrap at batch <= 296 on one B200: 5.77 ms
         // (4 per CTA), 4.47 ms (2 per CTA), 5.1 ms (1 per CTA: one warp per scheduler, latency-bound -- not instantiated).
+        // At most one ciphertext per SM: the latency layout (one warp per digit polynomial), see the kernel header.
+        if (dk == 4 && t.skip_top && ((group == 0 && c.batch <= sm_count) || group == 1))
+            return launch_lat<10, 4>(a, s);
         if (group == 0 && dk == 4 && c.batch <= 2 * sm_count)
             group = 2;
         if (group == 0) group = (dk <= 4) ? 4 : 2;
