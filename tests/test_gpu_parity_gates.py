@@ -156,3 +156,36 @@ def test_host_buffer_pipeline_matches_single_shot(keyset, rng, monkeypatch):
         idx = np.r_[0:3, 4094:4099, batch - 3:batch]
         want = ks.port.eval_bin_gate(ks.bk, ks.ksk, po.GATES[gate], c1[idx], c2[idx], q)
         assert np.array_equal(piped[idx], want), gate
+
+
+def test_std128_cta_shapes_agree(keyset, rng):
+    """The three CTA shapes of the STD128 CGGI kernel -- 4 ciphertexts per CTA (throughput), 2 per CTA (batches that
+    cannot fill the SMs) and the latency layout (one ciphertext per CTA, one warp per digit polynomial plus two
+    pointwise helper warps; picked automatically for batches <= one ciphertext per SM) -- produce the same bits, equal
+    to the oracle, on ragged batches with extreme mask values."""
+    ks = keyset("std128_ginx")
+    q, n = ks.p.q, ks.p.n
+    c1 = rng.integers(0, q, (13, n + 1), dtype=np.uint64)
+    c2 = rng.integers(0, q, (13, n + 1), dtype=np.uint64)
+    c1[0, :n], c2[0, :n] = 0, 0                       # every rotation exponent zero
+    c1[1, :n], c2[1, :n] = q - 1, 0                   # exponent 2N/q everywhere
+    c1[2, :n], c2[2, :n] = q // 2, 0                  # exponent N: X^N = -1
+    g = ks.gpu()
+    outs = {}
+    try:
+        for grp in (0, 1, 2, 4):
+            g.set_option("group", grp)
+            outs[grp] = {gate: g.EvalBinGate(gate, c1, c2) for gate in ("NAND", "XNOR")}
+    finally:
+        g.set_option("group", 0)
+    for grp in (1, 2, 4):
+        for gate in ("NAND", "XNOR"):
+            assert np.array_equal(outs[grp][gate], outs[0][gate]), (grp, gate)
+    want = ks.port.eval_bin_gate(ks.bk, ks.ksk, po.GATES["NAND"], c1[:4], c2[:4], q)
+    assert np.array_equal(outs[1]["NAND"][:4], want)
+    # a single ciphertext, and a batch just above one-per-SM (falls back to 2 per CTA)
+    one = g.EvalBinGate("NAND", c1[:1], c2[:1])
+    assert np.array_equal(one, outs[0]["NAND"][:1])
+    big1 = np.tile(c1, (12, 1))[:150]
+    big2 = np.tile(c2, (12, 1))[:150]
+    assert np.array_equal(g.EvalBinGate("NAND", big1, big2), np.tile(outs[0]["NAND"], (12, 1))[:150])

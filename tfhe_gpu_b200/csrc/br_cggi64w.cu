@@ -534,7 +534,9 @@ cudaError_t launch_w(const CGGI64WArgs& a, cudaStream_t s) {
 bool cggi64w_supported(const tfhe_b200_params& p) {
     if (!cggi64_supported(p) || p.numDigitsToThrow != 0)
         return false;
-    return p.digitsG == 2 || p.digitsG == 3;
+    // 4 digits: 8 digit regions of 16 KB leave room for ONE ciphertext per CTA (8 warps) -- still twice the warps of the
+    // 64 x 32 layout, which is limited to one ciphertext per CTA as well at this size
+    return p.digitsG == 2 || p.digitsG == 3 || p.digitsG == 4;
 }
 
 // twC: [15][128][2]; twB: [16][8][2]; twU: [fwd | negated inv][15][2]
@@ -601,6 +603,8 @@ cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStr
         return launch_w<2, 2>(a, s);
     if (c.digitsKept == 3)
         return launch_w<3, 2>(a, s);
+    if (c.digitsKept == 4)
+        return launch_w<4, 1>(a, s);
     return cudaErrorInvalidConfiguration;
 }
 
