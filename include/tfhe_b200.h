@@ -87,7 +87,11 @@ size_t tfhe_b200_bk_words(const tfhe_b200_params* params);
 size_t tfhe_b200_ksk_words(const tfhe_b200_params* params);
 /* name of the blind-rotation kernel variant the handle dispatches to ("cggi_u32_ntt32", "generic_u64", ...) */
 const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h);
-/* tuning knob: force the generic kernel (used by tests to cross-check the two implementations) */
+/* tuning knobs (tests and measurements; results never depend on them):
+ *   "force_generic" = 1  run the generic kernel instead of the specialised one (cross-check of the two implementations)
+ *   "group"              ciphertexts per CTA of the specialised CGGI kernels: 0 = automatic (throughput shape for large
+ *                        batches, latency shapes for batches that cannot fill the SMs), 4 / 2 = fixed, 1 = one
+ *                        ciphertext per CTA (32-bit rings: the latency layout, one warp per digit polynomial) */
 int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value);
 
 /* --------------------------------------------------------------------------------------------------------

@@ -235,3 +235,24 @@ def test_large_precision_logq29(keyset):
             total += ks.port.decrypt_batch(ks.sk, np.ascontiguousarray(gd[j:j + 1, k, :]), int(mod), pk)[0] * scale
             scale *= pk
         assert total % P == m
+
+
+@pytest.mark.parametrize("name", ["toy_func12", "toy_sign17"])
+def test_cggi64_cta_shapes_agree(keyset, rng, name):
+    """The wide 64-bit kernel runs two ciphertexts per CTA (throughput) or one (batches of at most one ciphertext per SM,
+    picked automatically): same bits from both shapes and from the generic kernel, on a ragged batch."""
+    ks = keyset(name)
+    p = ks.p
+    g = ks.gpu()
+    assert g.kernel_variant.startswith("cggi_u64_ntt16x128")
+    ct = rng.integers(0, p.q, (7, p.n + 1), dtype=np.uint64)
+    tab = rng.integers(0, p.q, p.q, dtype=np.uint64)
+    outs = {}
+    try:
+        for grp in (0, 1, 2):
+            g.set_option("group", grp)
+            outs[grp] = g.BootstrapFunc(ct, p.q, tab, p.q)
+    finally:
+        g.set_option("group", 0)
+    assert np.array_equal(outs[1], outs[2]) and np.array_equal(outs[0], outs[2])
+    assert np.array_equal(outs[1], ks.port.bootstrap_func(ks.bk, ks.ksk, ct, p.q, tab, p.q))

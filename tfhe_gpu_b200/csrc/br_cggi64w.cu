@@ -577,7 +577,7 @@ void cggi64w_build_tables(const tfhe_b200_params& p, std::vector<u64>& twU, std:
             }
 }
 
-cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s) {
+cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s, int sm_count, int group) {
     CGGI64WArgs a;
     a.c = c;
     a.mod = t.mod;
@@ -599,10 +599,13 @@ cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStr
     const u64 ninv = h_powmod((u64)N, t.mod.Q - 2, t.mod.Q);
     a.ninvM = to_mont<u64>(ninv, t.mod);
     a.kfix = h_mulmod((u64)(pw % t.mod.Q), ninv, t.mod.Q);
+    // a batch of at most one ciphertext per SM is latency-bound: one ciphertext per CTA (8 warps instead of 16 competing
+    // for the SM) finishes a rotation step sooner; `group` = 1 / 2 forces a shape (tests, measurements)
+    const bool one = group == 1 || (group == 0 && sm_count > 0 && c.batch <= sm_count);
     if (c.digitsKept == 2)
-        return launch_w<2, 2>(a, s);
+        return one ? launch_w<2, 1>(a, s) : launch_w<2, 2>(a, s);
     if (c.digitsKept == 3)
-        return launch_w<3, 2>(a, s);
+        return one ? launch_w<3, 1>(a, s) : launch_w<3, 2>(a, s);
     if (c.digitsKept == 4)
         return launch_w<4, 1>(a, s);
     return cudaErrorInvalidConfiguration;

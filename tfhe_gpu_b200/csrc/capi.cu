@@ -779,7 +779,7 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
     else if (h->have_cggi64w && !h->force_generic && !getenv("TFHE_B200_C64_NARROW")) {
         CGGI64WTables t;
         t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twC = d.twCw; t.twB = d.twBw; t.twU = d.twUw;
-        CUDA_TRY(launch_br_cggi64w(c, t, d.stream));
+        CUDA_TRY(launch_br_cggi64w(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_cggi64 && !h->force_generic) {
         CGGI64Tables t;

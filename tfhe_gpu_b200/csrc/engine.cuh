@@ -98,7 +98,7 @@ struct CGGI64WTables {
 };
 bool cggi64w_supported(const tfhe_b200_params& p);
 void cggi64w_build_tables(const tfhe_b200_params& p, std::vector<u64>& twU, std::vector<u64>& twB, std::vector<u64>& twC);
-cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s);
+cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s, int sm_count = 0, int group = 0);
 
 // GPU key generation (keygen.cu)
 int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const signed char* sk_ring, u64 seed, int device,
