@@ -33,7 +33,12 @@ def test_std128_ap_specialised_and_generic_kernels_agree(keyset, rng):
     c2[0, :n] = 0                                            # every refresh digit is zero: all steps sit out
     g = ks.gpu()
     assert g.kernel_variant.startswith("dm_u32")
-    a = g.EvalBinGate("NAND", c1, c2)
+    a = g.EvalBinGate("NAND", c1, c2)              # 21 ciphertexts: the latency layout (one ciphertext per CTA)
+    g.set_option("group", 4)                       # the throughput shape (4 ciphertexts per CTA)
+    try:
+        assert np.array_equal(g.EvalBinGate("NAND", c1, c2), a)
+    finally:
+        g.set_option("group", 0)
     g.set_option("force_generic", 1)
     try:
         b = g.EvalBinGate("NAND", c1, c2)

@@ -33,10 +33,17 @@ struct DM32Args {
     u32 Q2, dig_off, dig_add, ninvM, zero;
 };
 
-template <int LOGN, int DK, int G>
-__global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const __grid_constant__ DM32Args A) {
+// LAT = true: latency layout for batches of at most one ciphertext per SM (same idea as br_cggi32.cu): G = 1, 2*DK
+// warps; warps 0 .. 2*(DK-1)-1 own one digit polynomial each (the DK-1 warps of a component run the inverse transform
+// redundantly, extract their own digit, do ONE forward transform), the last pair only helps in the pointwise stage.
+template <int LOGN, int DK, int G, bool LAT = false>
+__global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
+    br_dm32_kernel(const __grid_constant__ DM32Args A) {
     using K = KCfg<LOGN, DK, G>;
-    constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS, NT = K::NT;
+    constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS;
+    constexpr int NT = LAT ? 2 * DK * TPN : K::NT;
+    constexpr int CT_THREADS = LAT ? NT : 2 * TPN;   // threads that serve one ciphertext
+    static_assert(!LAT || G == 1, "latency layout: one ciphertext per CTA");
     constexpr int P = D / 2;   // uint4 planes per slot (2*D words)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32* Dsm = reinterpret_cast<u32*>(smem_raw);              // [G][D][RS]
@@ -47,7 +54,9 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
     const u32 n = C.n;
     const u32 steps = n * C.digitsR;
     const int tid = threadIdx.x;
-    const int g = tid / (2 * TPN), j = (tid / TPN) & 1, T = tid % TPN;
+    const int g = LAT ? 0 : tid / (2 * TPN), j = (tid / TPN) & 1, T = tid % TPN;
+    const int lw = LAT ? tid / (2 * TPN) : 0;     // latency layout: digit polynomial of this warp
+    const bool helper = LAT && lw == DK - 1;      // latency layout: pointwise-only warps
     const int ct = blockIdx.x * G + g;
     const bool live = ct < C.batch;
     const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
@@ -55,8 +64,8 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
     {
         // rgsw-acc-dm.cpp:102-109: aI = (q - a_i) mod q with q = the scheme's q (NOT the ciphertext modulus)
         const u32 q = (u32)C.q_lwe;
-        const int lt = tid % (2 * TPN);
-        for (u32 i = lt; i < n; i += 2 * TPN) {
+        const int lt = tid % CT_THREADS;
+        for (u32 i = lt; i < n; i += CT_THREADS) {
             u32 aI = (q - (u32)(lwe[i] % q)) % q;
             for (u32 k = 0; k < C.digitsR; k++, aI /= C.baseR) {
                 u32 a0 = aI % C.baseR;
@@ -129,7 +138,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
     };
 
     // evaluation-domain accumulator (scaled by N^-1, see br_cggi32.cu) of the initial accumulator -> top-digit region
-    {
+    if (!LAT || lw == 0) {
         u32 v[32];
 #pragma unroll
         for (int r = 0; r < 32; r++)
@@ -155,10 +164,10 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
 
     // The ciphertexts of a CTA share nothing but the tables: from here on every (ciphertext) pair of warps runs on its
     // own, synchronised by a named barrier, and a ciphertext whose refresh digit is zero skips the step entirely.
-    const int lt = tid % (2 * TPN);                 // thread within the ciphertext
+    const int lt = tid % CT_THREADS;                // thread within the ciphertext
     const int bar_id = 1 + g;
-    auto ct_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(2 * TPN) : "memory"); };
-    constexpr int MIT = N / (2 * TPN);              // pointwise iterations per thread (slots lt + 2*TPN*it)
+    auto ct_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(CT_THREADS) : "memory"); };
+    constexpr int MIT = N / CT_THREADS;             // pointwise iterations per thread (slots lt + CT_THREADS*it)
     u32* top0 = myD + (size_t)(2 * (DK - 1)) * RS;  // evaluation-domain accumulator rows (a, b)
 
     for (u32 s = 0; s < steps; s++) {
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
             cur[x] = __ldg(kp + (size_t)x * N);
         // ---- phase 1: digits 0..DK-2 of component j -> forward NTT -------------------------------------------------
 #pragma unroll 1
-        for (int l = 0; l < DK - 1; l++) {
+        for (int l = (LAT ? lw : 0); l < (LAT ? (helper ? lw : lw + 1) : DK - 1); l++) {
             u32 v[32];
             const u32 sh = gBits * l;
 #pragma unroll
@@ -203,9 +212,9 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
             if (it + 1 < MIT) {
 #pragma unroll
                 for (int x = 0; x < P; x++)
-                    nxt[x] = __ldg(kp + (size_t)x * N + (size_t)(it + 1) * 2 * TPN);
+                    nxt[x] = __ldg(kp + (size_t)x * N + (size_t)(it + 1) * CT_THREADS);
             }
-            const u32 pk = pos_of(lt + it * 2 * TPN);
+            const u32 pk = pos_of(lt + it * CT_THREADS);
             u32 xd[D];
 #pragma unroll
             for (int l = 0; l < D; l++)
@@ -238,9 +247,9 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
         ct_sync();
 
         // ---- phase 3: c = INTT(result), read from the accumulator row, through row j as scratch ---------------------
-        {
+        if (!helper) {
             u32 v[32];
-            u32* reg = myD + (size_t)j * RS;
+            u32* reg = myD + (size_t)(LAT ? j + 2 * lw : j) * RS;   // scratch: this warp's own digit region
             const int Tv = TPN - 1 - T;
             load_B(v, top0 + (size_t)j * RS, Tv);
             inv_passB<PB>(v, tw, twp, Q, Q2, A.zero);
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(KCfg<LOGN, DK, G>::NT, 1) br_dm32_kernel(const
         }
     }
 
-    if (live) {
+    if (live && (!LAT || lw == 0)) {
         if (C.write_acc) {
             u64* dst = C.acc_io + (size_t)ct * 2 * N;
 #pragma unroll
@@ -300,7 +309,7 @@ bool dm32_supported(const tfhe_b200_params& p) {
     return cggi32_skip_top_ok(p);
 }
 
-cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s) {
+cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group) {
     DM32Args a;
     a.c = c;
     a.mod = t.mod;
@@ -327,6 +336,16 @@ cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_
     cudaError_t e = cudaFuncSetAttribute(br_dm32_kernel<10, 4, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
+    if (group == 1 || (group == 0 && sm_count > 0 && c.batch <= sm_count)) {
+        // at most one ciphertext per SM: latency layout (one ciphertext per CTA, 8 warps)
+        using K1 = KCfg<10, 4, 1>;
+        const size_t smem1 = (size_t)K1::D * K1::RS * 4 + (size_t)c.n * c.digitsR * 4 + 64;
+        e = cudaFuncSetAttribute(br_dm32_kernel<10, 4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess)
+            return e;
+        br_dm32_kernel<10, 4, 1, true><<<c.batch, 2 * 4 * K1::TPN, smem1, s>>>(a);
+        return cudaGetLastError();
+    }
     const int grid = (c.batch + G - 1) / G;
     br_dm32_kernel<10, 4, G><<<grid, K::NT, smem, s>>>(a);
     return cudaGetLastError();

@@ -774,7 +774,7 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
         CGGI32Tables t;
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB;
         t.skip_top = true;
-        CUDA_TRY(launch_br_dm32(c, t, d.stream));
+        CUDA_TRY(launch_br_dm32(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_cggi64w && !h->force_generic && !getenv("TFHE_B200_C64_NARROW")) {
         CGGI64WTables t;

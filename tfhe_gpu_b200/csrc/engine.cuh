@@ -70,7 +70,7 @@ bool cggi32_skip_top_ok(const tfhe_b200_params& p);
 bool cggi_skip_top_wrapfix_ok(const tfhe_b200_params& p);   // top digit may wrap but the 64-bit kernel can repair it
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group);
 bool dm32_supported(const tfhe_b200_params& p);
-cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s);
+cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count = 0, int group = 0);
 void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::vector<u32>& twB);
 
 // optimised CGGI kernel for the 54-bit sets, N = 2048 (br_cggi64.cu)
