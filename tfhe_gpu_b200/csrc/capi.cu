@@ -72,6 +72,7 @@ struct Dev {
     u64* twBw = nullptr;
     u64* twUw = nullptr;
     void* ksk = nullptr;
+    u64* ks_partial = nullptr;   // column-sum accumulator of split key switches (batches below one ciphertext per SM)
     Arena ws;
 };
 
@@ -422,7 +423,7 @@ static int free_dev(Dev& d, bool borrowed_streams = false) {
         d.stream = d.xfer_in = d.xfer_out = nullptr;
     if (d.stream)
         cudaStreamSynchronize(d.stream);
-    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twU64, d.twCw, d.twBw, d.twUw, d.twB, d.ksk, d.ws.base};
+    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twU64, d.twCw, d.twBw, d.twUw, d.twB, d.ksk, d.ks_partial, d.ws.base};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -532,6 +533,7 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
             cudaDeviceProp prop;
             CUDA_TRY(cudaGetDeviceProperties(&prop, d.id));
             d.sm_count = prop.multiProcessorCount;
+            CUDA_TRY(cudaMalloc((void**)&d.ks_partial, mkmswitch_partial_bytes(h->row_stride, d.sm_count)));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_in, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_out, cudaStreamNonBlocking));
@@ -812,6 +814,7 @@ static int mkmswitch_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* ext,
     a.N = p.N; a.n = p.n; a.baseKS = p.baseKS; a.dKS = p.dKS; a.row_stride = h->row_stride;
     a.Q = p.Q; a.qKS = p.qKS; a.fmod = fmod; a.batch = batch; a.ext = ext; a.out = out;
     a.ksk = d.ksk; a.ksk_bytes = h->ksk_bytes;
+    a.partial = d.ks_partial; a.sm_count = d.sm_count;
     CUDA_TRY(launch_mkmswitch(a, d.stream));
     if (launches)
         (*launches)++;

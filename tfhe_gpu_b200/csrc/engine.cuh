@@ -114,7 +114,14 @@ struct KSArgs {
     u64* out;          // [batch][n+1] mod fmod
     const void* ksk;   // [N][baseKS][dKS][row_stride] entries of ksk_bytes each
     int ksk_bytes;     // 2, 4 or 8
+    // small batches: the N*dKS gathered rows of a ciphertext are split over `splits` CTAs that add their column sums
+    // into `partial` ([batch][row_stride] u64, zeroed by the launcher); a second tiny kernel finishes (b - sum, ModSwitch)
+    u64* partial = nullptr;
+    int splits = 1;
+    int sm_count = 0;
 };
+// bytes of KSArgs::partial scratch needed for split launches of up to max_batch ciphertexts
+size_t mkmswitch_partial_bytes(u32 row_stride, int max_batch);
 cudaError_t launch_mkmswitch(const KSArgs& a, cudaStream_t s);
 
 // out = ((sx*x + sy*y) mod m, b += cb) then optionally reduced mod m2 (SetModulus); words = n+1

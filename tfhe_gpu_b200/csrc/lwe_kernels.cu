@@ -27,7 +27,6 @@ template <typename TK, int VW, int S>
 __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 N = A.N, n = A.n, dKS = A.dKS;
-    const u32 rows = N * dKS;
     unsigned long long* colsum = reinterpret_cast<unsigned long long*>(smem_raw);  // [row_stride]
     unsigned short* dig = reinterpret_cast<unsigned short*>(colsum + A.row_stride);  // [rows]
     __shared__ u64 b_ms;
@@ -35,9 +34,14 @@ __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG
     const int ct = blockIdx.x;
     const u64* ext = A.ext + (size_t)ct * (N + 1);
     const double dQ = (double)A.Q, dqKS = (double)A.qKS;
+    // this CTA's share of the mask entries (all of them unless the launch is split)
+    const u32 ipc = (N + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * ipc, i_hi = min(N, i_lo + ipc);
+    const u32 r_lo = i_lo * dKS, r_hi = i_hi * dKS;
 
     // ModSwitch Q -> qKS and base-baseKS digit extraction of the N mask entries
-    for (u32 i = threadIdx.x; i <= N; i += blockDim.x) {
+    for (u32 i = i_lo + threadIdx.x; i <= N; i += blockDim.x) {
+        if (i >= i_hi && i != N)
+            continue;
         u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
         if (i == N)
             b_ms = v;
@@ -48,6 +52,8 @@ __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG
             }
         }
     }
+    if (threadIdx.x == 0 && A.splits > 1)   // the loop above reaches i == N only from some threads' strides
+        b_ms = round_qQ(ext[N], A.qKS, dqKS, dQ);
     for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
         colsum[k] = 0;
     __syncthreads();
@@ -73,7 +79,8 @@ __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG
         // rows per trip: 4 measured 20.1 ms per 2048 ciphertexts of the 54-bit table (1 row: 29.1 ms; 8 rows with a
         // 255-register budget: 38.8 ms, occupancy lost)
         constexpr int U = S <= 3 ? 4 : (S == 4 ? 2 : 1);
-        u32 r = rg;
+        const u32 rows = r_hi;
+        u32 r = r_lo + rg;
         for (; r + (U - 1) * RG < rows; r += U * RG) {
             const KVec<TK, VW>* rp[U];
 #pragma unroll
@@ -124,6 +131,12 @@ __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG
         }
     }
     __syncthreads();
+    if (A.splits > 1) {   // partial column sums -> global accumulator; mkmswitch_finish_kernel completes the switch
+        unsigned long long* part = reinterpret_cast<unsigned long long*>(A.partial) + (size_t)ct * A.row_stride;
+        for (u32 k = threadIdx.x; k <= n; k += blockDim.x)
+            atomicAdd(part + k, colsum[k]);
+        return;
+    }
 
     // a_out = 0 - sum, b_out = b - sum (mod qKS), then ModSwitch qKS -> fmod
     u64* out = A.out + (size_t)ct * (n + 1);
@@ -153,7 +166,7 @@ static cudaError_t launch_ks_t(const KSArgs& a, cudaStream_t s) {
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
         if (e != cudaSuccess)                                                                                    \
             return e;                                                                                            \
-        mkmswitch_kernel<TK, VW, SS><<<a.batch, threads, smem, s>>>(a, TC, RG);                                  \
+        mkmswitch_kernel<TK, VW, SS><<<dim3(a.batch, a.splits), threads, smem, s>>>(a, TC, RG);                  \
     }
     if (S == 1)
         KS_LAUNCH(1)
@@ -182,7 +195,6 @@ template <int S>
 __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int TC, int RG) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 N = A.N, n = A.n, dKS = A.dKS;
-    const u32 rows = N * dKS;
     u32* colsum = reinterpret_cast<u32*>(smem_raw);           // [row_stride]
     u32* rowoff = colsum + A.row_stride;                      // [rows] table row index of every gathered row
     __shared__ u64 b_ms;
@@ -190,18 +202,18 @@ __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int T
     const int ct = blockIdx.x;
     const u64* ext = A.ext + (size_t)ct * (N + 1);
     const double dQ = (double)A.Q, dqKS = (double)A.qKS;
-    for (u32 i = threadIdx.x; i <= N; i += blockDim.x) {
+    const u32 ipc = (N + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * ipc, i_hi = min(N, i_lo + ipc);
+    const u32 r_lo = i_lo * dKS, rows = i_hi * dKS;
+    for (u32 i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
         u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
-        if (i == N)
-            b_ms = v;
-        else {
-            for (u32 j = 0; j < dKS; j++) {
-                u32 a0 = (u32)(v % A.baseKS);
-                v /= A.baseKS;
-                rowoff[i * dKS + j] = (i * A.baseKS + a0) * dKS + j;
-            }
+        for (u32 j = 0; j < dKS; j++) {
+            u32 a0 = (u32)(v % A.baseKS);
+            v /= A.baseKS;
+            rowoff[i * dKS + j] = (i * A.baseKS + a0) * dKS + j;
         }
     }
+    if (threadIdx.x == 0)
+        b_ms = round_qQ(ext[N], A.qKS, dqKS, dQ);
     for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
         colsum[k] = 0;
     __syncthreads();
@@ -216,8 +228,8 @@ __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int T
 #pragma unroll
             for (int v = 0; v < 4; v++)
                 lo[s][v] = hi[s][v] = 0;
-        // rows rg, rg + RG, ... in groups of four
-        u32 r = rg;
+        // rows r_lo + rg, r_lo + rg + RG, ... in groups of four
+        u32 r = r_lo + rg;
         for (; r + 3 * RG < rows; r += 4 * RG) {
             const u32 o0 = rowoff[r], o1 = rowoff[r + RG], o2 = rowoff[r + 2 * RG], o3 = rowoff[r + 3 * RG];
 #pragma unroll
@@ -265,6 +277,12 @@ __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int T
         }
     }
     __syncthreads();
+    if (A.splits > 1) {
+        unsigned long long* part = reinterpret_cast<unsigned long long*>(A.partial) + (size_t)ct * A.row_stride;
+        for (u32 k = threadIdx.x; k <= n; k += blockDim.x)
+            atomicAdd(part + k, (unsigned long long)colsum[k]);
+        return;
+    }
     u64* out = A.out + (size_t)ct * (n + 1);
     const double dfmod = (double)A.fmod;
     for (u32 k = threadIdx.x; k <= n; k += blockDim.x) {
@@ -290,13 +308,62 @@ static cudaError_t launch_ks_packed16(const KSArgs& a, cudaStream_t s) {
                                          (int)smem);
     if (e != cudaSuccess)
         return e;
-    mkmswitch_packed16_kernel<1><<<a.batch, threads, smem, s>>>(a, TC, RG);
+    mkmswitch_packed16_kernel<1><<<dim3(a.batch, a.splits), threads, smem, s>>>(a, TC, RG);
     return cudaGetLastError();
 }
 
-cudaError_t launch_mkmswitch(const KSArgs& a, cudaStream_t s) {
-    if (a.batch <= 0)
+// second half of a split key switch: a_out = 0 - sum, b_out = MS(b) - sum (mod qKS), then ModSwitch qKS -> fmod
+__global__ void mkmswitch_finish_kernel(KSArgs A) {
+    const u32 n = A.n;
+    const double dQ = (double)A.Q, dqKS = (double)A.qKS, dfmod = (double)A.fmod;
+    const size_t total = (size_t)A.batch * (n + 1);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t ct = idx / (n + 1);
+        const u32 k = (u32)(idx - ct * (n + 1));
+        const u64 sum = A.partial[ct * A.row_stride + k] % A.qKS;
+        const u64 base = (k == n) ? round_qQ(A.ext[ct * (A.N + 1) + A.N], A.qKS, dqKS, dQ) : 0;
+        const u64 v = base >= sum ? base - sum : base + A.qKS - sum;
+        A.out[idx] = round_qQ(v, A.fmod, dfmod, dqKS);
+    }
+}
+
+size_t mkmswitch_partial_bytes(u32 row_stride, int max_batch) {
+    return (size_t)max_batch * row_stride * 8;
+}
+
+static cudaError_t launch_mkmswitch_main(const KSArgs& a, cudaStream_t s);
+
+cudaError_t launch_mkmswitch(const KSArgs& a0, cudaStream_t s) {
+    if (a0.batch <= 0)
         return cudaSuccess;
+    KSArgs a = a0;
+    // One CTA per ciphertext walks N*dKS dependent gather trips; a batch that leaves SMs idle is split so that about two
+    // CTAs per SM share the rows of each ciphertext (the column sums meet in a global accumulator).
+    a.splits = 1;
+    if (a.partial && a.sm_count > 0 && a.batch < a.sm_count && !getenv("TFHE_B200_NO_KSSPLIT")) {
+        int sp = (2 * a.sm_count + a.batch - 1) / a.batch;
+        if (sp > 16)
+            sp = 16;
+        if (sp > (int)a.N)
+            sp = (int)a.N;
+        a.splits = sp < 2 ? 1 : sp;
+    }
+    if (a.splits == 1) {
+        a.partial = nullptr;
+        return launch_mkmswitch_main(a, s);
+    }
+    cudaError_t e = cudaMemsetAsync(a.partial, 0, mkmswitch_partial_bytes(a.row_stride, a.batch), s);
+    if (e != cudaSuccess)
+        return e;
+    e = launch_mkmswitch_main(a, s);
+    if (e != cudaSuccess)
+        return e;
+    const size_t total = (size_t)a.batch * (a.n + 1);
+    mkmswitch_finish_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_mkmswitch_main(const KSArgs& a, cudaStream_t s) {
     // packed path: u16 entries, 4 rows cannot overflow a 16-bit lane, 32-bit column sums cannot overflow
     if (a.ksk_bytes == 2 && a.qKS <= (1u << 14) && (u64)a.N * a.dKS * a.qKS < (1ULL << 32) && !getenv("TFHE_B200_NO_KSPACK")) {
         cudaError_t e = launch_ks_packed16(a, s);
