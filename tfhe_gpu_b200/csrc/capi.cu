@@ -533,7 +533,7 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
             cudaDeviceProp prop;
             CUDA_TRY(cudaGetDeviceProperties(&prop, d.id));
             d.sm_count = prop.multiProcessorCount;
-            CUDA_TRY(cudaMalloc((void**)&d.ks_partial, mkmswitch_partial_bytes(h->row_stride, d.sm_count)));
+            CUDA_TRY(cudaMalloc((void**)&d.ks_partial, mkmswitch_partial_bytes(h->row_stride, 2 * d.sm_count)));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_in, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_out, cudaStreamNonBlocking));

@@ -23,7 +23,7 @@ struct alignas(16) KVec {
     TK v[VW];
 };
 
-template <typename TK, int VW, int S>
+template <typename TK, int VW, int S, bool SPLIT>
 __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 N = A.N, n = A.n, dKS = A.dKS;
@@ -35,12 +35,14 @@ __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG
     const u64* ext = A.ext + (size_t)ct * (N + 1);
     const double dQ = (double)A.Q, dqKS = (double)A.qKS;
     // this CTA's share of the mask entries (all of them unless the launch is split)
-    const u32 ipc = (N + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * ipc, i_hi = min(N, i_lo + ipc);
+    // (SPLIT = false is the plain one-CTA-per-ciphertext kernel: the range is everything and folds away)
+    const u32 ipc = SPLIT ? (N + gridDim.y - 1) / gridDim.y : N, i_lo = SPLIT ? blockIdx.y * ipc : 0;
+    const u32 i_hi = SPLIT ? min(N, i_lo + ipc) : N;
     const u32 r_lo = i_lo * dKS, r_hi = i_hi * dKS;
 
     // ModSwitch Q -> qKS and base-baseKS digit extraction of the N mask entries
     for (u32 i = i_lo + threadIdx.x; i <= N; i += blockDim.x) {
-        if (i >= i_hi && i != N)
+        if (SPLIT && i >= i_hi && i != N)
             continue;
         u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
         if (i == N)
@@ -52,8 +54,6 @@ __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG
             }
         }
     }
-    if (threadIdx.x == 0 && A.splits > 1)   // the loop above reaches i == N only from some threads' strides
-        b_ms = round_qQ(ext[N], A.qKS, dqKS, dQ);
     for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
         colsum[k] = 0;
     __syncthreads();
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(512) mkmswitch_kernel(KSArgs A, int TC, int RG
         }
     }
     __syncthreads();
-    if (A.splits > 1) {   // partial column sums -> global accumulator; mkmswitch_finish_kernel completes the switch
+    if (SPLIT) {   // partial column sums -> global accumulator; mkmswitch_finish_kernel completes the switch
         unsigned long long* part = reinterpret_cast<unsigned long long*>(A.partial) + (size_t)ct * A.row_stride;
         for (u32 k = threadIdx.x; k <= n; k += blockDim.x)
             atomicAdd(part + k, colsum[k]);
@@ -162,11 +162,11 @@ static cudaError_t launch_ks_t(const KSArgs& a, cudaStream_t s) {
     size_t smem = (size_t)a.row_stride * 8 + (size_t)a.N * a.dKS * 2 + 16;
 #define KS_LAUNCH(SS)                                                                                            \
     {                                                                                                            \
-        cudaError_t e = cudaFuncSetAttribute(mkmswitch_kernel<TK, VW, SS>,                                       \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        auto kern = a.splits > 1 ? mkmswitch_kernel<TK, VW, SS, true> : mkmswitch_kernel<TK, VW, SS, false>;     \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
         if (e != cudaSuccess)                                                                                    \
             return e;                                                                                            \
-        mkmswitch_kernel<TK, VW, SS><<<dim3(a.batch, a.splits), threads, smem, s>>>(a, TC, RG);                  \
+        kern<<<dim3(a.batch, a.splits), threads, smem, s>>>(a, TC, RG);                                          \
     }
     if (S == 1)
         KS_LAUNCH(1)
@@ -195,6 +195,7 @@ template <int S>
 __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int TC, int RG) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 N = A.N, n = A.n, dKS = A.dKS;
+    const u32 rows = N * dKS;
     u32* colsum = reinterpret_cast<u32*>(smem_raw);           // [row_stride]
     u32* rowoff = colsum + A.row_stride;                      // [rows] table row index of every gathered row
     __shared__ u64 b_ms;
@@ -202,7 +203,107 @@ __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int T
     const int ct = blockIdx.x;
     const u64* ext = A.ext + (size_t)ct * (N + 1);
     const double dQ = (double)A.Q, dqKS = (double)A.qKS;
-    const u32 ipc = (N + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * ipc, i_hi = min(N, i_lo + ipc);
+    for (u32 i = threadIdx.x; i <= N; i += blockDim.x) {
+        u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
+        if (i == N)
+            b_ms = v;
+        else {
+            for (u32 j = 0; j < dKS; j++) {
+                u32 a0 = (u32)(v % A.baseKS);
+                v /= A.baseKS;
+                rowoff[i * dKS + j] = (i * A.baseKS + a0) * dKS + j;
+            }
+        }
+    }
+    for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
+        colsum[k] = 0;
+    __syncthreads();
+
+    const int tc = threadIdx.x % TC, rg = threadIdx.x / TC;
+    const u32 CV = A.row_stride / 8;
+    const uint4* tab = reinterpret_cast<const uint4*>(A.ksk);
+    if (rg < RG) {
+        u32 lo[S][4], hi[S][4];
+#pragma unroll
+        for (int s = 0; s < S; s++)
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+                lo[s][v] = hi[s][v] = 0;
+        // rows rg, rg + RG, ... in groups of four
+        u32 r = rg;
+        for (; r + 3 * RG < rows; r += 4 * RG) {
+            const u32 o0 = rowoff[r], o1 = rowoff[r + RG], o2 = rowoff[r + 2 * RG], o3 = rowoff[r + 3 * RG];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const u32 cv = tc + s * TC;
+                if (cv < CV) {
+                    const uint4 a = __ldg(tab + (size_t)o0 * CV + cv), b = __ldg(tab + (size_t)o1 * CV + cv);
+                    const uint4 c = __ldg(tab + (size_t)o2 * CV + cv), d = __ldg(tab + (size_t)o3 * CV + cv);
+                    const u32 p[4] = {a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y, a.z + b.z + c.z + d.z,
+                                      a.w + b.w + c.w + d.w};
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        lo[s][v] += p[v] & 0xffffu;
+                        hi[s][v] += p[v] >> 16;
+                    }
+                }
+            }
+        }
+        for (; r < rows; r += RG) {
+            const u32 o0 = rowoff[r];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const u32 cv = tc + s * TC;
+                if (cv < CV) {
+                    const uint4 a = __ldg(tab + (size_t)o0 * CV + cv);
+                    const u32 p[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        lo[s][v] += p[v] & 0xffffu;
+                        hi[s][v] += p[v] >> 16;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            const u32 cv = tc + s * TC;
+            if (cv < CV) {
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    atomicAdd(&colsum[cv * 8 + 2 * v], lo[s][v]);
+                    atomicAdd(&colsum[cv * 8 + 2 * v + 1], hi[s][v]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    u64* out = A.out + (size_t)ct * (n + 1);
+    const double dfmod = (double)A.fmod;
+    for (u32 k = threadIdx.x; k <= n; k += blockDim.x) {
+        u64 sum = (u64)colsum[k] % A.qKS;
+        u64 base = (k == n) ? b_ms : 0;
+        u64 v = base >= sum ? base - sum : base + A.qKS - sum;
+        out[k] = round_qQ(v, A.fmod, dfmod, dqKS);
+    }
+}
+
+// Split variant (small batches): gridDim.y CTAs share the rows of a ciphertext; kept as a separate kernel because the
+// plain kernel's load scheduling (four gathered rows in flight before the first add) is sensitive to any change of its
+// source: the templated merge of the two measured 3.09 ms instead of 2.22 ms per 16384 ciphertexts.
+template <int S>
+__global__ void __launch_bounds__(288) mkmswitch_packed16_split_kernel(KSArgs A, int TC, int RG) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 N = A.N, n = A.n, dKS = A.dKS;
+    u32* colsum = reinterpret_cast<u32*>(smem_raw);           // [row_stride]
+    u32* rowoff = colsum + A.row_stride;                      // [rows] table row index of every gathered row
+    __shared__ u64 b_ms;
+
+    const int ct = blockIdx.x;
+    const u64* ext = A.ext + (size_t)ct * (N + 1);
+    const double dQ = (double)A.Q, dqKS = (double)A.qKS;
+    const u32 ipc = (N + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * ipc;
+    const u32 i_hi = min(N, i_lo + ipc);
     const u32 r_lo = i_lo * dKS, rows = i_hi * dKS;
     for (u32 i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
         u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
@@ -212,7 +313,7 @@ __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int T
             rowoff[i * dKS + j] = (i * A.baseKS + a0) * dKS + j;
         }
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x == blockDim.x - 1)   // a thread with the fewest loop trips
         b_ms = round_qQ(ext[N], A.qKS, dqKS, dQ);
     for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
         colsum[k] = 0;
@@ -277,19 +378,10 @@ __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int T
         }
     }
     __syncthreads();
-    if (A.splits > 1) {
+    {
         unsigned long long* part = reinterpret_cast<unsigned long long*>(A.partial) + (size_t)ct * A.row_stride;
         for (u32 k = threadIdx.x; k <= n; k += blockDim.x)
             atomicAdd(part + k, (unsigned long long)colsum[k]);
-        return;
-    }
-    u64* out = A.out + (size_t)ct * (n + 1);
-    const double dfmod = (double)A.fmod;
-    for (u32 k = threadIdx.x; k <= n; k += blockDim.x) {
-        u64 sum = (u64)colsum[k] % A.qKS;
-        u64 base = (k == n) ? b_ms : 0;
-        u64 v = base >= sum ? base - sum : base + A.qKS - sum;
-        out[k] = round_qQ(v, A.fmod, dfmod, dqKS);
     }
 }
 
@@ -304,11 +396,11 @@ static cudaError_t launch_ks_packed16(const KSArgs& a, cudaStream_t s) {
     size_t smem = (size_t)a.row_stride * 4 + (size_t)a.N * a.dKS * 4 + 16;
     if (S != 1 || smem > 200 * 1024)
         return cudaErrorNotSupported;
-    cudaError_t e = cudaFuncSetAttribute(mkmswitch_packed16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    auto kern = a.splits > 1 ? mkmswitch_packed16_split_kernel<1> : mkmswitch_packed16_kernel<1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
-    mkmswitch_packed16_kernel<1><<<dim3(a.batch, a.splits), threads, smem, s>>>(a, TC, RG);
+    kern<<<dim3(a.batch, a.splits), threads, smem, s>>>(a, TC, RG);
     return cudaGetLastError();
 }
 
@@ -337,11 +429,11 @@ cudaError_t launch_mkmswitch(const KSArgs& a0, cudaStream_t s) {
     if (a0.batch <= 0)
         return cudaSuccess;
     KSArgs a = a0;
-    // One CTA per ciphertext walks N*dKS dependent gather trips; a batch that leaves SMs idle is split so that about two
-    // CTAs per SM share the rows of each ciphertext (the column sums meet in a global accumulator).
+    // One CTA per ciphertext walks N*dKS dependent gather trips; a batch below two ciphertexts per SM is split so that
+    // about four CTAs per SM share the rows of each ciphertext (the column sums meet in a global accumulator).
     a.splits = 1;
-    if (a.partial && a.sm_count > 0 && a.batch < a.sm_count && !getenv("TFHE_B200_NO_KSSPLIT")) {
-        int sp = (2 * a.sm_count + a.batch - 1) / a.batch;
+    if (a.partial && a.sm_count > 0 && a.batch < 2 * a.sm_count && !getenv("TFHE_B200_NO_KSSPLIT")) {
+        int sp = (4 * a.sm_count + a.batch - 1) / a.batch;   // about four CTAs per SM in total
         if (sp > 16)
             sp = 16;
         if (sp > (int)a.N)

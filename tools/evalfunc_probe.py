@@ -13,7 +13,7 @@ del bk, ksk
 q = p.q; pt = q // (2 * p.beta)
 lut = np.array([((x // (q // pt)) ** 3 % pt) * (q // pt) for x in range(q)], dtype=np.uint64)
 rng = np.random.default_rng(0)
-for b in (16, 64, 147, 148):
+for b in (16, 64, 148, 256, 512):
     ct = rng.integers(0, q, (b, p.n + 1), dtype=np.uint64)
     for name, fn in (("EvalFunc", lambda: ctx.EvalFunc(ct, lut)), ("BootstrapFunc", lambda: ctx.BootstrapFunc(ct, q, lut, q)), ("EvalFloor", lambda: ctx.EvalFloor(ct, q))):
         fn()
