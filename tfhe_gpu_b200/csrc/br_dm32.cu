@@ -346,6 +346,16 @@ cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_
         br_dm32_kernel<10, 4, 1, true><<<c.batch, 2 * 4 * K1::TPN, smem1, s>>>(a);
         return cudaGetLastError();
     }
+    if (group == 2 || (group == 0 && sm_count > 0 && c.batch <= 2 * sm_count)) {
+        // at most two ciphertexts per SM: CTAs of two (4 warps per SM instead of 8 competing for the multiplier pipe)
+        using K2 = KCfg<10, 4, 2>;
+        const size_t smem2 = (size_t)2 * K2::D * K2::RS * 4 + (size_t)2 * c.n * c.digitsR * 4 + 64;
+        e = cudaFuncSetAttribute(br_dm32_kernel<10, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess)
+            return e;
+        br_dm32_kernel<10, 4, 2><<<(c.batch + 1) / 2, K2::NT, smem2, s>>>(a);
+        return cudaGetLastError();
+    }
     const int grid = (c.batch + G - 1) / G;
     br_dm32_kernel<10, 4, G><<<grid, K::NT, smem, s>>>(a);
     return cudaGetLastError();
