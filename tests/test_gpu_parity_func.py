@@ -256,3 +256,23 @@ def test_cggi64_cta_shapes_agree(keyset, rng, name):
         g.set_option("group", 0)
     assert np.array_equal(outs[1], outs[2]) and np.array_equal(outs[0], outs[2])
     assert np.array_equal(outs[1], ks.port.bootstrap_func(ks.bk, ks.ksk, ct, p.q, tab, p.q))
+
+
+def test_floor_logq11_one_thrown_digit(keyset, rng):
+    """The reference's EvalFloor timing set (time-estimate.cpp:96-123: logQ = 11, numDigitsToThrow = 1): N = 1024, 27-bit Q,
+    baseG = 32, 5 kept digits -- the 5-digit instantiation of the 32-bit kernel; floor and a raw functional bootstrap
+    against the oracle, specialised and generic kernels against each other."""
+    ks = keyset("toy_func11_throw1")
+    p = ks.p
+    g = ks.gpu()
+    assert p.numDigitsToThrow == 1 and p.digitsG - p.numDigitsToThrow == 5 and g.kernel_variant == "cggi_u32_ntt32"
+    ct = rng.integers(0, p.q, (9, p.n + 1), dtype=np.uint64)
+    assert np.array_equal(g.EvalFloor(ct, p.q), ks.port.eval_floor(ks.bk, ks.ksk, ct, p.q))
+    tab = rng.integers(0, p.q, p.q, dtype=np.uint64)
+    a = g.BootstrapFunc(ct, p.q, tab, p.q)
+    assert np.array_equal(a, ks.port.bootstrap_func(ks.bk, ks.ksk, ct, p.q, tab, p.q))
+    g.set_option("force_generic", 1)
+    try:
+        assert np.array_equal(g.BootstrapFunc(ct, p.q, tab, p.q), a)
+    finally:
+        g.set_option("force_generic", 0)

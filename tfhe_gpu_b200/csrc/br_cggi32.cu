@@ -511,7 +511,7 @@ bool cggi32_supported(const tfhe_b200_params& p) {
     if (p.Q >= (1ULL << 32) / 22)  // lazy forward NTT bound: values < 22 Q must fit 32 bits
         return false;
     const u32 dk = p.digitsG - p.numDigitsToThrow;
-    if (dk != 2 && dk != 3 && dk != 4 && dk != 6)
+    if (dk != 2 && dk != 3 && dk != 4 && dk != 5 && dk != 6)
         return false;
     if (p.n > 4096)
         return false;
@@ -683,6 +683,7 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
         CASE(10, 3, 4)
         CASE(10, 2, 4)
         CASE(10, 6, 2)
+        CASE(10, 5, 2)   // logQ = 11 with one thrown digit (the reference's EvalFloor timing set, time-estimate.cpp:96-123)
     }
     else if (c.logN == 9) {
         if (group == 0) group = (dk <= 4) ? 8 : 4;
