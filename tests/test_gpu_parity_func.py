@@ -237,10 +237,11 @@ def test_large_precision_logq29(keyset):
         assert total % P == m
 
 
-@pytest.mark.parametrize("name", ["toy_func12", "toy_sign17"])
+@pytest.mark.parametrize("name", ["toy_func12", "toy_sign17", "toy_func12_throw1", "toy_sign17_throw1"])
 def test_cggi64_cta_shapes_agree(keyset, rng, name):
     """The wide 64-bit kernel runs two ciphertexts per CTA (throughput) or one (batches of at most one ciphertext per SM,
-    picked automatically): same bits from both shapes and from the generic kernel, on a ragged batch."""
+    picked automatically): same bits from both shapes and from the oracle, on a ragged batch.  The thrown-digit sets (the
+    reference's own timing configurations, time-estimate.cpp:59-190) take its plain path (no top-digit elimination)."""
     ks = keyset(name)
     p = ks.p
     g = ks.gpu()

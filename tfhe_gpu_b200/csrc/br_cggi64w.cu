@@ -169,10 +169,15 @@ struct KW {
                                    2 * (size_t)G * 2 * (WB + 4) * 4;
 };
 
-template <int DK, int G>
+// PLAIN = true: no top-digit elimination (thrown digits, or a top digit that is neither exact nor repairable).  The
+// region layout stays the same -- DK - 1 digit rows per component plus the evaluation-domain accumulator rows, which
+// are still maintained (acc_eval += delta) and inverse-transformed, only no longer multiplied by a key row: DK - 1 is
+// then the number of KEPT digits, the key has 2 (DK - 1) rows per secret-key half, and there is no wrap repair.
+template <int DK, int G, bool PLAIN = false>
 __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __grid_constant__ CGGI64WArgs A) {
     using K = KW<DK, G>;
     constexpr int D = K::D, NT = K::NT, NF = DK - 1;
+    constexpr int DKEY = PLAIN ? D - 2 : D;   // key rows per secret-key half
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* Dsm = reinterpret_cast<u64*>(smem_raw);                                  // [G][D][N]
     ulonglong2* twC = reinterpret_cast<ulonglong2*>(Dsm + (size_t)G * D * N);    // [15][128]
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
 
     for (u32 i = 0; i < n; i++) {
         // ---- phase 1: wrapped-top-digit detection, digits 0..DK-2 -> forward transforms ----------------------------
-        {
+        if (!PLAIN) {
             u32 wm = 0;
             const u32 wsh = gBits * DK;
 #pragma unroll
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
                     c[r] = park[posw(T + TPN * r)];
             }
             u64 v[CPT];
-            const u32 sh = gBits * l;
+            const u32 sh = gBits * (l + (PLAIN ? C.numThrow : 0));
 #pragma unroll
             for (int r = 0; r < CPT; r++) {
                 i64 dv = (c[r] < QHalf) ? (i64)c[r] : (i64)c[r] - (i64)Q;
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
 
         // ---- phase 2: pointwise stage (wrap repair first, see br_cggi64.cu) ------------------------------------------
         bool anyflag = false;
-        {
+        if (!PLAIN) {
             const u32* fl = wany + (size_t)(i & 1) * G * 8;
             u32 f = 0;
 #pragma unroll
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
         {
             constexpr int ITERS = N / NT;
             static_assert(N % NT == 0, "unsupported CTA shape");
-            constexpr int PL = 2 * D;
+            constexpr int PL = 2 * DKEY;
             const ulonglong2* bki = reinterpret_cast<const ulonglong2*>(A.bk) + (size_t)i * PL * N;
             u32 ee[G];
 #pragma unroll
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
 #pragma unroll 1
             for (int it = 0; it < ITERS; it++) {
                 const int k = tid + it * NT;
-                u64 bkv[4 * D];
+                u64 bkv[4 * DKEY];
 #pragma unroll
                 for (int x = 0; x < PL; x++) {
                     ulonglong2 w = bki[(size_t)x * N + k];
@@ -416,15 +421,15 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
                     u64 f1 = __ldg(A.psi_pow + xx);
                     u64 f2 = __ldg(A.psi_pow + ((2 * N - xx) & (2 * N - 1)));
                     const Limb x0(xd[0]);
-                    L3 a00(x0, bkv[(0 * D) * 2 + 0]), a01(x0, bkv[(0 * D) * 2 + 1]);
-                    L3 a10(x0, bkv[(1 * D) * 2 + 0]), a11(x0, bkv[(1 * D) * 2 + 1]);
+                    L3 a00(x0, bkv[(0 * DKEY) * 2 + 0]), a01(x0, bkv[(0 * DKEY) * 2 + 1]);
+                    L3 a10(x0, bkv[(1 * DKEY) * 2 + 0]), a11(x0, bkv[(1 * DKEY) * 2 + 1]);
 #pragma unroll
-                    for (int l = 1; l < D; l++) {
+                    for (int l = 1; l < DKEY; l++) {
                         const Limb x(xd[l]);
-                        a00.mac(x, bkv[(0 * D + l) * 2 + 0]);
-                        a01.mac(x, bkv[(0 * D + l) * 2 + 1]);
-                        a10.mac(x, bkv[(1 * D + l) * 2 + 0]);
-                        a11.mac(x, bkv[(1 * D + l) * 2 + 1]);
+                        a00.mac(x, bkv[(0 * DKEY + l) * 2 + 0]);
+                        a01.mac(x, bkv[(0 * DKEY + l) * 2 + 1]);
+                        a10.mac(x, bkv[(1 * DKEY + l) * 2 + 0]);
+                        a11.mac(x, bkv[(1 * DKEY + l) * 2 + 1]);
                     }
                     const Limb s00(redc128(a00.value(), Q, qinv)), s01(redc128(a01.value(), Q, qinv));
                     const Limb s10(redc128(a10.value(), Q, qinv)), s11(redc128(a11.value(), Q, qinv));
@@ -515,21 +520,29 @@ u64 shoup_w(u64 w, u64 Q) {
     return (u64)((((unsigned __int128)w) << 64) / Q);
 }
 
-template <int DK, int G>
+template <int DK, int G, bool PLAIN = false>
 cudaError_t launch_w(const CGGI64WArgs& a, cudaStream_t s) {
     using K = KW<DK, G>;
     if (K::smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(br_cggi64w_kernel<DK, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(br_cggi64w_kernel<DK, G, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)K::smem);
     if (e != cudaSuccess)
         return e;
     const int grid = (a.c.batch + G - 1) / G;
-    br_cggi64w_kernel<DK, G><<<grid, K::NT, K::smem, s>>>(a);
+    br_cggi64w_kernel<DK, G, PLAIN><<<grid, K::NT, K::smem, s>>>(a);
     return cudaGetLastError();
 }
 
 }  // namespace
+
+// plain path (no top-digit elimination): one or two kept digits
+bool cggi64w_plain_supported(const tfhe_b200_params& p) {
+    if (!cggi64_supported(p))
+        return false;
+    const u32 kept = p.digitsG - p.numDigitsToThrow;
+    return kept == 1 || kept == 2;
+}
 
 bool cggi64w_supported(const tfhe_b200_params& p) {
     if (!cggi64_supported(p) || p.numDigitsToThrow != 0)
@@ -589,7 +602,7 @@ cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStr
     a.Q2 = 2 * t.mod.Q;
     const u64 B = 1ULL << c.gBits;
     unsigned __int128 off = 0, pw = 1;
-    for (u32 i = 0; i < c.digitsKept; i++) {
+    for (u32 i = 0; i < c.digitsKept + (t.plain ? c.numThrow : 0); i++) {
         off += (B / 2) * pw;
         pw *= B;
     }
@@ -602,6 +615,13 @@ cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStr
     // a batch of at most one ciphertext per SM is latency-bound: one ciphertext per CTA (8 warps instead of 16 competing
     // for the SM) finishes a rotation step sooner; `group` = 1 / 2 forces a shape (tests, measurements)
     const bool one = group == 1 || (group == 0 && sm_count > 0 && c.batch <= sm_count);
+    if (t.plain) {   // DK template = kept digits + 1 (the accumulator rows take the place of the eliminated digit)
+        if (c.digitsKept == 1)
+            return one ? launch_w<2, 1, true>(a, s) : launch_w<2, 2, true>(a, s);
+        if (c.digitsKept == 2)
+            return one ? launch_w<3, 1, true>(a, s) : launch_w<3, 2, true>(a, s);
+        return cudaErrorInvalidConfiguration;
+    }
     if (c.digitsKept == 2)
         return one ? launch_w<2, 1>(a, s) : launch_w<2, 2>(a, s);
     if (c.digitsKept == 3)

@@ -399,7 +399,8 @@ extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
     if (h->have_dm32 && !h->force_generic)
         return "dm_u32_ntt32_skiptop";
     if (h->have_cggi64 && !h->force_generic)
-        return h->have_cggi64w ? "cggi_u64_ntt16x128_skiptop" : (h->skip_top ? "cggi_u64_ntt32x64_skiptop" : "cggi_u64_ntt32x64");
+        return h->have_cggi64w ? (h->skip_top ? "cggi_u64_ntt16x128_skiptop" : "cggi_u64_ntt16x128")
+                               : (h->skip_top ? "cggi_u64_ntt32x64_skiptop" : "cggi_u64_ntt32x64");
     return h->variant.c_str();
 }
 extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value) {
@@ -518,7 +519,8 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
     h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) ||
                    (h->have_cggi64 && (cggi32_skip_top_ok(p) || cggi_skip_top_wrapfix_ok(p)))) &&
                   !getenv("TFHE_B200_NO_SKIPTOP");
-    h->have_cggi64w = h->have_cggi64 && h->skip_top && cggi64w_supported(p) && !getenv("TFHE_B200_NO_C64W");
+    h->have_cggi64w = h->have_cggi64 && (h->skip_top ? cggi64w_supported(p) : cggi64w_plain_supported(p)) &&
+                      !getenv("TFHE_B200_NO_C64W");
     h->variant = h->is64 ? "generic_u64" : "generic_u32";
     if (p.method == TFHE_B200_METHOD_AP)
         h->variant += "_dm";
@@ -781,6 +783,7 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
     else if (h->have_cggi64w && !h->force_generic && !getenv("TFHE_B200_C64_NARROW")) {
         CGGI64WTables t;
         t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twC = d.twCw; t.twB = d.twBw; t.twU = d.twUw;
+        t.plain = !h->skip_top;
         CUDA_TRY(launch_br_cggi64w(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_cggi64 && !h->force_generic) {

@@ -95,8 +95,10 @@ struct CGGI64WTables {
     const u64* twC;       // device [15][128][2]
     const u64* twB;       // device [16][8][2]
     const u64* twU;       // device [2][15][2]
+    bool plain = false;   // no top-digit elimination (untransformed key, thrown digits honoured)
 };
 bool cggi64w_supported(const tfhe_b200_params& p);
+bool cggi64w_plain_supported(const tfhe_b200_params& p);
 void cggi64w_build_tables(const tfhe_b200_params& p, std::vector<u64>& twU, std::vector<u64>& twB, std::vector<u64>& twC);
 cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s, int sm_count = 0, int group = 0);
 
