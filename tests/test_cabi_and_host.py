@@ -77,6 +77,12 @@ def test_setup_argument_checks():
     with pytest.raises(tg.TfheB200Error, match="GPUSetup has not been called"):
         ctx.EvalBinGate("NAND", np.zeros((1, 3), dtype=np.uint64), np.ones((1, 3), dtype=np.uint64))
     ctx.GPUClean()  # GPUClean without GPUSetup is a no-op
+    # the key-map entry points need a handle too (and say so instead of crashing)
+    rc = lib.tfhe_b200_add_key_set(None, C.c_uint32(1 << 18), None, C.c_size_t(0), None, C.c_size_t(0), 0)
+    assert rc == -1 and b"GPUSetup has not been called" in lib.tfhe_b200_last_error()
+    assert lib.tfhe_b200_num_key_sets(None) == 0
+    with pytest.raises(tg.TfheB200Error, match="GPUSetup has not been called"):
+        ctx.AddKeySet(1 << 18, np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64))
 
 
 def test_product_never_imports_the_oracle():
