@@ -1,42 +1,64 @@
 #!/usr/bin/env python
-"""Headline benchmark: bootstrapped NAND gates/s, STD128 CGGI (BASELINE.json configs[1]).
+"""Benchmarks of the batched bootstrapping path.  Default: BASELINE.json configs[1] -- bootstrapped NAND gates/s,
+STD128 CGGI, batch 16384.
 
-    python bench.py --gpus N --steps K --warmup W            # our engine (one process per GPU under torchrun)
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU path on the host cores
+    python bench.py --gpus N --steps K --warmup W                 # our engine (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...       # the reference's own CPU path on the host cores
+    python bench.py --config {toy,std128,ap,func12,sign17,decomp17,mulmatrix}   # the other BASELINE.json configs
+    python bench.py --scaling strong --gpus N                     # ONE batch split over the N ranks (configs[1]:
+                                                                  # "batch 16384 ... then batch-sharded at 2/4/8 GPUs")
+    python bench.py --single-process --gpus N                     # the drop-in GPUSetup(numGPUs = N) path: one process,
+                                                                  # one host worker thread per GPU (not under torchrun)
 
-One "step" = one batched EvalBinGate(NAND) over `batch` synthetic random ciphertext pairs per GPU (uniform a, b --
-the path is data-oblivious for CGGI).  Keys are a real STD128 key set (generated once with the oracle's key
-generator so decrypt checks are possible).  Prints ONE JSON line (rank 0).
+One "step" = one batched call (EvalBinGate / EvalFunc / EvalSign / EvalDecomp / CiphertextMulMatrix) over the rank's
+share of the synthetic batch (uniform random ciphertexts: the path is data-oblivious for CGGI and the key switch).
+Prints ONE JSON line (rank 0).
 
-* value   : whole-job gates/s with the inputs already resident in HBM (device tensors through the C ABI).
-* e2e     : the same metric through the C ABI with HOST (pinned) buffers: H2D of both inputs and D2H of the result
-            are inside the timed region of every step.
+* value   : whole-job operations/s with the inputs already resident in HBM (device tensors through the C ABI).
+* e2e     : the same metric through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of the result are
+            inside the timed region of every step.  `e2e_pageable` (N = 1): the same with plain numpy (pageable) buffers,
+            which the library stages through its own pinned memory.
 * roofline: blind-rotation kernel vs the integer-pipe (IMAD) peak measured live by tfhe_gpu_b200/build/imad_peak;
-            roofline_hbm: the MS->KS->MS kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+            roofline_hbm: the MS->KS->MS kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json).  `traffic` is
+            read from profiles/ncu_traffic.json (written by tools/ncu_traffic.py from an `ncu --set full` capture).
 * cpu_baseline: the reference's scalar CPU path (oracle/_ref when present, else the oracle port) timed on a bounded
-            sample on this box's host cores.
+            sample on ALL host cores of this box (the thread count is set explicitly: torchrun exports
+            OMP_NUM_THREADS=1), rank 0 at N = 1 only.
+* reference_gpu: the reference's own CUDA path on the same GPUs (comparison build, `GPUSetup(N)`), run after our engine
+            has released them.
 """
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
 import time
 
-import numpy as np
+HOST_CORES = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+if int(os.environ.get("RANK", "0")) == 0:
+    # the CPU arms use every host core; must be in the environment before any OpenMP runtime is loaded
+    os.environ["OMP_NUM_THREADS"] = str(HOST_CORES)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# algorithmic work per STD128 CGGI bootstrap
-IMAD32_PER_BOOTSTRAP = 129.0e6          # 3 IMAD32 per modular multiplication, 42.99 M modmults
-KS_BYTES_PER_BOOTSTRAP = 2_101_248      # N*dKS*(n+1)*2 B gathered from the u16 key-switching table
-DRAM_TRAFFIC_PER_LAUNCH_16384 = 1.507e9 + 0.202e9      # br_cggi32 (profiles/r01_prof_cggi32_summary.md, r01e)
-KS_TABLE_BYTES = 1024 * 2 * 128 * 513 * 2   # N * dKS * baseKS * (n+1) u16 entries
-KS_DRAM_TRAFFIC_PER_LAUNCH_16384 = 5.30e9 + 0.07e9     # mkmswitch_packed16 (same file, prof_mkms_r01b)
-IMAD_PEAK_FALLBACK = 18.5e12            # profiles/r01_imad_peak.json (sustained, power-capped), this pool's B200
+IMAD_PEAK_FALLBACK = 18.5e12            # profiles/r01_imad_peak.json (sustained), this pool's B200
 HBM_FALLBACK_GBS = 6650.0               # B200_PROFILING.md fallback
+
+CONFIGS = {
+    # name: (BASELINE.json configs index, kind, default global batch, description)
+    "toy": (0, "gate", 1024, "TOY CGGI EvalBinGate"),
+    "std128": (1, "gate", 16384, "STD128 CGGI EvalBinGate"),
+    "ap": (2, "gate", 16384, "STD128 AP (DM) EvalBinGate"),
+    "func12": (3, "func", 8192, "EvalFunc arbitrary LUT x^3, STD128 functional set logQ=12 (N=2048, 54-bit Q)"),
+    "sign17": (4, "sign", 4096, "EvalSign, STD128 large-precision set logQ=17 (N=2048, 54-bit Q)"),
+    "decomp17": (4, "decomp", 4096, "EvalDecomp, STD128 large-precision set logQ=17 (N=2048, 54-bit Q)"),
+    "mulmatrix": (4, "mulmatrix", 1024, "CiphertextMulMatrix 1024 x 1024 (examples/GEMM.cpp:70-100), logQ=17 set"),
+}
 
 
 def parse():
@@ -45,11 +67,17 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16384, help="ciphertext pairs per GPU per step")
+    ap.add_argument("--config", default="std128", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch per GPU; strong: --batch split over the GPUs")
+    ap.add_argument("--batch", type=int, default=0, help="ciphertexts per step (0 = the BASELINE.json batch)")
     ap.add_argument("--gate", default="NAND")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="gates in the cpu_baseline sample (0 = 4 x cores)")
+    ap.add_argument("--single-process", action="store_true",
+                    help="drive all --gpus GPUs from this one process through GPUSetup(numGPUs) (not under torchrun)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="operations in the CPU sample (0 = about 10 s of work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own GPU path (comparison build)")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-buffer e2e leg")
     return ap.parse_args()
 
 
@@ -59,6 +87,16 @@ def measured_peaks():
             return json.load(f), "measured"
     except Exception:
         return {"hbm_gbs": HBM_FALLBACK_GBS}, "fallback"
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels, as written by
+    tools/ncu_traffic.py from an `ncu --set full` capture: {kernel substring: {"bytes": .., "batch": .., "source": ..}}."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler(threading.Thread):
@@ -105,91 +143,240 @@ def imad_peak_live():
         return IMAD_PEAK_FALLBACK, f"fallback (profiles/r01_imad_peak.json): {e}"
 
 
-def reference_gpu_arm(batch):
-    """The reference's OWN CUDA path (FFT kernels) on this box, when the comparison build exists
-    (oracle/Makefile `refgpu`: patched copy that dispatches its SM<900> templates on cc 10.0).  Runs in a subprocess
-    AFTER our engine has released the GPU; reported beside our numbers, never mixed into them."""
+def reference_gpu_arm(batch, ngpus):
+    """The reference's OWN CUDA path (FFT kernels) on this box, when the comparison build exists (oracle/Makefile
+    `refgpu`: patched copy that dispatches its SM<900> templates on cc 10.0), with `cc.GPUSetup(ngpus)`
+    (binfhecontext.cpp:349-360) and the whole batch in one call (it shards internally, bootstrapping.cu:1616-1667).
+    Runs in a subprocess AFTER our engine has released the GPUs; reported beside our numbers, never mixed into them."""
     so = os.path.join(ROOT, "oracle", "_ref", "libtfhe_ref_gpu.so")
     if not os.path.exists(so):
         return {"unavailable": "oracle/_ref/libtfhe_ref_gpu.so not built (make -C oracle refgpu)"}
+    batch = min(batch, 65536)   # its pinned staging is sized for 65536 ciphertexts (bootstrapping.cu:904-905)
     try:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_gpu_bench.py"), str(batch), "3"],
-                             capture_output=True, text=True, timeout=600).stdout
-        d = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+        env = dict(os.environ, OMP_NUM_THREADS=str(HOST_CORES))
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_gpu_bench.py"), str(batch), "3",
+                              str(ngpus)], capture_output=True, text=True, timeout=900, env=env).stdout
+        d = json.loads([ln for ln in out.splitlines() if ln.startswith("{")][-1])
         return {"value": d["gates_per_s"], "unit": "gates/s", "ms_per_ctx": d["ms_per_ctx"], "batch": d["batch"],
-                "decrypt_ok": d["decrypt_ok"], "kind": "reference GPU path (cuFFTDx FFT, SM<900> templates on sm_100)"}
+                "n_gpus": d.get("n_gpus", ngpus), "decrypt_ok": d["decrypt_ok"],
+                "kind": "reference GPU path (cuFFTDx FFT, SM<900> templates on sm_100)"}
     except Exception as e:  # noqa: BLE001
         return {"unavailable": f"reference GPU run failed: {e}"}
 
 
-def std128_keys():
-    from oracle import pyoracle as po   # key generation + CPU baselines only (test infrastructure)
+# --------------------------------------------------------------------------------------------------------------
+# workload description (shared by both arms)
+# --------------------------------------------------------------------------------------------------------------
+def mm_cggi(n, N, kept_digits):
+    """modular multiplications per CGGI bootstrap, d = 2 * digits rows."""
+    d = 2 * kept_digits
+    logN = N.bit_length() - 1
+    return n * ((d + 2) * (N // 2) * logN + 4 * d * N)
 
-    p = po.Port.params_named(po.STD128, po.GINX)
-    port = po.Port(p)
-    sk, bk, ksk = port.keygen(20261018)
-    return po, p, port, sk, bk, ksk
+
+def mm_dm(n, N, digits, baseR, digitsR):
+    d = 2 * digits
+    logN = N.bit_length() - 1
+    return n * digitsR * (1 - 1 / baseR) * ((d + 2) * (N // 2) * logN + 2 * (d - 1) * N)
+
+
+class Workload:
+    """Parameter set, operator and algorithmic work of one --config (test infrastructure `oracle.pyoracle` supplies the
+    parameter probes, the host key generator and the checker; the timed path is the CUDA engine)."""
+
+    def __init__(self, args):
+        from oracle import pyoracle as po
+
+        self.po, self.args, self.name = po, args, args.config
+        self.cfg_index, self.kind, self.default_batch, self.desc = CONFIGS[args.config]
+        if self.name == "toy":
+            self.ref_args = ("named", po.TOY, po.GINX)
+        elif self.name == "std128":
+            self.ref_args = ("named", po.STD128, po.GINX)
+        elif self.name == "ap":
+            self.ref_args = ("named", po.STD128, po.AP)
+        elif self.name == "func12":
+            self.ref_args = ("func", po.STD128, True, 12)
+        else:
+            self.ref_args = ("func", po.STD128, False, 17)
+        self.p = (po.Port.params_named(*self.ref_args[1:]) if self.ref_args[0] == "named"
+                  else po.Port.params_func(*self.ref_args[1:]))
+        p = self.p
+        self.ct_mod = (1 << 17) if self.kind in ("sign", "decomp", "mulmatrix") else p.q
+        self.boots = {"gate": 3 if args.gate in ("XOR", "XNOR") else 1, "func": 2, "sign": 5, "decomp": 4,
+                      "mulmatrix": 0}[self.kind]
+        kept = p.digitsG - p.numDigitsToThrow
+        per_mm = 3 if p.Q < (1 << 32) else 12      # IMAD32 per modular multiplication (SURVEY 8d convention)
+        if self.name == "ap":
+            self.imad_per_boot = per_mm * mm_dm(p.n, p.N, p.digitsG, p.baseR, p.digitsR)
+        else:
+            self.imad_per_boot = per_mm * mm_cggi(p.n, p.N, kept)
+        w = 2 if p.qKS <= (1 << 16) else (4 if p.qKS <= (1 << 32) else 8)
+        self.ks_bytes_per_boot = p.N * p.dKS * (p.n + 1) * w
+        self.ks_table_bytes = p.N * p.dKS * p.baseKS * (p.n + 1) * w
+        self.unit = {"gate": "gates/s", "func": "EvalFunc/s", "sign": "EvalSign/s", "decomp": "EvalDecomp/s",
+                     "mulmatrix": "output ciphertexts/s"}[self.kind]
+        if self.name == "std128" and args.gate == "NAND":
+            self.metric = "bootstrapped NAND gates/sec, STD128 CGGI"
+        else:
+            self.metric = f"{self.desc}{' (' + args.gate + ')' if self.kind == 'gate' else ''} per second"
+        self.host_keys = self.name in ("toy", "std128")     # oracle key generator on the host; else GPU key generation
+
+    # ---- keys ----------------------------------------------------------------------------------------------
+    def make_keys(self, dev):
+        """Rank 0: (bk, ksk) as host numpy arrays (oracle generator) or device tensors (tfhe_b200_keygen)."""
+        if self.host_keys:
+            port = self.po.Port(self.p)
+            _, bk, ksk = port.keygen(20261018)
+            return bk, ksk
+        from tfhe_gpu_b200 import gpu_keygen
+
+        r = np.random.default_rng(1)
+        sk = r.integers(-1, 2, self.p.n).astype(np.int8)
+        skN = r.integers(-1, 2, self.p.N).astype(np.int8)
+        return gpu_keygen(self.p.as_dict(), sk, skN, 20261018, device=dev.index)
+
+    # ---- inputs --------------------------------------------------------------------------------------------
+    def make_inputs(self, rng, count):
+        """Host int64 arrays of one step for `count` units."""
+        p = self.p
+        if self.kind == "gate":
+            return [rng.integers(0, p.q, (count, p.n + 1), dtype=np.int64) for _ in range(2)]
+        if self.kind == "func":
+            pt = p.q // (2 * p.beta)
+            lut = np.array([((x // (p.q // pt)) ** 3 % pt) * (p.q // pt) for x in range(p.q)], dtype=np.int64)
+            return [rng.integers(0, p.q, (count, p.n + 1), dtype=np.int64), lut]
+        if self.kind in ("sign", "decomp"):
+            return [rng.integers(0, self.ct_mod, (count, p.n + 1), dtype=np.int64)]
+        # mulmatrix: `count` = number of input (= output) ciphertexts; entries < 2^6 (GEMM.cpp:70-88)
+        return [rng.integers(0, self.ct_mod, (count, p.n + 1), dtype=np.int64),
+                rng.integers(0, 64, (count, count), dtype=np.int64)]
+
+    def io_bytes(self, count):
+        W = (self.p.n + 1) * 8
+        if self.kind == "gate":
+            return 2 * count * W, count * W
+        if self.kind == "func":
+            return count * W + self.p.q * 8, count * W
+        if self.kind == "sign":
+            return count * W, count * W
+        if self.kind == "decomp":
+            return count * W, 3 * count * W
+        return count * W + count * count * 8, count * W
+
+    def run(self, ctx, ins, out=None):
+        k = self.kind
+        if k == "gate":
+            return ctx.EvalBinGate(self.args.gate, ins[0], ins[1], out=out)
+        if k == "func":
+            return ctx.EvalFunc(ins[0], ins[1])
+        if k == "sign":
+            return ctx.EvalSign(ins[0], self.ct_mod)
+        if k == "decomp":
+            return ctx.EvalDecomp(ins[0], self.ct_mod)[0]
+        return ctx.CiphertextMulMatrix(ins[0], ins[1], self.ct_mod)
+
+    # ---- oracle (checker) ------------------------------------------------------------------------------------
+    def oracle(self, port, bk, ksk, ins, sl):
+        po, k, u = self.po, self.kind, (lambda a: np.ascontiguousarray(a).view(np.uint64))
+        if k == "gate":
+            return port.eval_bin_gate(bk, ksk, po.GATES[self.args.gate], u(ins[0][sl]), u(ins[1][sl]), self.ct_mod)
+        if k == "func":
+            return port.eval_func(bk, ksk, u(ins[0][sl]), self.ct_mod, u(ins[1]))
+        if k == "sign":
+            return port.eval_sign(bk, ksk, u(ins[0][sl]), self.ct_mod)
+        if k == "decomp":
+            return port.eval_decomp(bk, ksk, u(ins[0][sl]), self.ct_mod)[0]
+        return port.mul_matrix(u(ins[0]), ins[1], self.ct_mod)[sl]
 
 
 class CpuArm:
     """Reference scalar CPU path on the host cores.  kind 'reference' = the UNMODIFIED OpenFHE 1.0.4 / TFHE-GPU host
-    code compiled from /root/reference into oracle/_ref (the scalar cc.EvalBinGate looped over OpenMP threads, the
-    protocol of BASELINE.md section 3); kind 'port' = our C restatement, used only when oracle/_ref is absent."""
+    code compiled from /root/reference into oracle/_ref (the scalar cc.Eval* looped over OpenMP threads, the protocol of
+    BASELINE.md section 3); kind 'port' = our C restatement, used only when oracle/_ref is absent."""
 
-    def __init__(self, po, p, port, bk, ksk, gate):
-        self.po, self.p, self.port, self.bk, self.ksk, self.gate = po, p, port, bk, ksk, gate
-        self.ref = None
+    def __init__(self, wl):
+        po = wl.po
+        self.wl, self.po = wl, po
+        self.ref = self.port = None
         if po.have_ref():
-            self.ref = po.Ref.named(po.STD128, po.GINX)
+            a = wl.ref_args
+            self.ref = po.Ref.named(*a[1:]) if a[0] == "named" else po.Ref.func(*a[1:])
+            self.ref.set_num_threads(HOST_CORES)
             self.ref.keygen()                      # the reference draws its own (random) keys
             self.kind, self.cores = "reference", self.ref.num_threads()
         else:
-            self.kind, self.cores = "port", port.num_threads()
+            self.port = po.Port(wl.p)
+            self.port.set_num_threads(HOST_CORES)
+            _, self.bk, self.ksk = self.port.keygen(7)
+            self.kind, self.cores = "port", self.port.num_threads()
         self.rng = np.random.default_rng(5)
-        self._run(self.cores)                      # warm-up: lazy NTT table precomputation
+        self.unit_s = self._run(self.cores)        # warm-up (lazy NTT tables) and a first estimate: one unit per thread
 
     def _run(self, sample):
-        p, g = self.p, self.po.GATES[self.gate]
-        c1 = self.rng.integers(0, p.q, (sample, p.n + 1), dtype=np.uint64)
-        c2 = self.rng.integers(0, p.q, (sample, p.n + 1), dtype=np.uint64)
+        wl, u = self.wl, (lambda a: np.ascontiguousarray(a).view(np.uint64))
+        ins = wl.make_inputs(self.rng, sample)
         t = time.perf_counter()
         if self.ref is not None:
-            self.ref.eval_bin_gate(g, c1, c2, p.q)
+            r, k = self.ref, wl.kind
+            if k == "gate":
+                r.eval_bin_gate(self.po.GATES[wl.args.gate], u(ins[0]), u(ins[1]), wl.ct_mod)
+            elif k == "func":
+                r.eval_func(u(ins[0]), wl.ct_mod, u(ins[1]))
+            elif k == "sign":
+                r.eval_sign(u(ins[0]), wl.ct_mod)
+            elif k == "decomp":
+                r.eval_decomp(u(ins[0]), wl.ct_mod)
+            else:
+                r.mul_matrix(u(ins[0]), wl.ct_mod, ins[1], wl.ct_mod)
         else:
-            self.port.eval_bin_gate(self.bk, self.ksk, g, c1, c2, p.q)
+            wl.oracle(self.port, self.bk, self.ksk, ins, slice(None))
         return time.perf_counter() - t
+
+    def default_sample(self):
+        """About 10 s of CPU work, a whole number of units per thread."""
+        if self.wl.kind == "mulmatrix":
+            return 256
+        per_thread = max(1, min(64, int(round(10.0 / max(self.unit_s, 1e-3)))))
+        return self.cores * per_thread
 
     def measure(self, sample):
         dt = self._run(sample)
-        return dt, {"value": sample / dt, "unit": "gates/s", "cores": self.cores, "kind": self.kind,
-                    "sample": f"{sample} STD128 CGGI {self.gate} gates, scalar CPU API over {self.cores} OpenMP "
-                              f"threads, {dt:.2f} s",
-                    "ms_per_gate_per_thread": dt / sample * self.cores * 1e3}
+        what = f"{sample} x {self.wl.desc}" + (f"({self.wl.args.gate})" if self.wl.kind == "gate" else "")
+        return dt, {"value": sample / dt, "unit": self.wl.unit, "cores": self.cores, "kind": self.kind,
+                    "sample": f"{what}, scalar CPU API over {self.cores} OpenMP threads, {dt:.2f} s",
+                    "ms_per_op_per_thread": dt / sample * self.cores * 1e3}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's own CPU implementation of the path on all host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    po, p, port, sk, bk, ksk = std128_keys()
-    arm = CpuArm(po, p, port, bk, ksk, args.gate)
-    sample = args.cpu_sample or 4 * arm.cores
-    tot, base = 0.0, None
+    wl = Workload(args)
+    arm = CpuArm(wl)
+    sample = args.cpu_sample or arm.default_sample()
+    # keep the whole --steps/--warmup run within a few minutes
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    if not args.cpu_sample and arm.unit_s / arm.cores * sample > budget and wl.kind != "mulmatrix":
+        sample = max(arm.cores, int(budget / (arm.unit_s / arm.cores)) // arm.cores * arm.cores)
+    tot, base, times = 0.0, None, []
     for s in range(args.warmup + args.steps):
         dt, base = arm.measure(sample)
         if s >= args.warmup:
             tot += dt
+            times.append(dt)
     value = sample * args.steps / tot
+    batch = args.batch or wl.default_batch
     line = {
-        "impl": "reference", "metric": "bootstrapped NAND gates/sec, STD128 CGGI", "value": value, "unit": "gates/s",
+        "impl": "reference", "metric": wl.metric, "value": value, "unit": wl.unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"STD128 CGGI EvalBinGate({args.gate}), reference CPU (NTT) path, bounded sample "
-                               f"of {sample} gates per step (full workload: batch {args.batch} per GPU)"},
-        "cpu_baseline": {"value": value, "unit": "gates/s", "cores": base["cores"], "kind": base["kind"],
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"{wl.desc}, reference CPU (NTT) path, bounded sample of {sample} per step (full "
+                               f"workload: batch {batch}{' per GPU' if args.scaling == 'weak' else ' in total'})",
+                   "baseline_config_index": wl.cfg_index, "p50_ms_per_op": statistics.median(times) / sample * 1e3},
+        "cpu_baseline": {"value": value, "unit": wl.unit, "cores": base["cores"], "kind": base["kind"],
                          "sample": base["sample"]},
-        "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -204,37 +391,72 @@ def main():
     import torch.distributed as dist
 
     from tfhe_gpu_b200 import BinFHEContextB200
+    from tfhe_gpu_b200.dist import broadcast_keys, shard_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    if args.single_process and world > 1:
+        raise SystemExit("bench.py: --single-process is not run under torchrun")
+    n_gpus = args.gpus if args.single_process else world
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- keys: rank 0 generates, NCCL broadcast over NVLink replicates them (the only collective) -----------
-    from tfhe_gpu_b200.dist import broadcast_keys
+    wl = Workload(args)
+    po, p = wl.po, wl.p
+    warmup = max(args.warmup, 3)
 
-    po = p = port = sk = bk = ksk = pd = None
+    # ---- keys: rank 0 generates, ONE NCCL broadcast over NVLink replicates them (the only collective) ---------
+    bk = ksk = None
     if rank == 0:
-        po, p, port, sk, bk, ksk = std128_keys()
+        bk, ksk = wl.make_keys(dev)
+        if torch.is_tensor(bk):
+            torch.cuda.synchronize()
+    if torch.is_tensor(bk) or (rank != 0 and not wl.host_keys):
         pd = p.as_dict()
-    pd, bk_t, ksk_t = broadcast_keys(pd, bk, ksk, dev, src=0)
-    ctx = BinFHEContextB200().GPUSetup(pd, bk_t, ksk_t, numGPUs=1, first_device=local)
-    del bk_t, ksk_t
+        if world > 1:
+            if rank != 0:
+                bk = torch.empty(po.Port(p).bk_words(), dtype=torch.int64, device=dev)
+                ksk = torch.empty(po.Port(p).ksk_words(), dtype=torch.int64, device=dev)
+            dist.broadcast(bk, src=0)
+            dist.broadcast(ksk, src=0)
+            torch.cuda.synchronize(dev)
+        bk_t, ksk_t = bk, ksk
+    else:
+        pd, bk_t, ksk_t = broadcast_keys(p.as_dict() if rank == 0 else None, bk, ksk, dev, src=0)
+    t_setup = time.perf_counter()
+    ctx = BinFHEContextB200().GPUSetup(pd, bk_t, ksk_t, numGPUs=(n_gpus if args.single_process else 1),
+                                       first_device=local)
+    t_setup = time.perf_counter() - t_setup
+    # every rank keeps a host copy of the keys for its own oracle slice check (the checker needs them on the host)
+    bk_h = bk_t.cpu().numpy().view(np.uint64) if torch.is_tensor(bk_t) else bk_t
+    ksk_h = ksk_t.cpu().numpy().view(np.uint64) if torch.is_tensor(ksk_t) else ksk_t
+    del bk_t, ksk_t, bk, ksk
     torch.cuda.empty_cache()
 
-    n, q, batch = pd["n"], pd["q"], args.batch
-    N = pd["N"]
+    # ---- this rank's share of the synthetic batch ----------------------------------------------------------
+    batch = args.batch or wl.default_batch
+    if wl.kind == "mulmatrix":
+        count, global_batch = batch, batch          # one matrix product per step and rank (first GPU only)
+    elif args.scaling == "strong":
+        _, count = shard_range(batch, world, rank)
+        global_batch = batch
+    else:
+        count, global_batch = batch, batch * world
+    if args.single_process and args.scaling == "weak":
+        count = global_batch = batch * n_gpus
     rng = np.random.default_rng(1000 + rank)
-    h1 = torch.from_numpy(rng.integers(0, q, (batch, n + 1), dtype=np.int64)).pin_memory()
-    h2 = torch.from_numpy(rng.integers(0, q, (batch, n + 1), dtype=np.int64)).pin_memory()
-    d1, d2 = h1.to(dev), h2.to(dev)
-    hout = torch.empty((batch, n + 1), dtype=torch.int64).pin_memory()
+    host = [torch.from_numpy(a).pin_memory() for a in wl.make_inputs(rng, count)]
+    devt = [h.to(dev) for h in host]
+    hnp = [h.numpy().view(np.uint64) for h in host]
+    hout = None
+    if wl.kind == "gate":
+        hout = torch.empty((count, p.n + 1), dtype=torch.int64).pin_memory().numpy().view(np.uint64)
 
     def barrier():
         torch.cuda.synchronize()
@@ -242,122 +464,176 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        out = ctx.EvalBinGate(args.gate, d1, d2)       # synchronous C-ABI call, device-resident in/out
-        st = ctx.last_stats
-        return out, st.blind_rotate_ms, st.keyswitch_ms, st.total_ms, st.kernel_launches, st.bootstraps
-
     # ---- warm-up -------------------------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        out, *_ = step_resident()
+    out = None
+    for _ in range(warmup):
+        out = wl.run(ctx, devt)
 
-    # ---- correctness guard inside the bench: a small slice is checked against the oracle (rank 0) --------------------
-    parity = None
-    if rank == 0:
-        sl = slice(0, 4)
-        want = port.eval_bin_gate(bk, ksk, po.GATES[args.gate], h1[sl].numpy().view(np.uint64),
-                                  h2[sl].numpy().view(np.uint64), q)
-        parity = bool(np.array_equal(out[sl].cpu().numpy().view(np.uint64), want))
-        if not parity:
-            raise SystemExit("bench.py: GPU output differs from the oracle -- refusing to report a number")
+    # ---- correctness guard inside the bench: EVERY rank checks a slice of its own shard against the oracle ------
+    port = po.Port(p)
+    port.set_num_threads(max(1, HOST_CORES // max(1, world)))
+    sl = slice(0, 2 if wl.boots > 1 else 4)
+    want = wl.oracle(port, bk_h, ksk_h, [h.numpy() for h in host], sl)
+    got = out[sl].cpu().numpy().view(np.uint64)
+    ok = bool(np.array_equal(got, want))
+    okt = torch.tensor([1 if ok else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if int(okt[0]) != 1:
+        raise SystemExit(f"bench.py: GPU output differs from the oracle on rank {rank if not ok else '?'} -- "
+                         "refusing to report a number")
+    del bk_h, ksk_h, port
 
     # ---- timed region: device-resident ---------------------------------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
     br_ms = ks_ms = dev_ms = 0.0
-    launches = boots = 0
+    launches = 0
+    step_s = []
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, a, b, c, l, nb = step_resident()
-        br_ms += a; ks_ms += b; dev_ms += c; launches += l; boots = nb
+        ts = time.perf_counter()
+        wl.run(ctx, devt)                           # synchronous C-ABI call, device-resident in/out
+        step_s.append(time.perf_counter() - ts)
+        st = ctx.last_stats
+        br_ms += st.blind_rotate_ms; ks_ms += st.keyswitch_ms; dev_ms += st.total_ms; launches += st.kernel_launches
     barrier()
     dt = time.perf_counter() - t0
 
-    # ---- timed region: end to end through host buffers (H2D + compute + D2H inside every step) ------------------------
+    # ---- timed region: end to end through pinned host buffers (H2D + compute + D2H inside every step) ----------------
     for _ in range(2):
-        ctx.EvalBinGate(args.gate, h1.numpy().view(np.uint64), h2.numpy().view(np.uint64))
+        wl.run(ctx, hnp, out=hout)
+    e2e_step_s = []
     barrier()
     t1 = time.perf_counter()
-    e2e_launches = 0
     for _ in range(args.steps):
-        ctx.EvalBinGate(args.gate, h1.numpy().view(np.uint64), h2.numpy().view(np.uint64),
-                        out=hout.numpy().view(np.uint64))
-        e2e_launches += ctx.last_stats.kernel_launches
+        ts = time.perf_counter()
+        wl.run(ctx, hnp, out=hout)
+        e2e_step_s.append(time.perf_counter() - ts)
     barrier()
     dt_e2e = time.perf_counter() - t1
+
+    # ---- N = 1: the same through PAGEABLE host buffers (plain numpy, what a std::vector caller has) ------------------
+    dt_page = None
+    if n_gpus == 1 and not args.no_pageable and wl.kind != "mulmatrix":
+        pg = [np.array(a, copy=True) for a in hnp]
+        pgout = np.empty_like(hout) if hout is not None else None
+        for _ in range(2):
+            wl.run(ctx, pg, out=pgout)
+        nrep = max(2, min(args.steps, 5))
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        for _ in range(nrep):
+            wl.run(ctx, pg, out=pgout)
+        torch.cuda.synchronize()
+        dt_page = (time.perf_counter() - t2) / nrep
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    p50, p50_e2e = statistics.median(step_s), statistics.median(e2e_step_s)
     if world > 1:
-        t = torch.tensor([dt, dt_e2e], dtype=torch.float64, device=dev)
+        t = torch.tensor([dt, dt_e2e, p50, p50_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, dt_e2e = float(t[0]), float(t[1])
+        dt, dt_e2e, p50, p50_e2e = (float(x) for x in t)
+        ln = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln[0])
 
+    line = None
     if rank == 0:
-        total_gates = batch * world * args.steps
-        value = total_gates / dt
-        e2e_value = total_gates / dt_e2e
+        total_units = global_batch * args.steps
+        value = total_units / dt
+        e2e_value = total_units / dt_e2e
         peaks, peaks_src = measured_peaks()
         imad_peak, imad_src = imad_peak_live()
-        br_s = br_ms / args.steps * 1e-3          # average launch duration of the dominant kernel (CUDA events)
-        ks_s = ks_ms / args.steps * 1e-3
-        achieved_imad = IMAD32_PER_BOOTSTRAP * batch / br_s
-        achieved_ks = KS_BYTES_PER_BOOTSTRAP * batch / ks_s / 1e9
-        ks_compulsory = ((N + 1) * 8 + (n + 1) * 8) * batch + KS_TABLE_BYTES
+        traffic = ncu_traffic()
+        h2d, d2h = wl.io_bytes(count)
         line = {
-            "metric": "bootstrapped NAND gates/sec, STD128 CGGI", "value": value, "unit": "gates/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"STD128 CGGI EvalBinGate({args.gate}), batch {batch} ciphertext pairs per GPU "
-                                   f"(n=512 N=1024 Q=134215681 baseG=2^7 qKS=2^14 baseKS=128), bit-exact vs "
-                                   f"OpenFHE 1.0.4 CPU path",
-                       "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"batch-shard x{world}",
-                       "kernel": ctx.kernel_variant,
-                       "l2_note": "inputs (2 x 67 MB) + extracted LWE (134 MB) + KSK (269 MB) exceed the 126 MB L2 "
-                                  "every step; no explicit flush",
-                       "ms_per_bootstrap_p50": dt / args.steps * 1e3 / batch,
-                       "oracle_slice_bit_exact": parity},
-            "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": 2 * batch * (n + 1) * 8,
-                    "d2h_bytes_per_step": batch * (n + 1) * 8, "ms_per_step": dt_e2e / args.steps * 1e3},
+            "metric": wl.metric, "value": value, "unit": wl.unit,
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "u32" if p.Q < (1 << 32) else "u64", "data": "synthetic",
+            "config": {"workload": f"{wl.desc}{'(' + args.gate + ')' if wl.kind == 'gate' else ''}, batch "
+                                   f"{global_batch} in total = {count} per GPU rank (n={p.n} N={p.N} Q={p.Q} "
+                                   f"baseG={p.baseG} qKS={p.qKS} baseKS={p.baseKS}), bit-exact vs OpenFHE 1.0.4 CPU path",
+                       "baseline_config_index": wl.cfg_index,
+                       "batch_per_gpu": count if not args.single_process else global_batch // n_gpus,
+                       "global_batch": global_batch,
+                       "parallelism": (f"single process, GPUSetup(numGPUs={n_gpus}), one host worker per GPU"
+                                       if args.single_process else f"batch-shard x{world}, one process per GPU"),
+                       "kernel": ctx.kernel_variant, "bootstraps_per_op": wl.boots,
+                       "l2_note": "per-step working set (inputs, extracted LWE, key-switching table) exceeds the "
+                                  "126 MB L2; no explicit flush",
+                       "p50_ms_per_step": p50 * 1e3,
+                       "ms_per_ctx_p50": p50 * 1e3 / max(1, count),
+                       "ms_per_bootstrap_p50": p50 * 1e3 / max(1, count * max(1, wl.boots)),
+                       "gpu_setup_s": round(t_setup, 3),
+                       "oracle_slice_bit_exact_all_ranks": True},
+            "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": dt_e2e / args.steps * 1e3, "p50_ms_per_step": p50_e2e * 1e3,
+                    "host_buffers": "pinned"},
             "gpu_launches": launches,
-            "bootstraps_per_gate": boots,
-            "clocks": sampler.summary(),
-            "roofline": {"bound": "imad", "kernel": "br_cggi32_kernel", "achieved": achieved_imad / 1e12,
-                         "peak": imad_peak / 1e12, "unit": "TIMAD32/s", "frac": achieved_imad / imad_peak,
-                         "traffic": DRAM_TRAFFIC_PER_LAUNCH_16384 * batch / 16384 if args.gate == "NAND" else None,
-                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of one "
-                                           "16384-ciphertext launch (profiles/r01_prof_cggi32_summary.md), bytes",
-                         "peak_source": imad_src,
-                         "algorithmic": f"{IMAD32_PER_BOOTSTRAP:.4g} IMAD32 per bootstrap x {batch} per launch",
-                         "avg_launch_ms": br_s * 1e3, "share_of_step": br_ms / max(dev_ms, 1e-9)},
-            # MS->KS->MS (1.3% of the step): a gather of N*dKS table rows per ciphertext.  The gathered bytes are served
-            # mostly by L2 (the 134 MB u16 table does not quite fit, so part of it is re-read from HBM: "traffic"),
-            # hence three figures: compulsory HBM bytes (in + out + table once) = "achieved", the DRAM throughput
-            # ncu measured ("dram_gbs"), and the gather rate the SMs see ("gather_gbs").
-            "roofline_hbm": {"bound": "hbm", "kernel": "mkmswitch_packed16_kernel",
-                             "achieved": ks_compulsory / ks_s / 1e9,
-                             "peak": peaks.get("hbm_gbs", HBM_FALLBACK_GBS), "unit": "GB/s",
-                             "frac": ks_compulsory / ks_s / 1e9 / peaks.get("hbm_gbs", HBM_FALLBACK_GBS),
-                             "traffic": KS_DRAM_TRAFFIC_PER_LAUNCH_16384 * batch / 16384,
-                             "dram_gbs": KS_DRAM_TRAFFIC_PER_LAUNCH_16384 * batch / 16384 / ks_s / 1e9,
-                             "gather_gbs": achieved_ks,
-                             "peak_source": f"MEASURED_PEAKS.json ({peaks_src})",
-                             "algorithmic": f"{(N + 1) * 8} B in + {(n + 1) * 8} B out per bootstrap x {batch} + "
-                                            f"{KS_TABLE_BYTES} B table once; {KS_BYTES_PER_BOOTSTRAP} B gathered "
-                                            f"(L2) per bootstrap",
-                             "avg_launch_ms": ks_s * 1e3, "share_of_step": ks_ms / max(dev_ms, 1e-9)},
         }
-        if not args.no_cpu_baseline:
-            arm = CpuArm(po, p, port, bk, ksk, args.gate)
-            _, line["cpu_baseline"] = arm.measure(args.cpu_sample or 8 * arm.cores)
-        ctx.GPUClean()
-        if not args.no_ref_gpu and world == 1:
-            line["reference_gpu"] = reference_gpu_arm(batch)
-        print(json.dumps(line), flush=True)
+        if dt_page is not None:
+            line["e2e_pageable"] = {"value": count / dt_page, "unit": wl.unit, "ms_per_step": dt_page * 1e3,
+                                    "host_buffers": "pageable numpy arrays, staged through the handle's pinned memory"}
+        line["clocks"] = sampler.summary()
+        if wl.boots >= 1:
+            single = wl.boots == 1 and br_ms > 0
+            t_dom = (br_ms if single else dev_ms) / args.steps * 1e-3
+            achieved = wl.imad_per_boot * wl.boots * (count if not args.single_process else global_batch // n_gpus) / t_dom
+            kname = {"cggi_u32": "br_cggi32_kernel", "dm_u32": "br_dm32_kernel", "cggi_u64_ntt16": "br_cggi64w_kernel",
+                     "cggi_u64_ntt32": "br_cggi64_kernel"}
+            kern = next((v for k, v in kname.items() if ctx.kernel_variant.startswith(k)), "br_generic_kernel")
+            tr = traffic.get(kern)
+            line["roofline"] = {
+                "bound": "imad", "kernel": kern, "achieved": achieved / 1e12, "peak": imad_peak / 1e12,
+                "unit": "TIMAD32/s", "frac": achieved / imad_peak,
+                "traffic": (tr["bytes"] * count / tr["batch"]) if tr else None,
+                "traffic_source": tr["source"] if tr else None,
+                "peak_source": imad_src,
+                "algorithmic": f"{wl.imad_per_boot:.4g} IMAD32 per bootstrap x {wl.boots} bootstraps x {count} per "
+                               f"launch sequence",
+                "timed": ("blind-rotation launch (CUDA events inside the C ABI)" if single else
+                          "whole device time of the call (key switches and LWE glue included: a lower bound)"),
+                "avg_launch_ms": t_dom * 1e3, "share_of_step": (br_ms if single else dev_ms) / max(dev_ms, 1e-9)}
+            if wl.boots == 1 and ks_ms > 0:
+                ks_s = ks_ms / args.steps * 1e-3
+                ks_compulsory = ((p.N + 1) * 8 + (p.n + 1) * 8) * count + wl.ks_table_bytes
+                hbm = peaks.get("hbm_gbs", HBM_FALLBACK_GBS)
+                ktr = traffic.get("mkmswitch")
+                line["roofline_hbm"] = {
+                    "bound": "hbm", "kernel": "mkmswitch", "achieved": ks_compulsory / ks_s / 1e9, "peak": hbm,
+                    "unit": "GB/s", "frac": ks_compulsory / ks_s / 1e9 / hbm,
+                    "traffic": (ktr["bytes"] * count / ktr["batch"]) if ktr else None,
+                    "dram_gbs": (ktr["bytes"] * count / ktr["batch"] / ks_s / 1e9) if ktr else None,
+                    "gather_gbs": wl.ks_bytes_per_boot * count / ks_s / 1e9,
+                    "peak_source": f"MEASURED_PEAKS.json ({peaks_src})",
+                    "algorithmic": f"{(p.N + 1) * 8} B in + {(p.n + 1) * 8} B out per bootstrap x {count} + "
+                                   f"{wl.ks_table_bytes} B table once; {wl.ks_bytes_per_boot} B gathered per bootstrap",
+                    "avg_launch_ms": ks_s * 1e3, "share_of_step": ks_ms / max(dev_ms, 1e-9)}
+        else:
+            macs = count * count * (p.n + 1)
+            t_dom = dev_ms / args.steps * 1e-3
+            line["roofline"] = {"bound": "imad", "kernel": "mul_matrix32_kernel", "achieved": macs / t_dom / 1e12,
+                                "peak": imad_peak / 1e12, "unit": "TIMAD32/s", "frac": macs / t_dom / imad_peak,
+                                "traffic": None, "peak_source": imad_src,
+                                "algorithmic": f"{count} x {count} x {p.n + 1} multiply-accumulates, one IMAD32 each",
+                                "avg_launch_ms": t_dom * 1e3, "share_of_step": 1.0}
     ctx.GPUClean()
+    del devt
+    torch.cuda.empty_cache()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        dist.destroy_process_group()    # the other ranks exit and release their GPUs; rank 0 runs the comparison arms
+    if rank == 0:
+        if not args.no_cpu_baseline and n_gpus == 1:
+            arm = CpuArm(wl)
+            _, line["cpu_baseline"] = arm.measure(args.cpu_sample or arm.default_sample())
+        if not args.no_ref_gpu and wl.name == "std128" and args.gate == "NAND":
+            line["reference_gpu"] = reference_gpu_arm(global_batch, n_gpus)
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -36,6 +36,10 @@ typedef enum tfhe_b200_status {
 
 enum { TFHE_B200_HOST = 0, TFHE_B200_DEVICE = 1 };
 enum { TFHE_B200_METHOD_AP = 1, TFHE_B200_METHOD_GINX = 2 };            /* include/binfhe-constants.h:94-98 */
+/* tfhe_b200_params.flags.  KEEP_GENERIC: keep the generic-layout copy of the bootstrapping key in device memory beside
+ * the specialised layout, so that set_option("force_generic") can run the cross-check kernel (tests); by default it is
+ * released at the end of GPUSetup (saves one copy of the key per GPU: 2.1 GB for STD128 AP). */
+enum { TFHE_B200_FLAG_KEEP_GENERIC = 1 };
 /* include/binfhe-constants.h:101 */
 enum { TFHE_B200_OR = 0, TFHE_B200_AND, TFHE_B200_NOR, TFHE_B200_NAND, TFHE_B200_XOR_FAST, TFHE_B200_XNOR_FAST,
        TFHE_B200_XOR, TFHE_B200_XNOR };
@@ -48,7 +52,7 @@ typedef struct tfhe_b200_params {
     uint32_t baseG, digitsG, numDigitsToThrow;
     uint32_t baseR, digitsR;       /* AP/DM refresh base and digit count (0 for GINX)                          */
     uint32_t method;               /* TFHE_B200_METHOD_*                                                       */
-    uint32_t reserved;
+    uint32_t flags;                /* TFHE_B200_FLAG_* (0 = defaults)                                          */
     uint64_t psi;                  /* primitive 2N-th root of unity the BK polynomials were transformed with
                                       (ILNativeParams::GetRootOfUnity(); the engine uses the same bit-reversed
                                       evaluation order as core/include/math/hal/intnat/transformnat-impl.h)   */

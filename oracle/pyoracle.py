@@ -287,6 +287,9 @@ class Port:
     def num_threads(self):
         return int(self.L.tfo_num_threads())
 
+    def set_num_threads(self, n):
+        self.L.tfo_set_num_threads(C.c_int(int(n)))
+
 
 class Ref:
     """The unmodified reference CPU implementation (scalar API looped with OpenMP)."""
@@ -516,3 +519,6 @@ class Ref:
 
     def num_threads(self):
         return int(self.L.ref_num_threads())
+
+    def set_num_threads(self, n):
+        self.L.ref_set_num_threads(C.c_int(int(n)))

@@ -683,4 +683,10 @@ int ref_num_threads() {
     return omp_get_max_threads();
 }
 
+// bench.py sets the thread count explicitly: launchers such as torchrun export OMP_NUM_THREADS=1
+void ref_set_num_threads(int n) {
+    if (n > 0)
+        omp_set_num_threads(n);
+}
+
 }  // extern "C"

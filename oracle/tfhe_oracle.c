@@ -1128,3 +1128,9 @@ int tfo_mul_matrix(const tfo_ctx* c, int in, int outc, const u64* ct, const i64*
 int tfo_num_threads(void) {
     return omp_get_max_threads();
 }
+
+/* bench.py sets the thread count explicitly: launchers such as torchrun export OMP_NUM_THREADS=1 */
+void tfo_set_num_threads(int n) {
+    if (n > 0)
+        omp_set_num_threads(n);
+}

@@ -107,6 +107,7 @@ int tfo_mul_matrix(const tfo_ctx* c, int in, int outc, const uint64_t* ct, const
                    uint64_t* out);
 
 int tfo_num_threads(void);
+void tfo_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -48,7 +48,7 @@ class Params(C.Structure):
         ("baseKS", C.c_uint32), ("dKS", C.c_uint32),
         ("baseG", C.c_uint32), ("digitsG", C.c_uint32), ("numDigitsToThrow", C.c_uint32),
         ("baseR", C.c_uint32), ("digitsR", C.c_uint32),
-        ("method", C.c_uint32), ("reserved", C.c_uint32),
+        ("method", C.c_uint32), ("flags", C.c_uint32),
         ("psi", C.c_uint64), ("beta", C.c_uint64),
     ]
 
@@ -126,9 +126,14 @@ def _is_torch(x):
 
 
 class _Buf:
-    """Uniform view (pointer, space, shape) over a numpy array or a CUDA torch tensor of 64-bit integers."""
+    """Uniform view (pointer, space, shape) over a numpy array or a CUDA torch tensor of 64-bit integers.
+
+    Device tensors: the library runs on its own non-blocking streams and knows nothing about the producer's stream, so
+    the tensor's device is synchronised here before its pointer crosses the C ABI (which is synchronous anyway), and
+    `device` records where it lives so the caller can check it against the handle's first GPU."""
 
     def __init__(self, x, dtype=np.uint64):
+        self.device = None
         if _is_torch(x):
             import torch
 
@@ -137,6 +142,8 @@ class _Buf:
             else:
                 assert x.dtype in (torch.int64, torch.uint64), "device tensors must be 64-bit integers"
                 x = x.contiguous()
+                torch.cuda.current_stream(x.device).synchronize()
+                self.device = x.device.index
                 self.obj, self.ptr, self.space, self.shape = x, C.c_void_p(x.data_ptr()), DEVICE, tuple(x.shape)
                 return
         a = np.ascontiguousarray(x, dtype=dtype)
@@ -180,11 +187,14 @@ class BinFHEContextB200:
     def __init__(self):
         self._h = None
         self.params = None
+        self.first_device = 0
         self.last_stats = Stats()
 
     # ---- lifetime -------------------------------------------------------------------------------------
-    def GPUSetup(self, params, bk, ksk, numGPUs=0, first_device=0):
-        """binfhecontext.cpp:349-360.  `bk`/`ksk` may be numpy arrays or CUDA tensors (e.g. NCCL-broadcast)."""
+    def GPUSetup(self, params, bk, ksk, numGPUs=0, first_device=0, keep_generic=None):
+        """binfhecontext.cpp:349-360.  `bk`/`ksk` may be numpy arrays or CUDA tensors (e.g. NCCL-broadcast; they must
+        live on `first_device`).  `keep_generic` keeps the generic-layout key beside the specialised one so that
+        set_option("force_generic") works (TFHE_B200_FLAG_KEEP_GENERIC; default: environment TFHE_B200_KEEP_GENERIC)."""
         L = load_library()
         if self._h is not None:
             self.GPUClean()  # idempotent re-setup (the reference appends and double-counts GPUs: bootstrapping.cu:762)
@@ -192,15 +202,22 @@ class BinFHEContextB200:
             raise TfheB200Error(-1, "ERROR: Need to call BTKeyGen before calling GPUSetup")
         p = params if isinstance(params, Params) else Params.from_dict(
             params.as_dict() if hasattr(params, "as_dict") else params)
+        if keep_generic is not None:
+            p = Params.from_dict(p.as_dict())
+            p.flags = (p.flags | 1) if keep_generic else (p.flags & ~1)
         b, k = _Buf(bk), _Buf(ksk)
         if b.space != k.space:
             raise TfheB200Error(-1, "GPUSetup: bk and ksk must live in the same memory space")
+        for t in (b, k):
+            if t.space == DEVICE and t.device != first_device:
+                raise TfheB200Error(-1, f"GPUSetup: device-resident keys must live on the first GPU of the handle "
+                                        f"(cuda:{first_device}), got cuda:{t.device}")
         h = C.c_void_p()
         rc = L.tfhe_b200_setup(C.byref(p), b.ptr, C.c_size_t(int(np.prod(b.shape))), k.ptr,
                                C.c_size_t(int(np.prod(k.shape))), b.space, first_device, numGPUs, C.byref(h))
         if rc != 0:
             raise TfheB200Error(rc, L.tfhe_b200_last_error().decode())
-        self._h, self.params = h, p
+        self._h, self.params, self.first_device = h, p, first_device
         return self
 
     def AddKeySet(self, baseG, bk, ksk):
@@ -257,6 +274,13 @@ class BinFHEContextB200:
     def _st(self):
         return C.byref(self.last_stats)
 
+    def _dev(self, *bufs):
+        """Device-space operands must live on the handle's first GPU (include/tfhe_b200.h, `space`)."""
+        for b in bufs:
+            if b.space == DEVICE and b.device != self.first_device:
+                raise TfheB200Error(-1, f"device-resident operands must live on cuda:{self.first_device} "
+                                        f"(the handle's first GPU), got cuda:{b.device}")
+
     @staticmethod
     def _batch(buf, what):
         if len(buf.shape) != 2 or buf.shape[0] == 0:
@@ -267,6 +291,7 @@ class BinFHEContextB200:
     def EvalBinGate(self, gate, ct1, ct2, ct_mod=None, out=None):
         g = GATES[gate] if isinstance(gate, str) else int(gate)
         a, b = _Buf(ct1), _Buf(ct2)
+        self._dev(a, b)
         if a.shape[0] == 0 or b.shape[0] == 0:
             raise TfheB200Error(-1, "ERROR: EvalBinGate: input vector is empty")
         if a.shape != b.shape:
@@ -288,6 +313,7 @@ class BinFHEContextB200:
         outputs; `outputs` the wires to return -> [len(outputs)][batch][n+1].  Bit-identical to evaluating the nodes
         one by one with EvalBinGate / EvalNOT; intermediates never leave the device."""
         a = _Buf(inputs)
+        self._dev(a)
         if len(a.shape) != 3 or a.shape[0] == 0 or a.shape[1] == 0:
             raise TfheB200Error(-1, "ERROR: EvalCircuit: input vector is empty")
         arr = np.zeros((len(nodes), 3), dtype=np.int32)
@@ -304,6 +330,7 @@ class BinFHEContextB200:
 
     def BootstrapFunc(self, ct, ct_mod, table, fmod):
         a, t = _Buf(ct), _Buf(table)
+        self._dev(a, t)
         batch = self._batch(a, "EvalFunc")
         per_ct = int(len(t.shape) == 2)
         out = a.empty_like_out(a.shape)
@@ -313,6 +340,7 @@ class BinFHEContextB200:
 
     def EvalFunc(self, ct, lut, ct_mod=None):
         a, t = _Buf(ct), _Buf(lut)
+        self._dev(a, t)
         batch = self._batch(a, "EvalFunc")
         per_ct = int(len(t.shape) == 2)
         if per_ct and t.shape[0] != batch:
@@ -324,6 +352,7 @@ class BinFHEContextB200:
 
     def EvalFloor(self, ct, ct_mod, roundbits=0):
         a = _Buf(ct)
+        self._dev(a)
         batch = self._batch(a, "EvalFunc")
         out = a.empty_like_out(a.shape)
         self._call("tfhe_b200_eval_floor", self._handle(), batch, a.ptr, C.c_uint64(ct_mod), C.c_uint32(roundbits),
@@ -332,6 +361,7 @@ class BinFHEContextB200:
 
     def EvalSign(self, ct, ct_mod):
         a = _Buf(ct)
+        self._dev(a)
         batch = self._batch(a, "EvalFunc")
         out = a.empty_like_out(a.shape)
         self._call("tfhe_b200_eval_sign", self._handle(), batch, a.ptr, C.c_uint64(ct_mod), _Buf(out).ptr, a.space,
@@ -340,6 +370,7 @@ class BinFHEContextB200:
 
     def EvalDecomp(self, ct, ct_mod, max_digits=8):
         a = _Buf(ct)
+        self._dev(a)
         batch = self._batch(a, "EvalFunc")
         out = a.empty_like_out((batch, max_digits, a.shape[1]))
         mods = np.zeros(max_digits, dtype=np.uint64)
@@ -349,7 +380,9 @@ class BinFHEContextB200:
 
     def CiphertextMulMatrix(self, ct, matrix, modulus):
         a = _Buf(ct)
+        self._dev(a)
         m = _Buf(matrix, dtype=np.int64)
+        self._dev(m)
         if len(a.shape) != 2 or a.shape[0] == 0:
             raise TfheB200Error(-1, "Input ciphertexts are empty.")
         if len(m.shape) != 2 or m.shape[0] == 0 or m.shape[1] == 0:
@@ -365,6 +398,7 @@ class BinFHEContextB200:
     def EvalAcc(self, a_mask, ct_mod, acc):
         """GPUFFTBootstrap::EvalAcc_CUDA contract (bootstrapping.cuh:111-124)."""
         a, ac = _Buf(a_mask), _Buf(acc)
+        self._dev(a, ac)
         out = ac.obj.clone() if ac.space == DEVICE else ac.obj.copy()
         self._call("tfhe_b200_eval_acc", self._handle(), a.shape[0], a.ptr, C.c_uint64(ct_mod), _Buf(out).ptr,
                    a.space, self._st())
@@ -373,6 +407,7 @@ class BinFHEContextB200:
     def MKMSwitch(self, ct_ext, fmod):
         """GPUFFTBootstrap::MKMSwitch_CUDA contract (bootstrapping.cuh:126-136)."""
         a = _Buf(ct_ext)
+        self._dev(a)
         out = a.empty_like_out((a.shape[0], self.params.n + 1))
         self._call("tfhe_b200_mkmswitch", self._handle(), a.shape[0], a.ptr, C.c_uint64(fmod), _Buf(out).ptr, a.space,
                    self._st())

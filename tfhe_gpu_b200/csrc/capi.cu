@@ -6,12 +6,16 @@
 // std::vector<LWECiphertext> twice per bootstrap, bootstrapping.cu:1616-1667,1877-1905).
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "engine.cuh"
@@ -48,13 +52,70 @@ struct Arena {
     size_t cap = 0, off = 0;
 };
 
+// Handle-owned pinned staging for pageable host buffers (the reference keeps acc_host / ctExt_host pinned for 65536
+// ciphertexts, bootstrapping.cu:904-905): grow-only, carved per call like the device arena.
+struct Pinned {
+    unsigned char* base = nullptr;
+    size_t cap = 0, off = 0;
+};
+struct PendingOut {   // staged device->host copy: finished by a host memcpy once the stream has drained
+    void* dst;
+    const void* src;
+    size_t bytes;
+};
+
+// One host worker thread per GPU of a multi-GPU handle: the per-device body of a sharded call (launches, staging
+// memcpys, the final stream synchronisation) runs on it, so GPU k+1 is fed while GPU k is still being fed / drained.
+// The reference drives all GPUs from a single host thread (bootstrapping.cu:1616-1667).
+class Worker {
+  public:
+    Worker() : th_([this] { loop(); }) {}
+    ~Worker() {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        th_.join();
+    }
+    void submit(std::function<int()> f) {
+        {
+            std::lock_guard<std::mutex> l(m_);
+            job_ = std::move(f);
+            has_job_ = true;
+            done_ = false;
+        }
+        cv_.notify_all();
+    }
+    int wait(std::string* err) {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [this] { return done_; });
+        if (rc_ && err)
+            *err = err_;
+        return rc_;
+    }
+
+  private:
+    void loop();
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::function<int()> job_;
+    bool has_job_ = false, done_ = true, quit_ = false;
+    int rc_ = 0;
+    std::string err_;
+    std::thread th_;
+};
+
+constexpr int MAX_CHUNKS = 10;   // chunks of the pipelined host-buffer path
+
 struct Dev {
     int id = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t xfer_in = nullptr, xfer_out = nullptr;   // host<->device copies of the pipelined host-buffer path
     cudaEvent_t ev[6] = {};
-    cudaEvent_t pev[17] = {};                             // per-chunk hand-over events (no timing)
+    unsigned ev_mask = 0;                                 // which of ev[] were recorded by the current call
+    cudaEvent_t pev[3 * MAX_CHUNKS + 1] = {};             // per-chunk hand-over events (no timing)
     // key material / tables
     void* bk_generic = nullptr;
     u32* bk_cggi32 = nullptr;
@@ -74,7 +135,29 @@ struct Dev {
     void* ksk = nullptr;
     u64* ks_partial = nullptr;   // column-sum accumulator of split key switches (batches below one ciphertext per SM)
     Arena ws;
+    Pinned pin;                         // pinned host staging (inputs and outputs of the current call)
+    std::vector<PendingOut> pending;    // staged outputs to hand to the caller after the stream has drained
+    std::unique_ptr<Worker> worker;     // multi-GPU handles only
 };
+
+void Worker::loop() {
+    std::unique_lock<std::mutex> l(m_);
+    for (;;) {
+        cv_.wait(l, [this] { return has_job_ || quit_; });
+        if (quit_)
+            return;
+        std::function<int()> f = std::move(job_);
+        has_job_ = false;
+        l.unlock();
+        g_err.clear();
+        int rc = f();
+        l.lock();
+        rc_ = rc;
+        err_ = g_err;   // g_err is thread-local: hand the message to the calling thread
+        done_ = true;
+        cv_.notify_all();
+    }
+}
 
 }  // namespace
 
@@ -88,6 +171,7 @@ struct tfhe_b200_handle {
     bool have_cggi64w = false;   // wide variant usable (skip-top path of a supported ring)
     std::vector<u64> twA64_host;
     int force_generic = 0;
+    bool keep_generic = false;   // generic key layout retained beside the specialised one (cross-check kernel)
     int group = 0;  // ciphertexts per CTA of the cggi32 kernel (0 = default)
     u32 logN = 0, d = 0, gBits = 0;
     ModCtx<u32> m32;
@@ -130,22 +214,89 @@ static int arena_reserve(Dev& d, size_t bytes) {
     d.ws.base = nullptr;
     d.ws.cap = 0;
     size_t cap = bytes + (bytes >> 3) + (1 << 20);
-    CUDA_TRY(cudaMalloc((void**)&d.ws.base, cap));
+    if (cudaMalloc((void**)&d.ws.base, cap) != cudaSuccess) {
+        cudaGetLastError();
+        d.ws.base = nullptr;
+        FAIL(TFHE_B200_ENOMEM, "workspace: cudaMalloc of " + std::to_string(cap) + " bytes failed on device " +
+                                   std::to_string(d.id));
+    }
     d.ws.cap = cap;
     d.ws.off = 0;
     return 0;
 }
+// nullptr when the reservation was computed too small (a programming error in this file): the caller reports
+// TFHE_B200_ENOMEM instead of handing a kernel a bad pointer -- the library never exits the process
 template <typename T>
 static T* arena_take(Dev& d, size_t count) {
     size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
     if (d.ws.off + bytes > d.ws.cap) {
-        // a reservation computed too small is a programming error in this file: stop instead of handing a kernel a null
-        fprintf(stderr, "tfhe_b200: workspace arena overrun (%zu + %zu > %zu)\n", d.ws.off, bytes, d.ws.cap);
-        abort();
+        char buf[160];
+        snprintf(buf, sizeof(buf), "workspace arena overrun (%zu + %zu > %zu)", d.ws.off, bytes, d.ws.cap);
+        g_err = buf;
+        return nullptr;
     }
     T* p = reinterpret_cast<T*>(d.ws.base + d.ws.off);
     d.ws.off += bytes;
     return p;
+}
+#define TAKE(var, T, d, count)              \
+    T* var = arena_take<T>(d, count);       \
+    if (!var)                               \
+        return TFHE_B200_ENOMEM
+
+// ---- pinned staging --------------------------------------------------------------------------------------------
+static const size_t PIN_LIMIT = (size_t)3 << 30;   // larger calls copy straight from / to the caller's pageable memory
+
+// true when the CUDA driver can DMA from / to this host pointer directly (cudaHostAlloc / cudaHostRegister memory)
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+// reserve `bytes` of pinned staging for the current call (grow-only); failure is not an error: the copies then go
+// through the driver's own pageable path
+static void pin_reserve(Dev& d, size_t bytes) {
+    d.pin.off = 0;
+    if (bytes <= d.pin.cap || bytes > PIN_LIMIT)
+        return;
+    cudaSetDevice(d.id);
+    cudaStreamSynchronize(d.stream);
+    if (d.pin.base)
+        cudaFreeHost(d.pin.base);
+    d.pin.base = nullptr;
+    d.pin.cap = 0;
+    size_t cap = bytes + (bytes >> 3) + (1 << 20);
+    if (cudaHostAlloc((void**)&d.pin.base, cap, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        d.pin.base = nullptr;
+        return;
+    }
+    d.pin.cap = cap;
+}
+static unsigned char* pin_take(Dev& d, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (!d.pin.base || d.pin.off + bytes > d.pin.cap)
+        return nullptr;
+    unsigned char* p = d.pin.base + d.pin.off;
+    d.pin.off += bytes;
+    return p;
+}
+// host memcpy on a few threads (a single core moves ~10 GB/s, less than one GPU's PCIe link)
+static void par_memcpy(void* dst, const void* src, size_t bytes) {
+    const size_t blk = (size_t)2 << 20;
+    if (bytes < 2 * blk) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const long nblk = (long)((bytes + blk - 1) / blk);
+#pragma omp parallel for num_threads(4) schedule(static)
+    for (long b = 0; b < nblk; b++) {
+        const size_t o = (size_t)b * blk;
+        memcpy((char*)dst + o, (const char*)src + o, std::min(blk, bytes - o));
+    }
 }
 
 static u32 bitrev32(u32 x, u32 bits) {
@@ -164,11 +315,19 @@ static void shard_of(int batch, int nd, int k, int* start, int* count) {
     *count = base + (k < rem ? 1 : 0);
 }
 
+// Host-space copies of pageable memory go through the handle's pinned staging when the call reserved room for them
+// (pin_reserve): a host memcpy + a true asynchronous DMA instead of the driver's blocking pageable path.
 static int copy_in(Dev& d, Dev& d0, void* dst, const void* src, size_t bytes, int space) {
     if (!bytes)
         return 0;
-    if (space == TFHE_B200_HOST)
+    if (space == TFHE_B200_HOST) {
+        unsigned char* st = (bytes >= (64 << 10) && !host_is_pinned(src)) ? pin_take(d, bytes) : nullptr;
+        if (st) {
+            par_memcpy(st, src, bytes);
+            src = st;
+        }
         CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, d.stream));
+    }
     else if (d.id == d0.id)
         CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, d.stream));
     else
@@ -178,13 +337,24 @@ static int copy_in(Dev& d, Dev& d0, void* dst, const void* src, size_t bytes, in
 static int copy_out(Dev& d, Dev& d0, void* dst, const void* src, size_t bytes, int space) {
     if (!bytes)
         return 0;
-    if (space == TFHE_B200_HOST)
+    if (space == TFHE_B200_HOST) {
+        unsigned char* st = (bytes >= (64 << 10) && !host_is_pinned(dst)) ? pin_take(d, bytes) : nullptr;
+        if (st) {
+            d.pending.push_back(PendingOut{dst, st, bytes});   // finished by run_sharded after the stream has drained
+            dst = st;
+        }
         CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, d.stream));
+    }
     else if (d.id == d0.id)
         CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, d.stream));
     else
         CUDA_TRY(cudaMemcpyPeerAsync(dst, d0.id, src, d.id, bytes, d.stream));
     return 0;
+}
+// phase marker i of the current call (timing events of tfhe_b200_stats)
+static cudaError_t rec_ev(Dev& d, int i) {
+    d.ev_mask |= 1u << i;
+    return cudaEventRecord(d.ev[i], d.stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -407,8 +577,13 @@ extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_
     if (!h || !key)
         FAIL(TFHE_B200_EINVAL, "set_option: null argument");
     std::string k(key);
-    if (k == "force_generic")
+    if (k == "force_generic") {
+        if (value && !h->devs.empty() && !h->devs[0].bk_generic)
+            FAIL(TFHE_B200_EINVAL, "set_option: force_generic needs the generic key layout, which this handle released "
+                                   "(set TFHE_B200_FLAG_KEEP_GENERIC in params.flags or TFHE_B200_KEEP_GENERIC=1 "
+                                   "before GPUSetup)");
         h->force_generic = (int)value;
+    }
     else if (k == "group")
         h->group = (int)value;
     else
@@ -419,6 +594,7 @@ extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_
 }
 
 static int free_dev(Dev& d, bool borrowed_streams = false) {
+    d.worker.reset();   // joins the worker thread (idle between calls)
     cudaSetDevice(d.id);
     if (borrowed_streams)
         d.stream = d.xfer_in = d.xfer_out = nullptr;
@@ -428,6 +604,8 @@ static int free_dev(Dev& d, bool borrowed_streams = false) {
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
+    if (d.pin.base)
+        cudaFreeHost(d.pin.base);
     for (auto& e : d.ev)
         if (e)
             cudaEventDestroy(e);
@@ -524,6 +702,7 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
     h->variant = h->is64 ? "generic_u64" : "generic_u32";
     if (p.method == TFHE_B200_METHOD_AP)
         h->variant += "_dm";
+    h->keep_generic = (p.flags & TFHE_B200_FLAG_KEEP_GENERIC) || getenv("TFHE_B200_KEEP_GENERIC");
 
     h->devs.resize(num_gpus);
     int rc = 0;
@@ -543,6 +722,8 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                 CUDA_TRY(cudaEventCreate(&e));
             for (auto& e : d.pev)
                 CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            if (num_gpus > 1)
+                d.worker.reset(new Worker());
             int r = h->is64 ? build_tables<u64>(h, d, h->m64) : build_tables<u32>(h, d, h->m32);
             if (r)
                 return r;
@@ -586,69 +767,61 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                             : encode_keys<u32>(h, d0, h->m32, bk, ksk, key_space);
             if (r)
                 return r;
-            if (h->have_cggi32) {
-                CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi32, h->bk_words * 4));
-                // constants for the top-digit elimination: B^(l-top) (l < top) and B^-top, Montgomery form
-                const u32 dk = h->d / 2, top = dk - 1;
-                std::vector<u32> cM(dk);
-                const u64 Binv = h_powmod(p.baseG % p.Q, p.Q - 2, p.Q);
-                for (u32 l = 0; l < dk; l++) {
-                    u64 cst = h_powmod(Binv, l == top ? top : top - l, p.Q);
-                    if (l == top)   // the kernel keeps acc_eval scaled by N^-1: compensate in the row it multiplies
-                        cst = h_mulmod(cst, p.N % p.Q, p.Q);
-                    cM[l] = to_mont<u32>(cst, h->m32);
-                }
-                u32* dcM = nullptr;
-                CUDA_TRY(cudaMalloc((void**)&dcM, dk * 4));
-                CUDA_TRY(cudaMemcpy(dcM, cM.data(), dk * 4, cudaMemcpyHostToDevice));
-                bk_relayout_cggi32_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi32, (const u32*)d0.bk_generic, p.n,
-                                                                          h->d, p.N, h->m32, h->skip_top ? 1 : 0, dcM);
-                CUDA_TRY(cudaGetLastError());
-                CUDA_TRY(cudaStreamSynchronize(d0.stream));
-                CUDA_TRY(cudaFree(dcM));
-                CUDA_TRY(cudaGetLastError());
-                CUDA_TRY(cudaStreamSynchronize(d0.stream));
-            }
-            if (h->have_cggi64) {
-                const u32 dk = h->d / 2, top = dk - 1;
+            // constants of the top-digit elimination: B^(l-top) (l < top) and N * B^-top, Montgomery form (the kernels
+            // keep acc_eval scaled by N^-1: compensated in the row it multiplies); see the re-layout kernels above
+            const u32 dk = h->d / 2, top = dk - 1;
+            auto upload_cM = [&](void** dcM) -> int {
                 std::vector<u64> cM(dk);
                 const u64 Binv = h_powmod(p.baseG % p.Q, p.Q - 2, p.Q);
                 for (u32 l = 0; l < dk; l++) {
                     u64 cst = h_powmod(Binv, l == top ? top : top - l, p.Q);
                     if (l == top)
                         cst = h_mulmod(cst, p.N % p.Q, p.Q);
-                    cM[l] = to_mont<u64>(cst, h->m64);
+                    cM[l] = h->is64 ? to_mont<u64>(cst, h->m64) : (u64)to_mont<u32>(cst, h->m32);
                 }
-                u64* dcM = nullptr;
-                CUDA_TRY(cudaMalloc((void**)&dcM, dk * 8));
-                CUDA_TRY(cudaMemcpy(dcM, cM.data(), dk * 8, cudaMemcpyHostToDevice));
+                const size_t tsz = h->is64 ? 8 : 4;
+                std::vector<u32> cM32(cM.begin(), cM.end());
+                CUDA_TRY(cudaMalloc(dcM, dk * tsz));
+                CUDA_TRY(cudaMemcpy(*dcM, h->is64 ? (const void*)cM.data() : (const void*)cM32.data(), dk * tsz,
+                                    cudaMemcpyHostToDevice));
+                return 0;
+            };
+            void* dcM = nullptr;
+            if (h->have_cggi32 || h->have_cggi64 || h->have_dm32) {
+                r = upload_cM(&dcM);
+                if (r)
+                    return r;
+            }
+            if (h->have_cggi32) {
+                CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi32, h->bk_words * 4));
+                bk_relayout_cggi32_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi32, (const u32*)d0.bk_generic, p.n,
+                                                                          h->d, p.N, h->m32, h->skip_top ? 1 : 0,
+                                                                          (const u32*)dcM);
+                CUDA_TRY(cudaGetLastError());
+            }
+            if (h->have_cggi64) {
                 CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi64, h->bk_words * 8));
                 bk_relayout_cggi64_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi64, (const u64*)d0.bk_generic, p.n,
-                                                                          h->d, p.N, h->m64, h->skip_top ? 1 : 0, dcM);
+                                                                          h->d, p.N, h->m64, h->skip_top ? 1 : 0,
+                                                                          (const u64*)dcM);
                 CUDA_TRY(cudaGetLastError());
-                CUDA_TRY(cudaStreamSynchronize(d0.stream));
-                CUDA_TRY(cudaFree(dcM));
             }
             if (h->have_dm32) {
-                const u32 dk = h->d / 2, top = dk - 1;
-                std::vector<u32> cM(dk);
-                const u64 Binv = h_powmod(p.baseG % p.Q, p.Q - 2, p.Q);
-                for (u32 l = 0; l < dk; l++) {
-                    u64 cst = h_powmod(Binv, l == top ? top : top - l, p.Q);
-                    if (l == top)
-                        cst = h_mulmod(cst, p.N % p.Q, p.Q);
-                    cM[l] = to_mont<u32>(cst, h->m32);
-                }
-                u32* dcM = nullptr;
-                CUDA_TRY(cudaMalloc((void**)&dcM, dk * 4));
-                CUDA_TRY(cudaMemcpy(dcM, cM.data(), dk * 4, cudaMemcpyHostToDevice));
                 CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi32, h->bk_words * 4));
                 bk_relayout_dm32_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi32, (const u32*)d0.bk_generic,
                                                                         (size_t)p.n * p.baseR * p.digitsR, h->d, p.N,
-                                                                        h->m32, dcM);
+                                                                        h->m32, (const u32*)dcM);
                 CUDA_TRY(cudaGetLastError());
-                CUDA_TRY(cudaStreamSynchronize(d0.stream));
+            }
+            CUDA_TRY(cudaStreamSynchronize(d0.stream));
+            if (dcM)
                 CUDA_TRY(cudaFree(dcM));
+            // The generic layout is only the source of the specialised ones: release it once they exist, unless the
+            // caller asked to keep the cross-check kernel available (params.flags bit 0 or TFHE_B200_KEEP_GENERIC=1;
+            // set_option("force_generic") needs it).  STD128-AP: 2.1 GB, logQ = 17: 513 MB saved per GPU.
+            if (!h->keep_generic && (h->have_cggi32 || h->have_cggi64 || h->have_dm32)) {
+                CUDA_TRY(cudaFree(d0.bk_generic));
+                d0.bk_generic = nullptr;
             }
             const size_t tsz = h->is64 ? 8 : 4;
             const size_t ksk_bytes_total = (size_t)p.N * p.baseKS * p.dKS * h->row_stride * h->ksk_bytes;
@@ -663,8 +836,10 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
                         CUDA_TRY(pe);
                     cudaGetLastError();
                 }
-                CUDA_TRY(cudaMalloc(&d.bk_generic, h->bk_words * tsz));
-                CUDA_TRY(cudaMemcpyPeerAsync(d.bk_generic, d.id, d0.bk_generic, d0.id, h->bk_words * tsz, d.stream));
+                if (d0.bk_generic) {
+                    CUDA_TRY(cudaMalloc(&d.bk_generic, h->bk_words * tsz));
+                    CUDA_TRY(cudaMemcpyPeerAsync(d.bk_generic, d.id, d0.bk_generic, d0.id, h->bk_words * tsz, d.stream));
+                }
                 if (h->have_cggi32 || h->have_dm32) {
                     CUDA_TRY(cudaMalloc((void**)&d.bk_cggi32, h->bk_words * 4));
                     CUDA_TRY(cudaMemcpyPeerAsync(d.bk_cggi32, d.id, d0.bk_cggi32, d0.id, h->bk_words * 4, d.stream));
@@ -723,6 +898,7 @@ extern "C" int tfhe_b200_add_key_set(tfhe_b200_handle* h, uint32_t baseG, const 
     // the child only ever runs inside the parent's calls: same streams, so stream order covers every dependency
     for (size_t k = 0; k < c->devs.size(); k++) {
         Dev& d = c->devs[k];
+        d.worker.reset();   // the child runs on the parent's workers
         cudaSetDevice(d.id);
         cudaStreamDestroy(d.stream);
         cudaStreamDestroy(d.xfer_in);
@@ -753,21 +929,8 @@ struct AccDesc {
     u64 ext_add_b = 0;
 };
 
-static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u64 ct_mod, const AccDesc& a, u64* ext,
-                        int* launches) {
-    const tfhe_b200_params& p = h->p;
-    BRCommon c;
-    memset(&c, 0, sizeof(c));
-    c.N = p.N; c.logN = h->logN; c.n = p.n; c.d = h->d;
-    c.gBits = h->gBits; c.numThrow = (p.method == TFHE_B200_METHOD_GINX) ? p.numDigitsToThrow : 0;
-    c.digitsKept = h->d / 2;
-    c.method = p.method; c.baseR = p.baseR; c.digitsR = p.digitsR; c.q_lwe = p.q;
-    c.batch = batch; c.ct = ct; c.ct_mod = ct_mod;
-    c.acc_init = a.mode; c.gate_q1 = a.gate_q1; c.Q8 = p.Q / 8 + 1;
-    c.scale = a.fmod ? p.Q / a.fmod : 0;
-    c.table = a.table; c.acc_io = a.acc_io; c.write_acc = a.write_acc;
-    c.ext = ext; c.ext_add_b = a.ext_add_b;
-    if (batch <= 0)
+static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, int* launches) {
+    if (c.batch <= 0)
         return 0;
     if (h->have_cggi32 && !h->force_generic) {
         CGGI32Tables t;
@@ -792,6 +955,8 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
         t.twA = d.twU64; t.skip_top = h->skip_top;
         CUDA_TRY(launch_br_cggi64(c, t, d.stream, h->group));
     }
+    else if (!d.bk_generic)
+        FAIL(TFHE_B200_EINVAL, "blind rotation: the generic key layout was released at GPUSetup");
     else if (h->is64) {
         BRTables<u64> t;
         t.mod = h->m64; t.tw_fwd = (const u64*)d.tw_fwd; t.tw_inv = (const u64*)d.tw_inv;
@@ -811,6 +976,86 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
     return 0;
 }
 
+// Ciphertexts per CTA of the throughput shape of the active kernel (one CTA per SM: a wave is sm_count x this many).
+static int throughput_group(const tfhe_b200_handle* h) {
+    const u32 dk = h->d / 2;
+    if (h->force_generic)
+        return 1;
+    if (h->group > 0)
+        return h->group;
+    if (h->have_cggi32)
+        return h->logN == 10 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4);
+    if (h->have_dm32)
+        return 4;
+    if (h->have_cggi64)
+        return dk <= 3 ? 2 : 1;
+    return 1;
+}
+// ... and the largest remainder (in ciphertexts per SM) for which the kernel has a latency shape; 0 = none.
+static void tail_shapes(const tfhe_b200_handle* h, int* per_cta, int* tail_per_sm) {
+    *per_cta = *tail_per_sm = 0;
+    if (h->force_generic || h->group != 0)
+        return;
+    const u32 dk = h->d / 2;
+    if (h->have_cggi32) {
+        if (h->logN == 10 && dk == 4) {   // CTAs of 4; CTAs of 2 (<= 2 per SM) and the latency layout (<= 1 per SM)
+            *per_cta = 4;
+            *tail_per_sm = 2;
+        }
+    }
+    else if (h->have_dm32) {
+        *per_cta = 4;
+        *tail_per_sm = 2;
+    }
+    else if (h->have_cggi64w && dk <= 3 && !getenv("TFHE_B200_C64_NARROW")) {
+        *per_cta = 2;                      // CTAs of 2 (16 warps); one ciphertext per CTA (<= 1 per SM)
+        *tail_per_sm = 1;
+    }
+}
+
+static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u64 ct_mod, const AccDesc& a, u64* ext,
+                        int* launches) {
+    const tfhe_b200_params& p = h->p;
+    BRCommon c;
+    memset(&c, 0, sizeof(c));
+    c.N = p.N; c.logN = h->logN; c.n = p.n; c.d = h->d;
+    c.gBits = h->gBits; c.numThrow = (p.method == TFHE_B200_METHOD_GINX) ? p.numDigitsToThrow : 0;
+    c.digitsKept = h->d / 2;
+    c.method = p.method; c.baseR = p.baseR; c.digitsR = p.digitsR; c.q_lwe = p.q;
+    c.batch = batch; c.ct = ct; c.ct_mod = ct_mod;
+    c.acc_init = a.mode; c.gate_q1 = a.gate_q1; c.Q8 = p.Q / 8 + 1;
+    c.scale = a.fmod ? p.Q / a.fmod : 0;
+    c.table = a.table; c.acc_io = a.acc_io; c.write_acc = a.write_acc;
+    c.ext = ext; c.ext_add_b = a.ext_add_b;
+    if (batch <= 0)
+        return 0;
+    // Wave quantisation: CTAs walk the n rotation steps in lock-step, so a launch costs ceil(CTAs / SMs) wave times and
+    // a last wave that fills only part of the SMs still costs a whole one.  When that remainder is small enough for a
+    // latency shape (fewer ciphertexts per CTA: a shorter step), it runs as a second launch of that shape instead --
+    // STD128 at 2048 ciphertexts per GPU (16384 over 8 GPUs): 3 waves of 5.7 ms + one of 4.4 ms instead of 4 x 5.7 ms.
+    int per_cta, tail_per_sm;
+    tail_shapes(h, &per_cta, &tail_per_sm);
+    const int wave = per_cta * d.sm_count;
+    const int rem = wave ? batch % wave : 0;
+    if (wave && batch > wave && rem > 0 && rem <= tail_per_sm * d.sm_count && !getenv("TFHE_B200_NO_TAIL")) {
+        const int head = batch - rem;
+        c.batch = head;
+        int r = blind_rotate_launch(h, d, c, launches);
+        if (r)
+            return r;
+        c.batch = rem;
+        c.ct = ct + (size_t)head * (p.n + 1);
+        if (c.table && a.mode == ACC_TABLE_PER)
+            c.table = a.table + (size_t)head * ct_mod;
+        if (c.acc_io)
+            c.acc_io = a.acc_io + (size_t)head * 2 * p.N;
+        if (c.ext)
+            c.ext = ext + (size_t)head * (p.N + 1);
+        return blind_rotate_launch(h, d, c, launches);
+    }
+    return blind_rotate_launch(h, d, c, launches);
+}
+
 static int mkmswitch_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* ext, u64 fmod, u64* out, int* launches) {
     const tfhe_b200_params& p = h->p;
     KSArgs a;
@@ -826,12 +1071,12 @@ static int mkmswitch_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* ext,
 
 // One bootstrap = blind rotation + extraction + MS/KS/MS.  `ext` is scratch of batch*(N+1) words.
 static int bootstrap_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u64 ct_mod, const AccDesc& a, u64 fmod,
-                         u64* ext, u64* out, int* launches, cudaEvent_t ev_mid = nullptr) {
+                         u64* ext, u64* out, int* launches, int ev_mid = -1) {
     int rc = blind_rotate(h, d, batch, ct, ct_mod, a, ext, launches);
     if (rc)
         return rc;
-    if (ev_mid)
-        CUDA_TRY(cudaEventRecord(ev_mid, d.stream));
+    if (ev_mid >= 0)
+        CUDA_TRY(rec_ev(d, ev_mid));
     return mkmswitch_dev(h, d, batch, ext, fmod, out, launches);
 }
 
@@ -878,7 +1123,7 @@ static int gate_dev(tfhe_b200_handle* h, Dev& d, int gate, int batch, const u64*
         AFFINE(prep, c1, c2, 1, 1, 0, 0, q, 0);   // ct1 + ct2
     AccDesc a;
     a.mode = ACC_GATE; a.gate_q1 = mult[gate] * (p.q >> 3); a.ext_add_b = p.Q / 8 + 1;
-    int rc = bootstrap_dev(h, d, batch, prep, q, a, q, ext, out, launches, d.ev[2]);
+    int rc = bootstrap_dev(h, d, batch, prep, q, a, q, ext, out, launches, 2);
     (*nboot)++;
     return rc;
 }
@@ -892,13 +1137,12 @@ static int floor_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* in, u64 
     const u64 beta = p.beta;
     const u64 q = roundbits == 0 ? p.q : beta * 2 * (1ULL << roundbits);
     u64 *cq = tmp, *r = tmp + S;
-    std::vector<u64> f(q);
     AFFINE(out, in, nullptr, 1, 0, 0, beta, mod, 0);   // ct1 = ct + beta
     AFFINE(cq, out, nullptr, 1, 0, 0, 0, mod, q);      // ct1Modq
-    for (u64 x = 0; x < q; x++)
-        f[x] = (x < q / 2) ? mod - q / 4 : q / 4;
-    CUDA_TRY(cudaMemcpyAsync(tab, f.data(), q * 8, cudaMemcpyHostToDevice, d.stream));
-    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    // f1(x) = x < q/2 ? Q - q/4 : q/4  (binfhe-base-scheme.cpp:934-939); tables are generated on the device in stream
+    // order, so the body never waits for the GPU
+    CUDA_TRY(launch_step_table(tab, STEP_HALF, q, mod - q / 4, q / 4, d.stream));
+    (*launches)++;
     AccDesc a;
     a.mode = ACC_TABLE; a.table = tab; a.fmod = mod;
     int rc = bootstrap_dev(h, d, batch, cq, q, a, mod, ext, r, launches);
@@ -906,17 +1150,9 @@ static int floor_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* in, u64 
     (*nboot)++;
     AFFINE(out, out, r, 1, -1, 0, 0, mod, 0);          // ct1 -= ct2
     AFFINE(cq, out, nullptr, 1, 0, 0, 0, mod, q);      // ct2Modq
-    for (u64 x = 0; x < q; x++) {
-        if (x < q / 4)
-            f[x] = mod - q / 2 - x;
-        else if (x < 3 * q / 4)
-            f[x] = x;
-        else
-            f[x] = mod + q / 2 - x;
-    }
-    CUDA_TRY(cudaStreamSynchronize(d.stream));  // previous bootstrap still reads `tab`
-    CUDA_TRY(cudaMemcpyAsync(tab, f.data(), q * 8, cudaMemcpyHostToDevice, d.stream));
-    CUDA_TRY(cudaStreamSynchronize(d.stream));
+    // f2 (binfhe-base-scheme.cpp:941-952)
+    CUDA_TRY(launch_step_table(tab, STEP_FLOOR2, q, mod, 0, d.stream));
+    (*launches)++;
     rc = bootstrap_dev(h, d, batch, cq, q, a, mod, ext, r, launches);
     if (rc) return rc;
     (*nboot)++;
@@ -934,59 +1170,81 @@ struct CallCtx {
     int nboot = 0;
 };
 
+// Runs `body` once per GPU on that GPU's shard.  A single-GPU handle runs it inline; a multi-GPU handle hands every
+// shard to that GPU's worker thread, so all GPUs are fed, drained and synchronised concurrently (the reference walks its
+// GPUs from one host thread: bootstrapping.cu:1616-1667, :1642-1646).
 template <typename F>
 static int run_sharded(tfhe_b200_handle* h, int batch, tfhe_b200_stats* stats, F body) {
     std::lock_guard<std::mutex> lock(h->mu);
     const int nd = (int)h->devs.size();
-    int launches = 0, nboot = 0;
-    int rc = 0;
-    for (int k = 0; k < nd && rc == 0; k++) {
+    std::vector<int> launches(nd, 0), nboot(nd, 0);
+    auto per_dev = [&](int k) -> int {
         Dev& d = h->devs[k];
         int start, count;
         shard_of(batch, nd, k, &start, &count);
+        d.ev_mask = 0;
+        d.pending.clear();
+        d.pin.off = 0;
         auto run = [&]() -> int {
             CUDA_TRY(cudaSetDevice(d.id));
-            if (k == 0)
-                CUDA_TRY(cudaEventRecord(d.ev[0], d.stream));
-            int nb = 0;
-            int r = body(d, start, count, &launches, &nb);
-            if (k == 0)
-                nboot = nb;
+            CUDA_TRY(rec_ev(d, 0));
+            int r = count > 0 ? body(d, start, count, &launches[k], &nboot[k]) : 0;
             if (r)
                 return r;
-            if (k == 0)
-                CUDA_TRY(cudaEventRecord(d.ev[5], d.stream));
+            CUDA_TRY(rec_ev(d, 5));
             return 0;
         };
-        rc = run();
-    }
-    for (int k = 0; k < nd; k++) {
-        Dev& d = h->devs[k];
-        cudaSetDevice(d.id);
-        cudaError_t e = cudaStreamSynchronize(d.stream);
+        int rc = run();
+        cudaError_t e = cudaStreamSynchronize(d.stream);   // also on failure: nothing of this call may stay in flight
         if (e != cudaSuccess && rc == 0) {
             g_err = std::string("stream sync failed: ") + cudaGetErrorString(e);
             rc = TFHE_B200_ECUDA;
         }
+        if (rc == 0)
+            for (const PendingOut& po : d.pending)
+                par_memcpy(po.dst, po.src, po.bytes);
+        d.pending.clear();
+        return rc;
+    };
+    int rc = 0;
+    if (nd == 1)
+        rc = per_dev(0);
+    else {
+        for (int k = 0; k < nd; k++)
+            h->devs[k].worker->submit([&per_dev, k] { return per_dev(k); });
+        for (int k = 0; k < nd; k++) {
+            std::string err;
+            int r = h->devs[k].worker->wait(&err);
+            if (r && rc == 0) {
+                rc = r;
+                g_err = err;
+            }
+        }
     }
     if (rc == 0 && stats) {
         memset(stats, 0, sizeof(*stats));
+        // phases from the first GPU (fields whose markers this call did not record stay 0), total = slowest GPU
         Dev& d0 = h->devs[0];
+        auto span = [&](Dev& d, int a, int b, float* out) {
+            float t = 0;
+            if ((d.ev_mask >> a & 1) && (d.ev_mask >> b & 1) && cudaEventElapsedTime(&t, d.ev[a], d.ev[b]) == cudaSuccess)
+                *out = t;
+        };
+        for (Dev& d : h->devs) {
+            cudaSetDevice(d.id);
+            float t = 0;
+            span(d, 0, 5, &t);
+            stats->total_ms = std::max(stats->total_ms, t);
+        }
         cudaSetDevice(d0.id);
-        float t = 0;
-        if (cudaEventElapsedTime(&t, d0.ev[0], d0.ev[5]) == cudaSuccess)
-            stats->total_ms = t;
-        if (cudaEventElapsedTime(&t, d0.ev[0], d0.ev[1]) == cudaSuccess)
-            stats->h2d_ms = t;
-        if (cudaEventElapsedTime(&t, d0.ev[1], d0.ev[2]) == cudaSuccess)
-            stats->blind_rotate_ms = t;
-        if (cudaEventElapsedTime(&t, d0.ev[2], d0.ev[3]) == cudaSuccess)
-            stats->keyswitch_ms = t;
-        if (cudaEventElapsedTime(&t, d0.ev[4], d0.ev[5]) == cudaSuccess)
-            stats->d2h_ms = t;
+        span(d0, 0, 1, &stats->h2d_ms);
+        span(d0, 1, 2, &stats->blind_rotate_ms);
+        span(d0, 2, 3, &stats->keyswitch_ms);
+        span(d0, 4, 5, &stats->d2h_ms);
         cudaGetLastError();
-        stats->bootstraps = (uint32_t)nboot;
-        stats->kernel_launches = (uint32_t)launches;
+        stats->bootstraps = (uint32_t)nboot[0];
+        for (int k = 0; k < nd; k++)
+            stats->kernel_launches += (uint32_t)launches[k];
     }
     return rc;
 }
@@ -1044,8 +1302,10 @@ extern "C" int tfhe_b200_eval_acc(tfhe_b200_handle* h, int batch, const uint64_t
         size_t need = (size_t)count * (W + 2 * N) * 8 + 4096;
         int r = arena_reserve(d, need);
         if (r) return r;
-        u64* ct = arena_take<u64>(d, (size_t)count * W);
-        u64* ac = arena_take<u64>(d, (size_t)count * 2 * N);
+        TAKE(ct, u64, d, (size_t)count * W);
+        TAKE(ac, u64, d, (size_t)count * 2 * N);
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, 2 * (size_t)count * 2 * N * 8 + 4096);
         // the operator passes only the mask; b is unused because the accumulator is explicit
         CUDA_TRY(cudaMemsetAsync(ct, 0, (size_t)count * W * 8, d.stream));
         if (space == TFHE_B200_HOST)
@@ -1055,23 +1315,22 @@ extern "C" int tfhe_b200_eval_acc(tfhe_b200_handle* h, int batch, const uint64_t
             CUDA_TRY(cudaMemcpy2DAsync(ct, W * 8, a + (size_t)start * n, n * 8, n * 8, count,
                                        cudaMemcpyDeviceToDevice, d.stream));
         else {
-            u64* tmpa = arena_take<u64>(d, (size_t)count * n);
-            if (!tmpa) FAIL(TFHE_B200_ENOMEM, "workspace");
+            TAKE(tmpa, u64, d, (size_t)count * n);
             CUDA_TRY(cudaMemcpyPeerAsync(tmpa, d.id, a + (size_t)start * n, d0.id, (size_t)count * n * 8, d.stream));
             CUDA_TRY(cudaMemcpy2DAsync(ct, W * 8, tmpa, n * 8, n * 8, count, cudaMemcpyDeviceToDevice, d.stream));
         }
         r = copy_in(d, d0, ac, acc + (size_t)start * 2 * N, (size_t)count * 2 * N * 8, space);
         if (r) return r;
-        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        CUDA_TRY(rec_ev(d, 1));
         AccDesc ad;
         ad.mode = ACC_EXPLICIT; ad.acc_io = ac; ad.write_acc = 1;
         r = blind_rotate(h, d, count, ct, ct_mod, ad, nullptr, launches);
         if (r) return r;
         (*nboot) = 1;
-        if (d.id == d0.id) {
-            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        {
+            CUDA_TRY(rec_ev(d, 2));
+            CUDA_TRY(rec_ev(d, 3));
+            CUDA_TRY(rec_ev(d, 4));
         }
         return copy_out(d, d0, acc + (size_t)start * 2 * N, ac, (size_t)count * 2 * N * 8, space);
     });
@@ -1089,20 +1348,22 @@ extern "C" int tfhe_b200_mkmswitch(tfhe_b200_handle* h, int batch, const uint64_
         const u32 W = p.n + 1, N = p.N;
         int r = arena_reserve(d, (size_t)count * (W + N + 1) * 8 + 4096);
         if (r) return r;
-        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
-        u64* o = arena_take<u64>(d, (size_t)count * W);
+        TAKE(ext, u64, d, (size_t)count * (N + 1));
+        TAKE(o, u64, d, (size_t)count * W);
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, (size_t)count * (N + 1 + W) * 8 + 4096);
         r = copy_in(d, d0, ext, in + (size_t)start * (N + 1), (size_t)count * (N + 1) * 8, space);
         if (r) return r;
-        if (d.id == d0.id) {
-            CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
+        {
+            CUDA_TRY(rec_ev(d, 1));
+            CUDA_TRY(rec_ev(d, 2));
         }
         r = mkmswitch_dev(h, d, count, ext, fmod, o, launches);
         if (r) return r;
         (void)nboot;
-        if (d.id == d0.id) {
-            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        {
+            CUDA_TRY(rec_ev(d, 3));
+            CUDA_TRY(rec_ev(d, 4));
         }
         return copy_out(d, d0, out + (size_t)start * W, o, (size_t)count * W * 8, space);
     });
@@ -1128,11 +1389,18 @@ extern "C" int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, c
         const size_t scratch_bytes = mul_matrix_scratch_bytes(in, out_cols, W, modulus);
         int r = arena_reserve(d, ((size_t)in * W + (size_t)in * out_cols + (size_t)out_cols * W) * 8 + scratch_bytes + 4096);
         if (r) return r;
-        u64* dct = arena_take<u64>(d, (size_t)in * W);
-        i64* dM = arena_take<i64>(d, (size_t)in * out_cols);
-        u64* dout = arena_take<u64>(d, (size_t)out_cols * W);
+        TAKE(dct, u64, d, (size_t)in * W);
+        TAKE(dM, i64, d, (size_t)in * out_cols);
+        TAKE(dout, u64, d, (size_t)out_cols * W);
         void* scratch = scratch_bytes ? (void*)arena_take<u32>(d, scratch_bytes / 4) : nullptr;
-        CUDA_TRY(cudaEventRecord(d.ev[0], d.stream));
+        if (scratch_bytes && !scratch)
+            return TFHE_B200_ENOMEM;
+        d.ev_mask = 0;
+        d.pending.clear();
+        d.pin.off = 0;
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, ((size_t)in * W + (size_t)in * out_cols + (size_t)out_cols * W) * 8 + 4096);
+        CUDA_TRY(rec_ev(d, 0));
         r = copy_in(d, d, dct, ct, (size_t)in * W * 8, space);
         if (r) return r;
         r = copy_in(d, d, dM, matrix, (size_t)in * out_cols * 8, space);
@@ -1140,8 +1408,11 @@ extern "C" int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, c
         CUDA_TRY(launch_mul_matrix(dout, dct, dM, in, out_cols, W, modulus, scratch, d.stream));
         r = copy_out(d, d, out, dout, (size_t)out_cols * W * 8, space);
         if (r) return r;
-        CUDA_TRY(cudaEventRecord(d.ev[5], d.stream));
+        CUDA_TRY(rec_ev(d, 5));
         CUDA_TRY(cudaStreamSynchronize(d.stream));
+        for (const PendingOut& po : d.pending)
+            par_memcpy(po.dst, po.src, po.bytes);
+        d.pending.clear();
         if (stats) {
             memset(stats, 0, sizeof(*stats));
             cudaEventElapsedTime(&stats->total_ms, d.ev[0], d.ev[5]);
@@ -1175,70 +1446,113 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
         const size_t S = (size_t)count * W;
         int r = arena_reserve(d, (7 * S + (size_t)count * (N + 1)) * 8 + 8192);
         if (r) return r;
-        u64* c1 = arena_take<u64>(d, S);
-        u64* c2 = arena_take<u64>(d, S);
-        u64* o = arena_take<u64>(d, S);
-        u64* tmp = arena_take<u64>(d, 4 * S);
-        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
-        if (space == TFHE_B200_HOST && count >= 4096 && !getenv("TFHE_B200_NO_PIPELINE")) {
-            // Host buffers: the shard goes through in up to 4 chunks so that the upload of chunk k+1 and the download
-            // of chunk k-1 ride under the bootstraps of chunk k (three streams, hand-over by events).  The reference
-            // copies everything in, computes, copies everything out (bootstrapping.cu:1562-1853).
-            // chunk boundaries on whole waves of CTAs (sm_count x 4 ciphertexts), or the partial last wave of every
-            // chunk would cost more than the overlap gains
-            const int unit = d.sm_count * 4;
+        TAKE(c1, u64, d, S);
+        TAKE(c2, u64, d, S);
+        TAKE(o, u64, d, S);
+        TAKE(tmp, u64, d, 4 * S);
+        TAKE(ext, u64, d, (size_t)count * (N + 1));
+        const int unit = d.sm_count * throughput_group(h);   // one wave of the throughput shape
+        const bool pin_in = space == TFHE_B200_HOST && host_is_pinned(ct1) && host_is_pinned(ct2);
+        const bool pin_out = space == TFHE_B200_HOST && host_is_pinned(out);
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, (pin_in ? 0 : 2 * (S * 8 + 256)) + (pin_out ? 0 : S * 8 + 256) + 4096);
+        if (space == TFHE_B200_HOST && count >= 3 * unit && !getenv("TFHE_B200_NO_PIPELINE")) {
+            // Host buffers: the shard goes through in chunks so that the upload of chunk k+1 and the download of chunk
+            // k-1 ride under the bootstraps of chunk k (three streams, hand-over by events).  The reference copies
+            // everything in, computes, copies everything out (bootstrapping.cu:1562-1853).  Chunk boundaries lie on
+            // whole waves of CTAs (sm_count x ciphertexts per CTA), or the partial last wave of every chunk would cost more
+            // than the overlap gains; the first and the last chunk are ONE wave, so that only one wave's worth of input
+            // is exposed before the first launch and one wave's worth of output after the last.  Pageable buffers are
+            // staged through the handle's pinned memory (host memcpy of chunk k+1 while the GPU works on chunk k).
             const int waves = (count + unit - 1) / unit;
-            const int wpc = (waves + 3) / 4;
-            const int nch = (waves + wpc - 1) / wpc;
-            auto chunk = [&](int k, int* off, int* cnt) {
-                *off = k * wpc * unit;
-                *cnt = std::min(wpc * unit, count - *off);
-            };
-            if (d.id == d0.id) CUDA_TRY(cudaStreamWaitEvent(d.xfer_in, d.ev[0], 0));
-            for (int k = 0; k < nch; k++) {
-                int off, cnt;
-                chunk(k, &off, &cnt);
-                const size_t o8 = (size_t)off * W, b8 = (size_t)cnt * W * 8;
-                CUDA_TRY(cudaMemcpyAsync(c1 + o8, ct1 + (size_t)(start + off) * W, b8, cudaMemcpyHostToDevice, d.xfer_in));
-                CUDA_TRY(cudaMemcpyAsync(c2 + o8, ct2 + (size_t)(start + off) * W, b8, cudaMemcpyHostToDevice, d.xfer_in));
-                CUDA_TRY(cudaEventRecord(d.pev[k], d.xfer_in));
+            int wsz[MAX_CHUNKS], nch = 0;
+            {
+                const int mid = waves - 2, nmid = std::min(MAX_CHUNKS - 2, (mid + 5) / 6);   // middle chunks of <= ~6 waves
+                wsz[nch++] = 1;
+                for (int k = 0; k < nmid; k++)
+                    wsz[nch++] = mid / nmid + (k < mid % nmid ? 1 : 0);
+                wsz[nch++] = 1;
             }
-            if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+            int coff[MAX_CHUNKS + 1];
+            coff[0] = 0;
+            for (int k = 0; k < nch; k++)
+                coff[k + 1] = std::min(count, coff[k] + wsz[k] * unit);
+            coff[nch] = count;
+            unsigned char *sin1 = nullptr, *sin2 = nullptr, *sout = nullptr;
+            if (!pin_in) {
+                sin1 = pin_take(d, S * 8);
+                sin2 = pin_take(d, S * 8);
+            }
+            if (!pin_out)
+                sout = pin_take(d, S * 8);
+            cudaEvent_t* ev_in = d.pev;
+            cudaEvent_t* ev_done = d.pev + MAX_CHUNKS;
+            cudaEvent_t* ev_out = d.pev + 2 * MAX_CHUNKS;
+            CUDA_TRY(cudaStreamWaitEvent(d.xfer_in, d.ev[0], 0));
+            CUDA_TRY(rec_ev(d, 1));
+            auto upload = [&](int k) -> int {
+                const int off = coff[k], cnt = coff[k + 1] - off;
+                const size_t o8 = (size_t)off * W, b8 = (size_t)cnt * W * 8;
+                const u64 *s1 = ct1 + (size_t)(start + off) * W, *s2 = ct2 + (size_t)(start + off) * W;
+                if (sin1 && sin2) {
+                    par_memcpy(sin1 + o8 * 8, s1, b8);
+                    par_memcpy(sin2 + o8 * 8, s2, b8);
+                    s1 = reinterpret_cast<const u64*>(sin1 + o8 * 8);
+                    s2 = reinterpret_cast<const u64*>(sin2 + o8 * 8);
+                }
+                CUDA_TRY(cudaMemcpyAsync(c1 + o8, s1, b8, cudaMemcpyHostToDevice, d.xfer_in));
+                CUDA_TRY(cudaMemcpyAsync(c2 + o8, s2, b8, cudaMemcpyHostToDevice, d.xfer_in));
+                CUDA_TRY(cudaEventRecord(ev_in[k], d.xfer_in));
+                return 0;
+            };
+            r = upload(0);
+            if (r) return r;
             for (int k = 0; k < nch; k++) {
-                int off, cnt, nb = 0;
-                chunk(k, &off, &cnt);
+                const int off = coff[k], cnt = coff[k + 1] - off;
                 const size_t o8 = (size_t)off * W;
-                CUDA_TRY(cudaStreamWaitEvent(d.stream, d.pev[k], 0));
+                int nb = 0;
+                CUDA_TRY(cudaStreamWaitEvent(d.stream, ev_in[k], 0));
                 r = gate_dev(h, d, gate, cnt, c1 + o8, c2 + o8, ct_mod, o + o8, tmp, ext, launches, &nb);
                 if (r) return r;
                 *nboot = nb;
-                CUDA_TRY(cudaEventRecord(d.pev[8 + k], d.stream));
-                CUDA_TRY(cudaStreamWaitEvent(d.xfer_out, d.pev[8 + k], 0));
-                CUDA_TRY(cudaMemcpyAsync(out + (size_t)(start + off) * W, o + o8, (size_t)cnt * W * 8,
-                                         cudaMemcpyDeviceToHost, d.xfer_out));
+                CUDA_TRY(cudaEventRecord(ev_done[k], d.stream));
+                CUDA_TRY(cudaStreamWaitEvent(d.xfer_out, ev_done[k], 0));
+                u64* dst = sout ? reinterpret_cast<u64*>(sout + o8 * 8) : out + (size_t)(start + off) * W;
+                CUDA_TRY(cudaMemcpyAsync(dst, o + o8, (size_t)cnt * W * 8, cudaMemcpyDeviceToHost, d.xfer_out));
+                CUDA_TRY(cudaEventRecord(ev_out[k], d.xfer_out));
+                if (k + 1 < nch) {   // staged while the GPU works on chunk k
+                    r = upload(k + 1);
+                    if (r) return r;
+                }
             }
-            if (d.id == d0.id) {
+            {
                 if (gate == TFHE_B200_XOR || gate == TFHE_B200_XNOR)
-                    CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
-                CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-                CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+                    CUDA_TRY(rec_ev(d, 2));
+                CUDA_TRY(rec_ev(d, 3));
+                CUDA_TRY(rec_ev(d, 4));
             }
-            CUDA_TRY(cudaEventRecord(d.pev[16], d.xfer_out));
-            CUDA_TRY(cudaStreamWaitEvent(d.stream, d.pev[16], 0));   // the caller's synchronisation covers the downloads
+            CUDA_TRY(cudaEventRecord(d.pev[3 * MAX_CHUNKS], d.xfer_out));
+            CUDA_TRY(cudaStreamWaitEvent(d.stream, d.pev[3 * MAX_CHUNKS], 0));   // the final synchronisation covers the downloads
+            if (sout)
+                for (int k = 0; k < nch; k++) {   // hand finished chunks to the caller while later ones still compute
+                    const int off = coff[k], cnt = coff[k + 1] - off;
+                    CUDA_TRY(cudaEventSynchronize(ev_out[k]));
+                    par_memcpy(out + (size_t)(start + off) * W, sout + (size_t)off * W * 8, (size_t)cnt * W * 8);
+                }
             return 0;
         }
         r = copy_in(d, d0, c1, ct1 + (size_t)start * W, S * 8, space);
         if (r) return r;
         r = copy_in(d, d0, c2, ct2 + (size_t)start * W, S * 8, space);
         if (r) return r;
-        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        CUDA_TRY(rec_ev(d, 1));
         r = gate_dev(h, d, gate, count, c1, c2, ct_mod, o, tmp, ext, launches, nboot);
         if (r) return r;
-        if (d.id == d0.id) {
+        {
             if (gate == TFHE_B200_XOR || gate == TFHE_B200_XNOR)
-                CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+                CUDA_TRY(rec_ev(d, 2));
+            CUDA_TRY(rec_ev(d, 3));
+            CUDA_TRY(rec_ev(d, 4));
         }
         return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
     });
@@ -1357,14 +1671,16 @@ extern "C" int tfhe_b200_eval_circuit(tfhe_b200_handle* h, int batch, int n_inpu
         const size_t n_wires = (size_t)n_inputs + n_prim;
         int r = arena_reserve(d, ((n_wires + max_group) * S + max_group * (size_t)count * (N + 1)) * 8 + 16384);
         if (r) return r;
-        u64* wires = arena_take<u64>(d, n_wires * S);
-        u64* prep = arena_take<u64>(d, max_group * S);
-        u64* ext = arena_take<u64>(d, max_group * (size_t)count * (N + 1));
+        TAKE(wires, u64, d, n_wires * S);
+        TAKE(prep, u64, d, max_group * S);
+        TAKE(ext, u64, d, max_group * (size_t)count * (N + 1));
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, ((size_t)n_inputs + n_outputs) * (S * 8 + 256) + 4096);
         for (int i = 0; i < n_inputs; i++) {
             r = copy_in(d, d0, wires + (size_t)i * S, inputs + ((size_t)i * batch + start) * W, S * 8, space);
             if (r) return r;
         }
-        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        CUDA_TRY(rec_ev(d, 1));
         const int batch_ = count;   // AFFINE uses `batch`
         int depth = 0;
         for (int lvl = 0; lvl <= max_level; lvl++) {
@@ -1403,10 +1719,10 @@ extern "C" int tfhe_b200_eval_circuit(tfhe_b200_handle* h, int batch, int n_inpu
         }
         (void)depth;
         *nboot = n_boot_nodes;   // bootstraps per batch element
-        if (d.id == d0.id) {
-            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        {
+            CUDA_TRY(rec_ev(d, 2));
+            CUDA_TRY(rec_ev(d, 3));
+            CUDA_TRY(rec_ev(d, 4));
         }
         for (int o = 0; o < n_outputs; o++) {
             r = copy_out(d, d0, out + ((size_t)o * batch + start) * W, wires + (size_t)wire_of[output_wires[o]] * S,
@@ -1432,23 +1748,25 @@ extern "C" int tfhe_b200_bootstrap_func(tfhe_b200_handle* h, int batch, const ui
         size_t tabw = per_ct ? (size_t)count * ct_mod : ct_mod;
         int r = arena_reserve(d, (2 * S + (size_t)count * (N + 1) + tabw) * 8 + 8192);
         if (r) return r;
-        u64* c = arena_take<u64>(d, S);
-        u64* o = arena_take<u64>(d, S);
-        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
-        u64* tab = arena_take<u64>(d, tabw);
+        TAKE(c, u64, d, S);
+        TAKE(o, u64, d, S);
+        TAKE(ext, u64, d, (size_t)count * (N + 1));
+        TAKE(tab, u64, d, tabw);
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, (2 * S + tabw) * 8 + 4096);
         r = copy_in(d, d0, c, ct + (size_t)start * W, S * 8, space);
         if (r) return r;
         r = copy_in(d, d0, tab, table + (per_ct ? (size_t)start * ct_mod : 0), tabw * 8, space);
         if (r) return r;
-        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        CUDA_TRY(rec_ev(d, 1));
         AccDesc a;
         a.mode = per_ct ? ACC_TABLE_PER : ACC_TABLE; a.table = tab; a.fmod = fmod;
-        r = bootstrap_dev(h, d, count, c, ct_mod, a, fmod, ext, o, launches, d.ev[2]);
+        r = bootstrap_dev(h, d, count, c, ct_mod, a, fmod, ext, o, launches, 2);
         if (r) return r;
         (*nboot) = 1;
-        if (d.id == d0.id) {
-            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        {
+            CUDA_TRY(rec_ev(d, 3));
+            CUDA_TRY(rec_ev(d, 4));
         }
         return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
     });
@@ -1503,19 +1821,21 @@ extern "C" int tfhe_b200_eval_func(tfhe_b200_handle* h, int batch, const uint64_
         const size_t ntab = per_ct ? (size_t)count : 1;
         int r = arena_reserve(d, (4 * S + (size_t)count * (N + 1) + ntab * (q + dq) + 2 * dq) * 8 + 16384);
         if (r) return r;
-        u64* c0 = arena_take<u64>(d, S);
-        u64* c1 = arena_take<u64>(d, S);
-        u64* c2 = arena_take<u64>(d, S);
-        u64* o = arena_take<u64>(d, S);
-        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
-        u64* dl = arena_take<u64>(d, ntab * q);    // raw LUT(s)
-        u64* dt = arena_take<u64>(d, ntab * dq);   // expanded table(s)
-        u64* df0 = arena_take<u64>(d, dq);
+        TAKE(c0, u64, d, S);
+        TAKE(c1, u64, d, S);
+        TAKE(c2, u64, d, S);
+        TAKE(o, u64, d, S);
+        TAKE(ext, u64, d, (size_t)count * (N + 1));
+        TAKE(dl, u64, d, ntab * q);    // raw LUT(s)
+        TAKE(dt, u64, d, ntab * dq);   // expanded table(s)
+        TAKE(df0, u64, d, dq);
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, (2 * S + ntab * q) * 8 + 4096);
         r = copy_in(d, d0, c0, ct + (size_t)start * W, S * 8, space);
         if (r) return r;
         r = copy_in(d, d0, dl, lut + (per_ct ? (size_t)start * q : 0), ntab * q * 8, space);
         if (r) return r;
-        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        CUDA_TRY(rec_ev(d, 1));
         AccDesc a;
         if (prop == 0) {
             AFFINE(c1, c0, nullptr, 1, 0, 0, beta, q, 0);
@@ -1525,11 +1845,8 @@ extern "C" int tfhe_b200_eval_func(tfhe_b200_handle* h, int batch, const uint64_
             (*nboot) = 1;
         }
         else if (prop == 2) {
-            std::vector<u64> f0(dq);
-            for (u64 x = 0; x < dq; x++)
-                f0[x] = (x < dq / 2) ? dq - dq / 4 : dq / 4;
-            CUDA_TRY(cudaMemcpyAsync(df0, f0.data(), dq * 8, cudaMemcpyHostToDevice, d.stream));
-            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            CUDA_TRY(launch_step_table(df0, STEP_HALF, dq, dq - dq / 4, dq / 4, d.stream));   // f0, :716-720
+            (*launches)++;
             AFFINE(c2, c0, nullptr, 1, 0, 0, beta, dq, 0);          // ct2 = ct1 + beta (mod 2q)
             a.mode = ACC_TABLE; a.table = df0; a.fmod = dq;
             r = bootstrap_dev(h, d, count, c2, dq, a, dq, ext, c1, launches);   // ct3
@@ -1545,11 +1862,8 @@ extern "C" int tfhe_b200_eval_func(tfhe_b200_handle* h, int batch, const uint64_
             (*nboot) = 2;
         }
         else {
-            std::vector<u64> f0(q);
-            for (u64 x = 0; x < q; x++)
-                f0[x] = (x < q / 2) ? q - q / 4 : q / 4;
-            CUDA_TRY(cudaMemcpyAsync(df0, f0.data(), q * 8, cudaMemcpyHostToDevice, d.stream));
-            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            CUDA_TRY(launch_step_table(df0, STEP_HALF, q, q - q / 4, q / 4, d.stream));
+            (*launches)++;
             AFFINE(c1, c0, nullptr, 1, 0, 0, beta, q, 0);
             a.mode = ACC_TABLE; a.table = df0; a.fmod = q;
             r = bootstrap_dev(h, d, count, c1, q, a, q, ext, c2, launches);     // ct2
@@ -1563,10 +1877,10 @@ extern "C" int tfhe_b200_eval_func(tfhe_b200_handle* h, int batch, const uint64_
             if (r) return r;
             (*nboot) = 2;
         }
-        if (d.id == d0.id) {
-            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        {
+            CUDA_TRY(rec_ev(d, 2));
+            CUDA_TRY(rec_ev(d, 3));
+            CUDA_TRY(rec_ev(d, 4));
         }
         return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
     });
@@ -1586,20 +1900,22 @@ extern "C" int tfhe_b200_eval_floor(tfhe_b200_handle* h, int batch, const uint64
         const size_t S = (size_t)count * W;
         int r = arena_reserve(d, (4 * S + (size_t)count * (N + 1) + qf) * 8 + 8192);
         if (r) return r;
-        u64* c = arena_take<u64>(d, S);
-        u64* o = arena_take<u64>(d, S);
-        u64* tmp = arena_take<u64>(d, 2 * S);
-        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
-        u64* tab = arena_take<u64>(d, qf);
+        TAKE(c, u64, d, S);
+        TAKE(o, u64, d, S);
+        TAKE(tmp, u64, d, 2 * S);
+        TAKE(ext, u64, d, (size_t)count * (N + 1));
+        TAKE(tab, u64, d, qf);
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, 2 * S * 8 + 4096);
         r = copy_in(d, d0, c, ct + (size_t)start * W, S * 8, space);
         if (r) return r;
-        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        CUDA_TRY(rec_ev(d, 1));
         r = floor_dev(h, d, count, c, ct_mod, roundbits, o, tmp, ext, tab, launches, nboot);
         if (r) return r;
-        if (d.id == d0.id) {
-            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        {
+            CUDA_TRY(rec_ev(d, 2));
+            CUDA_TRY(rec_ev(d, 3));
+            CUDA_TRY(rec_ev(d, 4));
         }
         return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
     });
@@ -1665,15 +1981,17 @@ static int sign_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint6
         const size_t outw = decomp ? S * max_digits : S;
         int r = arena_reserve(d, (5 * S + outw + (size_t)count * (N + 1) + 2 * q) * 8 + 16384);
         if (r) return r;
-        u64* cur = arena_take<u64>(d, S);
-        u64* nxt = arena_take<u64>(d, S);
-        u64* tmp = arena_take<u64>(d, 2 * S);
-        u64* o = arena_take<u64>(d, outw);
-        u64* ext = arena_take<u64>(d, (size_t)count * (N + 1));
-        u64* tab = arena_take<u64>(d, 2 * q);
+        TAKE(cur, u64, d, S);
+        TAKE(nxt, u64, d, S);
+        TAKE(tmp, u64, d, 2 * S);
+        TAKE(o, u64, d, outw);
+        TAKE(ext, u64, d, (size_t)count * (N + 1));
+        TAKE(tab, u64, d, 2 * q);
+        if (space == TFHE_B200_HOST)
+            pin_reserve(d, (S + outw) * 8 + 4096);
         r = copy_in(d, d0, cur, ct + (size_t)start * W, S * 8, space);
         if (r) return r;
-        if (d.id == d0.id) CUDA_TRY(cudaEventRecord(d.ev[1], d.stream));
+        CUDA_TRY(rec_ev(d, 1));
         u64 mod = ct_mod;
         int digit = 0;
         // current key set (curEK of binfhe-base-scheme.cpp:327-333); the child handle's Dev of the same index carries
@@ -1704,12 +2022,8 @@ static int sign_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint6
         }
         else {
             AFFINE(cur, cur, nullptr, 1, 0, 0, beta, mod, 0);
-            std::vector<u64> f3(mod);
-            for (u64 x = 0; x < mod; x++)
-                f3[x] = (x < mod / 2) ? q / 4 : q - q / 4;
-            CUDA_TRY(cudaStreamSynchronize(d.stream));
-            CUDA_TRY(cudaMemcpyAsync(tab, f3.data(), mod * 8, cudaMemcpyHostToDevice, d.stream));
-            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            CUDA_TRY(launch_step_table(tab, STEP_HALF, mod, q / 4, q - q / 4, d.stream));   // f3, :1004-1010
+            (*launches)++;
             AccDesc a;
             a.mode = ACC_TABLE; a.table = tab; a.fmod = q;
             r = bootstrap_dev(kh, kh->devs[dev_index], count, cur, mod, a, q, ext, nxt, launches);
@@ -1717,10 +2031,10 @@ static int sign_decomp(tfhe_b200_handle* h, int batch, const uint64_t* ct, uint6
             (*nboot)++;
             AFFINE(o, nxt, nullptr, 1, 0, 0, q - (q >> 2), q, 0);
         }
-        if (d.id == d0.id) {
-            CUDA_TRY(cudaEventRecord(d.ev[2], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[3], d.stream));
-            CUDA_TRY(cudaEventRecord(d.ev[4], d.stream));
+        {
+            CUDA_TRY(rec_ev(d, 2));
+            CUDA_TRY(rec_ev(d, 3));
+            CUDA_TRY(rec_ev(d, 4));
         }
         const size_t ow = decomp ? (size_t)max_digits * W : W;
         return copy_out(d, d0, out + (size_t)start * ow, o, (size_t)count * ow * 8, space);

@@ -134,6 +134,9 @@ cudaError_t launch_mod_switch(u64* out, const u64* in, u64 from_mod, u64 to_mod,
 // strided copy / reduce helpers
 cudaError_t launch_copy_mod(u64* out, size_t out_stride, const u64* in, size_t in_stride, u64 m, int batch, u32 words,
                             cudaStream_t s);
+// closed-form step tables of EvalFunc / EvalFloor / EvalSign, generated on the device (lwe_kernels.cu)
+enum StepTable : int { STEP_HALF = 0, STEP_FLOOR2 = 1 };
+cudaError_t launch_step_table(u64* tab, int kind, u64 len, u64 a, u64 b, cudaStream_t s);
 cudaError_t launch_lut_expand(u64* out, const u64* lut, u64 q, u64 tab_len, int mode, int batch, cudaStream_t s);
 size_t mul_matrix_scratch_bytes(int in, int outc, u32 words, u64 modulus);
 cudaError_t launch_mul_matrix(u64* out, const u64* ct, const i64* M, int in, int outc, u32 words, u64 modulus,

@@ -533,6 +533,32 @@ cudaError_t launch_mod_switch(u64* out, const u64* in, u64 from_mod, u64 to_mod,
     return cudaGetLastError();
 }
 
+// Closed-form step tables of the functional operators, built on the device so that the per-GPU bodies of a sharded
+// call never touch host memory between launches (the reference evaluates these lambdas per coefficient on the host:
+// binfhe-base-scheme.cpp:716-720 f0, :934-952 f1/f2, :1004-1010 f3).
+//   STEP_HALF : x < len/2 ? a : b                                   (f0 of EvalFunc, f1 of EvalFloor, f3 of EvalSign)
+//   STEP_FLOOR2: x < len/4 ? a - len/2 - x : (x < 3 len/4 ? x : a + len/2 - x)        (f2 of EvalFloor, a = mod)
+__global__ void step_table_kernel(u64* tab, int kind, u64 len, u64 a, u64 b) {
+    for (u64 x = (u64)blockIdx.x * blockDim.x + threadIdx.x; x < len; x += (u64)gridDim.x * blockDim.x) {
+        u64 v;
+        if (kind == STEP_HALF)
+            v = x < len / 2 ? a : b;
+        else
+            v = x < len / 4 ? a - len / 2 - x : (x < 3 * len / 4 ? x : a + len / 2 - x);
+        tab[x] = v;
+    }
+}
+
+cudaError_t launch_step_table(u64* tab, int kind, u64 len, u64 a, u64 b, cudaStream_t s) {
+    if (!len)
+        return cudaSuccess;
+    int blocks = (int)((len + 255) / 256);
+    if (blocks > 148 * 4)
+        blocks = 148 * 4;
+    step_table_kernel<<<blocks, 256, 0, s>>>(tab, kind, len, a, b);
+    return cudaGetLastError();
+}
+
 __global__ void copy_mod_kernel(u64* out, size_t out_stride, const u64* in, size_t in_stride, u64 m, int batch,
                                 u32 words) {
     size_t total = (size_t)batch * words;

@@ -28,6 +28,7 @@ def broadcast_keys(params_dict, bk, ksk, device, src=0):
         bk_t = torch.from_numpy(np.ascontiguousarray(bk).view(np.int64)).to(device)
         ksk_t = torch.from_numpy(np.ascontiguousarray(ksk).view(np.int64)).to(device)
     if world == 1:
+        torch.cuda.synchronize(device) if torch.device(device).type == "cuda" else None
         return params_dict, bk_t, ksk_t
     meta = [params_dict, int(bk_t.numel()), int(ksk_t.numel())] if rank == src else [None, 0, 0]
     dist.broadcast_object_list(meta, src=src)
@@ -36,4 +37,8 @@ def broadcast_keys(params_dict, bk, ksk, device, src=0):
         ksk_t = torch.empty(meta[2], dtype=torch.int64, device=device)
     dist.broadcast(bk_t, src=src)
     dist.broadcast(ksk_t, src=src)
+    # NCCL broadcasts are asynchronous to the host and ordered only on torch's stream; the engine re-encodes the keys on
+    # its own streams, so the data must have landed before the tensors are handed to tfhe_b200_setup
+    if torch.device(device).type == "cuda":
+        torch.cuda.synchronize(device)
     return meta[0], bk_t, ksk_t

@@ -15,9 +15,10 @@ from oracle import pyoracle as po  # noqa: E402
 SO = os.path.join(os.path.dirname(po.REF_SO), "libtfhe_ref_gpu.so")
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+ngpus = int(sys.argv[3]) if len(sys.argv) > 3 else 1      # cc.GPUSetup(numGPUs), binfhecontext.cpp:349-360
 r = po.Ref.named(po.STD128, po.GINX, so=SO)
 t = time.time(); r.keygen(); t_key = time.time() - t
-t = time.time(); r.gpu_setup(1); t_setup = time.time() - t
+t = time.time(); r.gpu_setup(ngpus); t_setup = time.time() - t
 q = r.p.q
 m1 = [i & 1 for i in range(batch)]
 m2 = [(i >> 1) & 1 for i in range(batch)]
@@ -32,7 +33,7 @@ dec = r.decrypt_batch(out[:256], q, 4)
 ok = dec == [1 - (a & b) for a, b in zip(m1[:256], m2[:256])]
 scalar = r.eval_bin_gate(po.GATES["NAND"], c1[:4], c2[:4], q)
 dt = sorted(times)[len(times) // 2]
-print(json.dumps({"impl": "reference GPU path (FFT, cuFFTDx SM<900> templates on sm_100)", "batch": batch,
+print(json.dumps({"impl": "reference GPU path (FFT, cuFFTDx SM<900> templates on sm_100)", "batch": batch, "n_gpus": ngpus,
                   "p50_s": dt, "gates_per_s": batch / dt, "ms_per_ctx": dt / batch * 1e3, "decrypt_ok": ok,
                   "bit_exact_vs_its_own_cpu_path": bool(np.array_equal(out[:4], scalar)),
                   "keygen_s": t_key, "gpu_setup_s": t_setup}), flush=True)
