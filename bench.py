@@ -234,7 +234,7 @@ class Workload:
         r = np.random.default_rng(1)
         sk = r.integers(-1, 2, self.p.n).astype(np.int8)
         skN = r.integers(-1, 2, self.p.N).astype(np.int8)
-        return gpu_keygen(self.p.as_dict(), sk, skN, 20261018, device=dev.index)
+        return gpu_keygen(self.p.as_dict(), sk, skN, key=bytes(range(32)), device=dev.index)   # fixed key: reproducible runs
 
     # ---- inputs --------------------------------------------------------------------------------------------
     def make_inputs(self, rng, count):

@@ -121,11 +121,20 @@ int tfhe_b200_num_key_sets(const tfhe_b200_handle* h);
  * expects (pass them on with key_space = TFHE_B200_DEVICE), so a 4.8 GB key-switching key never exists on the host.
  *   sk_lwe : the n ternary LWE secret coefficients in {-1, 0, 1};  sk_ring : the N ternary ring secret coefficients
  *   bk_dev : tfhe_b200_bk_words(params) u64 on `device`;  ksk_dev : tfhe_b200_ksk_words(params) u64 on `device`
- * Randomness: Philox4x32-10 streams keyed by `seed`, unbiased uniform residues, discrete Gaussian errors (sigma 3.19).
+ * Randomness: ChaCha20 in counter mode under a 256-bit key, independent derived keys for the public masks and the secret
+ * errors, unbiased uniform residues, discrete Gaussian errors (sigma 3.19).
+ *   key32  : 32 bytes of secret key material for the generator, from a cryptographically secure source (the reference
+ *            seeds a BLAKE2-based PRNG from the OS, core/include/math/distributiongenerator.h:86-130); NULL = the engine
+ *            draws them from the operating system (getrandom).  The same key reproduces the same evaluation keys.
  * Key generation is randomised: results are not comparable bit for bit with the reference (tests check decryption
  * correctness under these keys and the noise distribution of the key material). */
-int tfhe_b200_keygen(const tfhe_b200_params* params, const int8_t* sk_lwe, const int8_t* sk_ring, uint64_t seed,
+int tfhe_b200_keygen(const tfhe_b200_params* params, const int8_t* sk_lwe, const int8_t* sk_ring, const uint8_t* key32,
                      int device, uint64_t* bk_dev, uint64_t* ksk_dev);
+/* TEST ONLY -- deterministic generation from a 64-bit seed (fixtures, statistics tests).  A 64-bit seed can be searched
+ * exhaustively and every error term recomputed from it: keys made this way offer at most 64 bits of security whatever
+ * the parameter set claims.  Never use it for keys that leave the machine. */
+int tfhe_b200_keygen_test_seed(const tfhe_b200_params* params, const int8_t* sk_lwe, const int8_t* sk_ring,
+                               uint64_t seed, int device, uint64_t* bk_dev, uint64_t* ksk_dev);
 
 /* --------------------------------------------------------------------------------------------------------
  * Operator-level entry points (what the reference's host code calls).
@@ -152,6 +161,16 @@ int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, const uint64
 /* BinFHEContext::EvalBinGate(gate, vector, vector); ct modulus = ct_mod (normally q). */
 int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch, const uint64_t* ct1, const uint64_t* ct2,
                             uint64_t ct_mod, uint64_t* out, int space, tfhe_b200_stats* stats);
+
+/* The same for callers that hold every ciphertext as a separate object -- std::vector<LWECiphertext>, the reference's
+ * own argument type (lib/binfhecontext.cpp:323-325): a1[i] / a2[i] / a_out[i] point to the n mask words of ciphertext i
+ * (&ct->GetA()[0]; a NativeVector is a flat u64 array), b1 / b2 / b_out are dense arrays of the b words; the output
+ * objects are allocated by the caller.  Host memory only.  The gather of chunk k+1 into the handle's pinned staging and
+ * the scatter of chunk k-1 back into the output objects run inside the chunk pipeline while the GPU works on chunk k,
+ * so the flattening the reference does up front (lib/bootstrapping.cu:1562-1600) costs no wall time. */
+int tfhe_b200_eval_bin_gate_v(tfhe_b200_handle* h, int gate, int batch, const uint64_t* const* a1, const uint64_t* b1,
+                              const uint64_t* const* a2, const uint64_t* b2, uint64_t ct_mod, uint64_t* const* a_out,
+                              uint64_t* b_out, tfhe_b200_stats* stats);
 
 /* --------------------------------------------------------------------------------------------------------
  * SURVEY.md section 8(f) rank 1 -- gate-graph submission: a whole netlist of binary gates over a batch in ONE call,

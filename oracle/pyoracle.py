@@ -490,6 +490,16 @@ class Ref:
                                              C.c_uint64(mod), _p(out)))
         return out
 
+    def fused_bench_eval_bin_gate(self, gate, ct1, ct2, mod, reps):
+        """Times `reps` calls of the C++ adapter's EvalBinGate on std::vector<LWECiphertext> built once from the flat
+        arrays; returns (per-call seconds, result of the last call)."""
+        ct1, ct2 = _u64(ct1), _u64(ct2)
+        out = np.zeros_like(ct1)
+        secs = np.zeros(reps, dtype=np.float64)
+        self._chk(self.L.fused_bench_eval_bin_gate(self.h, self._fused, C.c_int(gate), C.c_int(ct1.shape[0]), _p(ct1),
+                                                   _p(ct2), C.c_uint64(mod), C.c_int(reps), _p(secs), _p(out)))
+        return secs, out
+
     def fused_eval_func(self, ct, mod, lut):
         ct, lut = _u64(ct), _u64(lut)
         out = np.zeros_like(ct)

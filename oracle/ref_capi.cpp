@@ -19,6 +19,7 @@
 #include "binfhe_b200.hpp"   // fused C++ adapter (only in the drop-in build, which links libtfhe_b200.so)
 #endif
 
+#include <chrono>
 #include <omp.h>
 #include <cstring>
 #include <string>
@@ -638,6 +639,26 @@ int fused_eval_bin_gate(void* h, void* f, int gate, int batch, const u64* ct1, c
     REF_TRY
     uint32_t n = ((RefCtx*)h)->cc.GetParams()->GetLWEParams()->Getn();
     auto r = ((tfhe_b200::BatchedBinFHE*)f)->EvalBinGate((BINGATE)gate, make_vec(ct1, batch, n, mod), make_vec(ct2, batch, n, mod));
+    put_vec(r, out, n);
+    return 0;
+    REF_CATCH(-1)
+}
+// Micro-benchmark of the drop-in C++ surface (measurement infrastructure): `reps` calls of
+// BatchedBinFHE::EvalBinGate(gate, std::vector<LWECiphertext>, std::vector<LWECiphertext>) on ciphertext OBJECTS built once
+// from the flat arrays; seconds[r] = wall time of call r, vectors in, vector out, everything a caller pays.  `out`
+// receives the result of the last call (for the parity check of the caller).
+int fused_bench_eval_bin_gate(void* h, void* f, int gate, int batch, const u64* ct1, const u64* ct2, u64 mod, int reps,
+                              double* seconds, u64* out) {
+    REF_TRY
+    uint32_t n = ((RefCtx*)h)->cc.GetParams()->GetLWEParams()->Getn();
+    auto v1 = make_vec(ct1, batch, n, mod), v2 = make_vec(ct2, batch, n, mod);
+    auto* gpu = (tfhe_b200::BatchedBinFHE*)f;
+    std::vector<LWECiphertext> r;
+    for (int k = 0; k < reps; k++) {
+        auto t0 = std::chrono::steady_clock::now();
+        r = gpu->EvalBinGate((BINGATE)gate, v1, v2);
+        seconds[k] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
     put_vec(r, out, n);
     return 0;
     REF_CATCH(-1)

@@ -187,3 +187,39 @@ def test_stats_fields_of_unrecorded_phases_are_zero(keyset):
     g.CiphertextMulMatrix(c1, M, q)
     st = g.last_stats
     assert st.total_ms > 0 and st.blind_rotate_ms == 0 and st.keyswitch_ms == 0 and st.bootstraps == 0
+
+
+def test_scattered_gate_entry_point(rng):
+    """tfhe_b200_eval_bin_gate_v: one pointer per ciphertext object (what std::vector<LWECiphertext> holds); gather and
+    scatter ride inside the chunk pipeline.  Same bits as the dense entry point and the oracle, for a pipelined batch
+    and for a small one."""
+    import ctypes as C
+
+    from tfhe_gpu_b200.context import load_library
+
+    p = po.Port.params_custom(12, 1024, 1024, Q27, 128, 1 << 7, 32, po.GINX)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    L = load_library()
+    try:
+        q, n = p.q, p.n
+        for batch in (3 * _sm_count() * 4 + 77, 9):
+            # every ciphertext its own allocation, in shuffled order, like heap-allocated LWECiphertext objects
+            a1 = [rng.integers(0, q, n, dtype=np.uint64) for _ in range(batch)]
+            a2 = [rng.integers(0, q, n, dtype=np.uint64) for _ in range(batch)]
+            b1 = rng.integers(0, q, batch, dtype=np.uint64)
+            b2 = rng.integers(0, q, batch, dtype=np.uint64)
+            ao = [np.zeros(n, dtype=np.uint64) for _ in range(batch)]
+            bo = np.zeros(batch, dtype=np.uint64)
+            PP = C.c_void_p * batch
+            rc = L.tfhe_b200_eval_bin_gate_v(g._h, 3, batch, PP(*[x.ctypes.data for x in a1]), C.c_void_p(b1.ctypes.data),
+                                             PP(*[x.ctypes.data for x in a2]), C.c_void_p(b2.ctypes.data), C.c_uint64(q),
+                                             PP(*[x.ctypes.data for x in ao]), C.c_void_p(bo.ctypes.data), None)
+            assert rc == 0, L.tfhe_b200_last_error()
+            c1 = np.concatenate([np.stack(a1), b1[:, None]], axis=1)
+            c2 = np.concatenate([np.stack(a2), b2[:, None]], axis=1)
+            want = port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, q)
+            got = np.concatenate([np.stack(ao), bo[:, None]], axis=1)
+            assert np.array_equal(got, want), batch
+    finally:
+        g.GPUClean()

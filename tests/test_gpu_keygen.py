@@ -123,3 +123,39 @@ def test_key_material_noise_and_determinism():
                 es.append(ev - qKS if ev > qKS // 2 else ev)
     es = np.array(es, dtype=np.int64)
     assert np.abs(es).max() <= 45 and abs(es.mean()) < 0.5 and 2.8 < es.std() < 3.6, (es.mean(), es.std())
+
+
+def test_secure_generator_key_material():
+    """tfhe_b200_keygen proper: 256-bit generator key (explicit, or drawn from the operating system when omitted).  The
+    same key reproduces the keys, fresh OS entropy does not, the TEST-ONLY seeded entry point is a different stream, and
+    gates decrypt under OS-keyed keys."""
+    from tfhe_gpu_b200 import BinFHEContextB200, gpu_keygen
+
+    p = po.Port.params_named(po.TOY, po.GINX)
+    port = po.Port(p)
+    sk, skN = _secrets(p, 9)
+    k1 = bytes(range(32))
+    bk_a, ksk_a = gpu_keygen(p.as_dict(), sk, skN, key=k1)
+    bk_b, ksk_b = gpu_keygen(p.as_dict(), sk, skN, key=k1)
+    bk_c, ksk_c = gpu_keygen(p.as_dict(), sk, skN, key=bytes(reversed(range(32))))
+    bk_os1, ksk_os1 = gpu_keygen(p.as_dict(), sk, skN)            # key from getrandom()
+    bk_os2, _ = gpu_keygen(p.as_dict(), sk, skN)
+    bk_seed, _ = gpu_keygen(p.as_dict(), sk, skN, seed=1)
+    assert bool((bk_a == bk_b).all()) and bool((ksk_a == ksk_b).all())
+    for other in (bk_c, bk_os1, bk_os2, bk_seed):
+        assert not bool((bk_a == other).all())
+    assert not bool((bk_os1 == bk_os2).all())
+    with pytest.raises(Exception):
+        gpu_keygen(p.as_dict(), sk, skN, key=b"short")
+    ctx = BinFHEContextB200().GPUSetup(p.as_dict(), bk_os1, ksk_os1, numGPUs=1)
+    try:
+        q, batch = p.q, 32
+        skm = _sk_mod(sk, p.qKS)
+        m1 = [i & 1 for i in range(batch)]
+        m2 = [(i >> 1) & 1 for i in range(batch)]
+        c1 = port.encrypt_batch(skm, m1, 4, q, 21)
+        c2 = port.encrypt_batch(skm, m2, 4, q, 22)
+        out = ctx.EvalBinGate("NAND", c1, c2)
+        assert port.decrypt_batch(skm, out, q, 4) == [1 - (a & b) for a, b in zip(m1, m2)]
+    finally:
+        ctx.GPUClean()

@@ -19,6 +19,9 @@
 #include "binfhecontext.h"
 #include "tfhe_b200.h"
 
+static_assert(sizeof(lbcrypto::NativeInteger) == sizeof(uint64_t),
+              "the adapter passes NativeVector storage to the C ABI as flat uint64_t arrays");
+
 namespace tfhe_b200 {
 
 class BatchedBinFHE {
@@ -89,12 +92,36 @@ public:
         if (&ct1 == &ct2 || ct1 == ct2)
             OPENFHE_THROW(config_error, "Input ciphertexts should be independant");
         const uint64_t mod = ct1[0]->GetModulus().ConvertToInt();
-        auto a = flatten(ct1), b = flatten(ct2);
-        std::vector<uint64_t> o(a.size());
-        check(tfhe_b200_eval_bin_gate(m_h, (int)gate, (int)ct1.size(), a.data(), b.data(), mod, o.data(),
-                                      TFHE_B200_HOST, nullptr),
+        // no flattening: the engine gathers straight from the ciphertext objects into its pinned staging, chunk by chunk
+        // under the running bootstraps, and scatters the results into the output objects the same way
+        // (tfhe_b200_eval_bin_gate_v); &GetA()[0] is a flat u64 array
+        const size_t batch = ct1.size(), n = m_p.n;
+        std::vector<const uint64_t*> a1(batch), a2(batch);
+        std::vector<uint64_t> b1(batch), b2(batch), bo(batch);
+        std::vector<uint64_t*> ao(batch);
+        std::vector<NativeVector> outA(batch);
+#pragma omp parallel for if (batch > 512)
+        for (size_t s = 0; s < batch; s++) {
+            if (ct1[s]->GetLength() != n || ct2[s]->GetLength() != n)
+                continue;   // reported below (no exceptions out of a parallel region)
+            a1[s] = reinterpret_cast<const uint64_t*>(&ct1[s]->GetA()[0]);
+            a2[s] = reinterpret_cast<const uint64_t*>(&ct2[s]->GetA()[0]);
+            b1[s] = ct1[s]->GetB().ConvertToInt();
+            b2[s] = ct2[s]->GetB().ConvertToInt();
+            outA[s] = NativeVector(n, NativeInteger(mod));
+            ao[s] = reinterpret_cast<uint64_t*>(&outA[s][0]);
+        }
+        for (size_t s = 0; s < batch; s++)
+            if (!a1[s])
+                OPENFHE_THROW(openfhe_error, "ERROR: EvalBinGate: ciphertext dimension does not match the key");
+        check(tfhe_b200_eval_bin_gate_v(m_h, (int)gate, (int)batch, a1.data(), b1.data(), a2.data(), b2.data(), mod,
+                                        ao.data(), bo.data(), nullptr),
               "EvalBinGate");
-        return unflatten(o, ct1.size(), mod);
+        std::vector<CT> ret(batch);
+#pragma omp parallel for if (batch > 512)
+        for (size_t s = 0; s < batch; s++)
+            ret[s] = std::make_shared<LWECiphertextImpl>(std::move(outA[s]), NativeInteger(bo[s]));
+        return ret;
     }
     // binfhecontext.cpp:327-330
     std::vector<CT> EvalFunc(const std::vector<CT>& ct, const std::vector<lbcrypto::NativeInteger>& LUT) const {

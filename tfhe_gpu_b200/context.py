@@ -88,7 +88,7 @@ EXPORTS = [
     "tfhe_b200_ksk_words", "tfhe_b200_kernel_variant", "tfhe_b200_set_option", "tfhe_b200_eval_acc",
     "tfhe_b200_mkmswitch", "tfhe_b200_mul_matrix", "tfhe_b200_eval_bin_gate", "tfhe_b200_bootstrap_func",
     "tfhe_b200_eval_func", "tfhe_b200_eval_floor", "tfhe_b200_eval_sign", "tfhe_b200_eval_decomp",
-    "tfhe_b200_eval_circuit", "tfhe_b200_keygen", "tfhe_b200_add_key_set", "tfhe_b200_num_key_sets",
+    "tfhe_b200_eval_bin_gate_v", "tfhe_b200_eval_circuit", "tfhe_b200_keygen", "tfhe_b200_keygen_test_seed", "tfhe_b200_add_key_set", "tfhe_b200_num_key_sets",
 ]
 
 
@@ -157,12 +157,16 @@ class _Buf:
         return np.empty(shape, dtype=np.uint64)
 
 
-def gpu_keygen(params, sk_lwe, sk_ring, seed, device=0):
+def gpu_keygen(params, sk_lwe, sk_ring, key=None, device=0, seed=None):
     """tfhe_b200_keygen: evaluation keys generated on the GPU.  `sk_lwe` / `sk_ring` are
-    the ternary secrets as signed values in {-1, 0, 1}.  Returns (bk, ksk) as int64 CUDA tensors in the layout
-    GPUSetup takes -- the keys never exist on the host."""
+    the ternary secrets as signed values in {-1, 0, 1}.  `key`: 32 bytes of generator key material from a CSPRNG, or
+    None (the engine draws them from the operating system).  An `int` selects the TEST-ONLY deterministic generator
+    (tfhe_b200_keygen_test_seed: at most 64 bits of security, for fixtures and statistics tests).  Returns (bk, ksk) as
+    int64 CUDA tensors in the layout GPUSetup takes -- the keys never exist on the host."""
     import torch
 
+    if seed is not None:           # keyword form of the TEST-ONLY seeded generator
+        key = int(seed)
     L = load_library()
     p = params if isinstance(params, Params) else Params.from_dict(
         params.as_dict() if hasattr(params, "as_dict") else params)
@@ -173,8 +177,15 @@ def gpu_keygen(params, sk_lwe, sk_ring, seed, device=0):
     dev = torch.device("cuda", device)
     bk = torch.empty(int(L.tfhe_b200_bk_words(C.byref(p))), dtype=torch.int64, device=dev)
     ksk = torch.empty(int(L.tfhe_b200_ksk_words(C.byref(p))), dtype=torch.int64, device=dev)
-    rc = L.tfhe_b200_keygen(C.byref(p), C.c_void_p(s1.ctypes.data), C.c_void_p(s2.ctypes.data), C.c_uint64(seed),
-                            device, C.c_void_p(bk.data_ptr()), C.c_void_p(ksk.data_ptr()))
+    common = (C.byref(p), C.c_void_p(s1.ctypes.data), C.c_void_p(s2.ctypes.data))
+    tail = (device, C.c_void_p(bk.data_ptr()), C.c_void_p(ksk.data_ptr()))
+    if isinstance(key, (int, np.integer)):
+        rc = L.tfhe_b200_keygen_test_seed(*common, C.c_uint64(int(key)), *tail)
+    else:
+        if key is not None and len(key) != 32:
+            raise TfheB200Error(-1, "KeyGen: key must be 32 bytes")
+        kb = (C.c_uint8 * 32).from_buffer_copy(bytes(key)) if key is not None else None
+        rc = L.tfhe_b200_keygen(*common, kb, *tail)
     if rc != 0:
         raise TfheB200Error(rc, L.tfhe_b200_last_error().decode())
     return bk, ksk

@@ -503,6 +503,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Mirrors the CASE table of launch_br_cggi32 exactly (instantiated shapes, shared-memory footprint of the default
+// group, 32-bit digit extraction): a set that passes here can be launched, anything else stays on the generic kernel.
 bool cggi32_supported(const tfhe_b200_params& p) {
     if (p.method != TFHE_B200_METHOD_GINX)
         return false;
@@ -510,10 +512,23 @@ bool cggi32_supported(const tfhe_b200_params& p) {
         return false;
     if (p.Q >= (1ULL << 32) / 22)  // lazy forward NTT bound: values < 22 Q must fit 32 bits
         return false;
-    const u32 dk = p.digitsG - p.numDigitsToThrow;
-    if (dk != 2 && dk != 3 && dk != 4 && dk != 5 && dk != 6)
+    if (p.digitsG <= p.numDigitsToThrow)
         return false;
-    if (p.n > 4096)
+    const u32 dk = p.digitsG - p.numDigitsToThrow;
+    const bool inst = p.N == 1024 ? (dk >= 2 && dk <= 6) : (dk == 2 || dk == 3 || dk == 4 || dk == 6);
+    if (!inst)
+        return false;
+    // digits are extracted from the low 32 bits of (centred value + offset): every digit window must lie inside them
+    u32 gbits = 0;
+    while ((1ULL << gbits) < p.baseG)
+        gbits++;
+    if ((1ULL << gbits) != p.baseG || gbits * p.digitsG > 32)
+        return false;
+    // shared memory of the throughput shape: G * D digit regions + psi table + G * n rotation exponents
+    const u32 G = p.N == 1024 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4);
+    const size_t RS = p.N + p.N / 8 + (p.N == 512 ? 16 : 0);
+    const size_t smem = (size_t)G * 2 * dk * RS * 4 + (size_t)2 * p.N * 4 + (size_t)G * ((p.n + 1) / 2 * 2) * 2 + 64;
+    if (smem > 227 * 1024)
         return false;
     return true;
 }

@@ -18,6 +18,10 @@
 #include <thread>
 #include <vector>
 
+#include <errno.h>
+#include <nvtx3/nvToolsExt.h>
+#include <sys/random.h>
+
 #include "engine.cuh"
 
 using namespace tfhe_b200;
@@ -26,6 +30,12 @@ static_assert(sizeof(tfhe_b200_params) == 88, "tfhe_b200_params layout is part o
 static_assert(sizeof(tfhe_b200_stats) == 32, "tfhe_b200_stats layout is part of the ABI");
 
 static thread_local std::string g_err;
+
+// NVTX range around a phase of a call (host side; shows up in Nsight Systems timelines, a no-op without a profiler)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define CUDA_TRY(x)                                                                                        \
     do {                                                                                                   \
@@ -651,6 +661,16 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
         FAIL(TFHE_B200_EINVAL, "setup: method must be AP (1) or GINX (2)");
     if (p.Q >= (1ULL << 55) || !(p.Q & 1))
         FAIL(TFHE_B200_ENOTSUP, "setup: Q must be an odd prime below 2^55 (lazy 128-bit accumulation bound)");
+    {
+        // the generic 64-bit kernel accumulates d products of lazily reduced transform outputs (< (1 + 2 log N) Q) in
+        // 128 bits and reduces once: d (1 + 2 log N) Q must stay below 2^64 (br_generic.cu, pointwise stage)
+        u32 lg = 0;
+        while ((1u << lg) < p.N)
+            lg++;
+        const unsigned __int128 bound = (unsigned __int128)(2 * p.digitsG) * (1 + 2 * lg) * p.Q;
+        if (p.Q >= (1ULL << 31) && bound >= ((unsigned __int128)1 << 64))
+            FAIL(TFHE_B200_ENOTSUP, "setup: 2*digitsG*(1 + 2 log N)*Q must stay below 2^64 (lazy accumulation bound)");
+    }
     if ((p.Q - 1) % (2ULL * p.N) != 0 || h_powmod(p.psi, p.N, p.Q) != p.Q - 1)
         FAIL(TFHE_B200_EINVAL, "setup: psi is not a primitive 2N-th root of unity mod Q");
     if (p.baseG == 0 || (p.baseG & (p.baseG - 1)) || p.digitsG <= p.numDigitsToThrow)
@@ -932,6 +952,7 @@ struct AccDesc {
 static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, int* launches) {
     if (c.batch <= 0)
         return 0;
+    NvtxRange nvtx("tfhe_b200:blind_rotate");
     if (h->have_cggi32 && !h->force_generic) {
         CGGI32Tables t;
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB; t.skip_top = h->skip_top;
@@ -1063,6 +1084,7 @@ static int mkmswitch_dev(tfhe_b200_handle* h, Dev& d, int batch, const u64* ext,
     a.Q = p.Q; a.qKS = p.qKS; a.fmod = fmod; a.batch = batch; a.ext = ext; a.out = out;
     a.ksk = d.ksk; a.ksk_bytes = h->ksk_bytes;
     a.partial = d.ks_partial; a.sm_count = d.sm_count;
+    NvtxRange nvtx("tfhe_b200:mkmswitch");
     CUDA_TRY(launch_mkmswitch(a, d.stream));
     if (launches)
         (*launches)++;
@@ -1186,6 +1208,7 @@ static int run_sharded(tfhe_b200_handle* h, int batch, tfhe_b200_stats* stats, F
         d.pending.clear();
         d.pin.off = 0;
         auto run = [&]() -> int {
+            NvtxRange nvtx("tfhe_b200:shard");
             CUDA_TRY(cudaSetDevice(d.id));
             CUDA_TRY(rec_ev(d, 0));
             int r = count > 0 ? body(d, start, count, &launches[k], &nboot[k]) : 0;
@@ -1263,7 +1286,7 @@ static int check_call(tfhe_b200_handle* h, int batch, const void* a, const void*
 // operator-level entry points
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int tfhe_b200_keygen(const tfhe_b200_params* params, const int8_t* sk_lwe, const int8_t* sk_ring,
-                                uint64_t seed, int device, uint64_t* bk_dev, uint64_t* ksk_dev) {
+                                const uint8_t* key32, int device, uint64_t* bk_dev, uint64_t* ksk_dev) {
     if (!params || !sk_lwe || !sk_ring || !bk_dev || !ksk_dev)
         FAIL(TFHE_B200_EINVAL, "KeyGen: null argument");
     const tfhe_b200_params& p = *params;
@@ -1283,10 +1306,39 @@ extern "C" int tfhe_b200_keygen(const tfhe_b200_params* params, const int8_t* sk
         FAIL(TFHE_B200_ENODEV, "KeyGen: no CUDA device (this engine has no CPU fallback)");
     if (device < 0 || device >= ndev)
         FAIL(TFHE_B200_EINVAL, "KeyGen: bad device index");
-    int rc = keygen_device(p, (const signed char*)sk_lwe, (const signed char*)sk_ring, seed, device, bk_dev, ksk_dev);
+    unsigned char key[32];
+    if (key32)
+        memcpy(key, key32, 32);
+    else {   // 256 bits from the operating system's CSPRNG
+        size_t got = 0;
+        while (got < sizeof(key)) {
+            ssize_t r = getrandom(key + got, sizeof(key) - got, 0);
+            if (r < 0) {
+                if (errno == EINTR)
+                    continue;
+                FAIL(TFHE_B200_EINVAL, "KeyGen: getrandom() failed; pass 32 bytes of key material explicitly");
+            }
+            got += (size_t)r;
+        }
+    }
+    int rc = keygen_device(p, (const signed char*)sk_lwe, (const signed char*)sk_ring, key, device, bk_dev, ksk_dev);
+    volatile unsigned char* wipe = key;
+    for (size_t i = 0; i < sizeof(key); i++)
+        wipe[i] = 0;
     if (rc)
         g_err = keygen_last_error();
     return rc;
+}
+
+// TEST ONLY: deterministic key generation from a 64-bit seed (reproducible fixtures, noise-statistics tests).  A 64-bit
+// seed can be searched exhaustively, so keys generated this way offer at most 64 bits of security whatever the
+// parameter set claims -- production callers use tfhe_b200_keygen with 32 bytes from a CSPRNG (or NULL).
+extern "C" int tfhe_b200_keygen_test_seed(const tfhe_b200_params* params, const int8_t* sk_lwe, const int8_t* sk_ring,
+                                          uint64_t seed, int device, uint64_t* bk_dev, uint64_t* ksk_dev) {
+    uint8_t key[32] = {};
+    memcpy(key, &seed, 8);
+    memcpy(key + 8, "tfhe_b200 TEST-ONLY seed", 24);
+    return tfhe_b200_keygen(params, sk_lwe, sk_ring, key, device, bk_dev, ksk_dev);
 }
 
 extern "C" int tfhe_b200_eval_acc(tfhe_b200_handle* h, int batch, const uint64_t* a, uint64_t ct_mod, uint64_t* acc,
@@ -1426,23 +1478,48 @@ extern "C" int tfhe_b200_mul_matrix(tfhe_b200_handle* h, int in, int out_cols, c
 // ---------------------------------------------------------------------------------------------------------
 // fused batched API
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch, const uint64_t* ct1,
-                                       const uint64_t* ct2, uint64_t ct_mod, uint64_t* out, int space,
-                                       tfhe_b200_stats* stats) {
-    int rc = check_call(h, batch, ct1, ct2, "EvalBinGate");
-    if (rc) return rc;
-    if (!out)
-        FAIL(TFHE_B200_EINVAL, "EvalBinGate: null output");
+// Host-side view of the operands of one EvalBinGate call: dense [batch][n+1] arrays (flat != nullptr), or one pointer
+// per ciphertext for callers that hold every ciphertext as a separate object (std::vector<LWECiphertext>).
+namespace {
+struct GateIO {
+    const u64 *ct1 = nullptr, *ct2 = nullptr;        // dense
+    u64* out = nullptr;
+    const u64 *const *a1 = nullptr, *const *a2 = nullptr;   // scattered: a1[i] -> n mask words, b1[i]
+    const u64 *b1 = nullptr, *b2 = nullptr;
+    u64* const* a_out = nullptr;
+    u64* b_out = nullptr;
+    bool scattered() const { return a1 != nullptr; }
+};
+// gather ciphertexts [first, first+cnt) of a scattered operand into a dense staging block
+void gather_cts(u64* dst, const u64* const* a, const u64* b, size_t first, size_t cnt, u32 n) {
+#pragma omp parallel for num_threads(4) schedule(static) if (cnt >= 256)
+    for (long i = 0; i < (long)cnt; i++) {
+        u64* row = dst + (size_t)i * (n + 1);
+        memcpy(row, a[first + i], (size_t)n * 8);
+        row[n] = b[first + i];
+    }
+}
+void scatter_cts(u64* const* a, u64* b, const u64* src, size_t first, size_t cnt, u32 n) {
+#pragma omp parallel for num_threads(4) schedule(static) if (cnt >= 256)
+    for (long i = 0; i < (long)cnt; i++) {
+        const u64* row = src + (size_t)i * (n + 1);
+        memcpy(a[first + i], row, (size_t)n * 8);
+        b[first + i] = row[n];
+    }
+}
+}  // namespace
+
+static int eval_bin_gate_impl(tfhe_b200_handle* h, int gate, int batch, const GateIO& io, uint64_t ct_mod, int space,
+                              tfhe_b200_stats* stats) {
+    const tfhe_b200_params& p = h->p;
     if (gate < 0 || gate > TFHE_B200_XNOR)
         FAIL(TFHE_B200_EINVAL, "EvalBinGate: unknown gate");
-    if (ct1 == ct2)
-        FAIL(TFHE_B200_EINVAL, "Input ciphertexts should be independant");
-    const tfhe_b200_params& p = h->p;
     if (ct_mod == 0 || (2ULL * p.N) % ct_mod)
         FAIL(TFHE_B200_EINVAL, "EvalBinGate: ciphertext modulus must divide 2N");
     Dev& d0 = h->devs[0];
+    const bool sc = io.scattered();
     return run_sharded(h, batch, stats, [&](Dev& d, int start, int count, int* launches, int* nboot) -> int {
-        const u32 W = p.n + 1, N = p.N;
+        const u32 W = p.n + 1, N = p.N, n = p.n;
         const size_t S = (size_t)count * W;
         int r = arena_reserve(d, (7 * S + (size_t)count * (N + 1)) * 8 + 8192);
         if (r) return r;
@@ -1452,18 +1529,56 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
         TAKE(tmp, u64, d, 4 * S);
         TAKE(ext, u64, d, (size_t)count * (N + 1));
         const int unit = d.sm_count * throughput_group(h);   // one wave of the throughput shape
-        const bool pin_in = space == TFHE_B200_HOST && host_is_pinned(ct1) && host_is_pinned(ct2);
-        const bool pin_out = space == TFHE_B200_HOST && host_is_pinned(out);
+        const bool pin_in = !sc && space == TFHE_B200_HOST && host_is_pinned(io.ct1) && host_is_pinned(io.ct2);
+        const bool pin_out = !sc && space == TFHE_B200_HOST && host_is_pinned(io.out);
         if (space == TFHE_B200_HOST)
             pin_reserve(d, (pin_in ? 0 : 2 * (S * 8 + 256)) + (pin_out ? 0 : S * 8 + 256) + 4096);
+        unsigned char *sin1 = nullptr, *sin2 = nullptr, *sout = nullptr;
+        if (space == TFHE_B200_HOST) {
+            if (!pin_in) {
+                sin1 = pin_take(d, S * 8);
+                sin2 = pin_take(d, S * 8);
+            }
+            if (!pin_out)
+                sout = pin_take(d, S * 8);
+            if (sc && !(sin1 && sin2 && sout))
+                FAIL(TFHE_B200_ENOMEM, "EvalBinGate: pinned staging for the gathered ciphertexts could not be allocated");
+        }
+        // stage rows [off, off+cnt) of the shard's inputs (host memcpy / gather) and return the DMA sources
+        auto stage_in = [&](int off, int cnt, const u64** s1, const u64** s2) {
+            const size_t o8 = (size_t)off * W, b8 = (size_t)cnt * W * 8;
+            if (sc) {
+                gather_cts(reinterpret_cast<u64*>(sin1) + o8, io.a1, io.b1, (size_t)start + off, cnt, n);
+                gather_cts(reinterpret_cast<u64*>(sin2) + o8, io.a2, io.b2, (size_t)start + off, cnt, n);
+            }
+            else if (sin1 && sin2) {
+                par_memcpy(sin1 + o8 * 8, io.ct1 + (size_t)(start + off) * W, b8);
+                par_memcpy(sin2 + o8 * 8, io.ct2 + (size_t)(start + off) * W, b8);
+            }
+            else {
+                *s1 = io.ct1 + (size_t)(start + off) * W;
+                *s2 = io.ct2 + (size_t)(start + off) * W;
+                return;
+            }
+            *s1 = reinterpret_cast<const u64*>(sin1) + o8;
+            *s2 = reinterpret_cast<const u64*>(sin2) + o8;
+        };
+        auto hand_out = [&](int off, int cnt) {   // staged results of rows [off, off+cnt) to the caller
+            const size_t o8 = (size_t)off * W;
+            if (sc)
+                scatter_cts(io.a_out, io.b_out, reinterpret_cast<const u64*>(sout) + o8, (size_t)start + off, cnt, n);
+            else
+                par_memcpy(io.out + (size_t)(start + off) * W, sout + o8 * 8, (size_t)cnt * W * 8);
+        };
         if (space == TFHE_B200_HOST && count >= 3 * unit && !getenv("TFHE_B200_NO_PIPELINE")) {
             // Host buffers: the shard goes through in chunks so that the upload of chunk k+1 and the download of chunk
             // k-1 ride under the bootstraps of chunk k (three streams, hand-over by events).  The reference copies
             // everything in, computes, copies everything out (bootstrapping.cu:1562-1853).  Chunk boundaries lie on
             // whole waves of CTAs (sm_count x ciphertexts per CTA), or the partial last wave of every chunk would cost more
             // than the overlap gains; the first and the last chunk are ONE wave, so that only one wave's worth of input
-            // is exposed before the first launch and one wave's worth of output after the last.  Pageable buffers are
-            // staged through the handle's pinned memory (host memcpy of chunk k+1 while the GPU works on chunk k).
+            // is exposed before the first launch and one wave's worth of output after the last.  Pageable buffers (and
+            // per-object ciphertexts) are staged through the handle's pinned memory: the host memcpy / gather of chunk
+            // k+1 and the hand-back of chunk k-1 run while the GPU works on chunk k.
             const int waves = (count + unit - 1) / unit;
             int wsz[MAX_CHUNKS], nch = 0;
             {
@@ -1478,13 +1593,6 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
             for (int k = 0; k < nch; k++)
                 coff[k + 1] = std::min(count, coff[k] + wsz[k] * unit);
             coff[nch] = count;
-            unsigned char *sin1 = nullptr, *sin2 = nullptr, *sout = nullptr;
-            if (!pin_in) {
-                sin1 = pin_take(d, S * 8);
-                sin2 = pin_take(d, S * 8);
-            }
-            if (!pin_out)
-                sout = pin_take(d, S * 8);
             cudaEvent_t* ev_in = d.pev;
             cudaEvent_t* ev_done = d.pev + MAX_CHUNKS;
             cudaEvent_t* ev_out = d.pev + 2 * MAX_CHUNKS;
@@ -1493,13 +1601,8 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
             auto upload = [&](int k) -> int {
                 const int off = coff[k], cnt = coff[k + 1] - off;
                 const size_t o8 = (size_t)off * W, b8 = (size_t)cnt * W * 8;
-                const u64 *s1 = ct1 + (size_t)(start + off) * W, *s2 = ct2 + (size_t)(start + off) * W;
-                if (sin1 && sin2) {
-                    par_memcpy(sin1 + o8 * 8, s1, b8);
-                    par_memcpy(sin2 + o8 * 8, s2, b8);
-                    s1 = reinterpret_cast<const u64*>(sin1 + o8 * 8);
-                    s2 = reinterpret_cast<const u64*>(sin2 + o8 * 8);
-                }
+                const u64 *s1, *s2;
+                stage_in(off, cnt, &s1, &s2);
                 CUDA_TRY(cudaMemcpyAsync(c1 + o8, s1, b8, cudaMemcpyHostToDevice, d.xfer_in));
                 CUDA_TRY(cudaMemcpyAsync(c2 + o8, s2, b8, cudaMemcpyHostToDevice, d.xfer_in));
                 CUDA_TRY(cudaEventRecord(ev_in[k], d.xfer_in));
@@ -1507,6 +1610,7 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
             };
             r = upload(0);
             if (r) return r;
+            int handed = 0;   // chunks already handed back to the caller (staged outputs)
             for (int k = 0; k < nch; k++) {
                 const int off = coff[k], cnt = coff[k + 1] - off;
                 const size_t o8 = (size_t)off * W;
@@ -1517,13 +1621,19 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
                 *nboot = nb;
                 CUDA_TRY(cudaEventRecord(ev_done[k], d.stream));
                 CUDA_TRY(cudaStreamWaitEvent(d.xfer_out, ev_done[k], 0));
-                u64* dst = sout ? reinterpret_cast<u64*>(sout + o8 * 8) : out + (size_t)(start + off) * W;
+                u64* dst = sout ? reinterpret_cast<u64*>(sout) + o8 : io.out + (size_t)(start + off) * W;
                 CUDA_TRY(cudaMemcpyAsync(dst, o + o8, (size_t)cnt * W * 8, cudaMemcpyDeviceToHost, d.xfer_out));
                 CUDA_TRY(cudaEventRecord(ev_out[k], d.xfer_out));
                 if (k + 1 < nch) {   // staged while the GPU works on chunk k
                     r = upload(k + 1);
                     if (r) return r;
                 }
+                // results that have already landed go back to the caller while the GPU keeps working
+                while (sout && handed < k && cudaEventQuery(ev_out[handed]) == cudaSuccess) {
+                    hand_out(coff[handed], coff[handed + 1] - coff[handed]);
+                    handed++;
+                }
+                cudaGetLastError();   // a cudaErrorNotReady from the query is not an error
             }
             {
                 if (gate == TFHE_B200_XOR || gate == TFHE_B200_XNOR)
@@ -1534,17 +1644,24 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
             CUDA_TRY(cudaEventRecord(d.pev[3 * MAX_CHUNKS], d.xfer_out));
             CUDA_TRY(cudaStreamWaitEvent(d.stream, d.pev[3 * MAX_CHUNKS], 0));   // the final synchronisation covers the downloads
             if (sout)
-                for (int k = 0; k < nch; k++) {   // hand finished chunks to the caller while later ones still compute
-                    const int off = coff[k], cnt = coff[k + 1] - off;
-                    CUDA_TRY(cudaEventSynchronize(ev_out[k]));
-                    par_memcpy(out + (size_t)(start + off) * W, sout + (size_t)off * W * 8, (size_t)cnt * W * 8);
+                for (; handed < nch; handed++) {
+                    CUDA_TRY(cudaEventSynchronize(ev_out[handed]));
+                    hand_out(coff[handed], coff[handed + 1] - coff[handed]);
                 }
             return 0;
         }
-        r = copy_in(d, d0, c1, ct1 + (size_t)start * W, S * 8, space);
-        if (r) return r;
-        r = copy_in(d, d0, c2, ct2 + (size_t)start * W, S * 8, space);
-        if (r) return r;
+        if (space == TFHE_B200_HOST) {
+            const u64 *s1, *s2;
+            stage_in(0, count, &s1, &s2);
+            CUDA_TRY(cudaMemcpyAsync(c1, s1, S * 8, cudaMemcpyHostToDevice, d.stream));
+            CUDA_TRY(cudaMemcpyAsync(c2, s2, S * 8, cudaMemcpyHostToDevice, d.stream));
+        }
+        else {
+            r = copy_in(d, d0, c1, io.ct1 + (size_t)start * W, S * 8, space);
+            if (r) return r;
+            r = copy_in(d, d0, c2, io.ct2 + (size_t)start * W, S * 8, space);
+            if (r) return r;
+        }
         CUDA_TRY(rec_ev(d, 1));
         r = gate_dev(h, d, gate, count, c1, c2, ct_mod, o, tmp, ext, launches, nboot);
         if (r) return r;
@@ -1554,8 +1671,43 @@ extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch,
             CUDA_TRY(rec_ev(d, 3));
             CUDA_TRY(rec_ev(d, 4));
         }
-        return copy_out(d, d0, out + (size_t)start * W, o, S * 8, space);
+        if (space == TFHE_B200_HOST && sout) {
+            CUDA_TRY(cudaMemcpyAsync(sout, o, S * 8, cudaMemcpyDeviceToHost, d.stream));
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            hand_out(0, count);
+            return 0;
+        }
+        return copy_out(d, d0, io.out + (size_t)start * W, o, S * 8, space);
     });
+}
+
+extern "C" int tfhe_b200_eval_bin_gate(tfhe_b200_handle* h, int gate, int batch, const uint64_t* ct1,
+                                       const uint64_t* ct2, uint64_t ct_mod, uint64_t* out, int space,
+                                       tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, ct1, ct2, "EvalBinGate");
+    if (rc) return rc;
+    if (!out)
+        FAIL(TFHE_B200_EINVAL, "EvalBinGate: null output");
+    if (ct1 == ct2)
+        FAIL(TFHE_B200_EINVAL, "Input ciphertexts should be independant");
+    GateIO io;
+    io.ct1 = ct1; io.ct2 = ct2; io.out = out;
+    return eval_bin_gate_impl(h, gate, batch, io, ct_mod, space, stats);
+}
+
+extern "C" int tfhe_b200_eval_bin_gate_v(tfhe_b200_handle* h, int gate, int batch, const uint64_t* const* a1,
+                                         const uint64_t* b1, const uint64_t* const* a2, const uint64_t* b2,
+                                         uint64_t ct_mod, uint64_t* const* a_out, uint64_t* b_out,
+                                         tfhe_b200_stats* stats) {
+    int rc = check_call(h, batch, a1, a2, "EvalBinGate");
+    if (rc) return rc;
+    if (!b1 || !b2 || !a_out || !b_out)
+        FAIL(TFHE_B200_EINVAL, "EvalBinGate: null pointer");
+    if (a1 == a2)
+        FAIL(TFHE_B200_EINVAL, "Input ciphertexts should be independant");
+    GateIO io;
+    io.a1 = a1; io.b1 = b1; io.a2 = a2; io.b2 = b2; io.a_out = a_out; io.b_out = b_out;
+    return eval_bin_gate_impl(h, gate, batch, io, ct_mod, TFHE_B200_HOST, stats);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -103,8 +103,8 @@ void cggi64w_build_tables(const tfhe_b200_params& p, std::vector<u64>& twU, std:
 cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s, int sm_count = 0, int group = 0);
 
 // GPU key generation (keygen.cu)
-int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const signed char* sk_ring, u64 seed, int device,
-                  u64* bk_dev, u64* ksk_dev);
+int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const signed char* sk_ring,
+                  const unsigned char key[32], int device, u64* bk_dev, u64* ksk_dev);
 const char* keygen_last_error();
 
 // LWE-side kernels (lwe_kernels.cu)

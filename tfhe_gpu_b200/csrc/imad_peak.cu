@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(256) k(unsigned* out, const unsigned* in, int 
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-struct Res { const char* name; double gops, per_sm_clk, ms; };
-static unsigned *g_out, *g_in; static long long* g_cyc; static int g_sms;
+struct Res { const char* name; double gops, per_sm_clk, per_sm_clk_wall, ms; int resident; };
+static unsigned *g_out, *g_in; static long long* g_cyc; static int g_sms; static double g_clock_hz;
 
 template <int V>
 Res run(const char* name, double ops, int ctas_per_sm) {
@@ -135,12 +135,22 @@ Res run(const char* name, double ops, int ctas_per_sm) {
     double avg = 0; for (auto c : hc) avg += (double)c; avg /= grid;
     Res r; r.name = name; r.ms = best;
     r.gops = (double)grid * block * iters * ops / (best * 1e-3) / 1e9;
-    r.per_sm_clk = (double)ctas_per_sm * block * iters * ops / avg;
+    // CTAs actually co-resident on an SM (the ~60-register probes fit 4 of 256 threads, not the 8 launched per SM): the
+    // launched CTAs run in ceil(ctas_per_sm / resident) rounds of `avg` cycles each
+    int resident = 0;
+    CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k<V>, block, 0));
+    if (resident > ctas_per_sm) resident = ctas_per_sm;
+    if (resident < 1) resident = 1;
+    const int rounds = (ctas_per_sm + resident - 1) / resident;
+    r.resident = resident;
+    r.per_sm_clk = (double)ctas_per_sm * block * iters * ops / (avg * rounds);
+    r.per_sm_clk_wall = r.gops * 1e9 / g_sms / g_clock_hz;   // from the wall clock and the maximum SM clock
     return r;
 }
 
 int main(int argc, char** argv) {
     cudaDeviceProp p; CHECK(cudaGetDeviceProperties(&p, 0)); g_sms = p.multiProcessorCount;
+    { int khz = 0; CHECK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0)); g_clock_hz = khz * 1e3; }
     int maxgrid = g_sms * 8;
     CHECK(cudaMalloc(&g_out, (size_t)maxgrid * 256 * 4)); CHECK(cudaMalloc(&g_cyc, maxgrid * 8));
     std::vector<unsigned> hin(256 * 24); for (size_t i = 0; i < hin.size(); i++) hin[i] = (unsigned)(i * 2654435761u + 12345u);
@@ -178,7 +188,7 @@ int main(int argc, char** argv) {
     FILE* f = argc > 1 ? fopen(argv[1], "w") : stdout;
     fprintf(f, "{\"gpu\": \"%s\", \"sms\": %d, \"variants\": {", p.name, g_sms);
     for (size_t i = 0; i < rs.size(); i++)
-        fprintf(f, "%s\"%s\": {\"gops\": %.1f, \"per_sm_per_clk\": %.2f, \"ms\": %.3f}", i ? ", " : "", rs[i].name, rs[i].gops, rs[i].per_sm_clk, rs[i].ms);
+        fprintf(f, "%s\"%s\": {\"gops\": %.1f, \"per_sm_per_clk\": %.2f, \"per_sm_per_clk_wall\": %.2f, \"resident_ctas\": %d, \"ms\": %.3f}", i ? ", " : "", rs[i].name, rs[i].gops, rs[i].per_sm_clk, rs[i].per_sm_clk_wall, rs[i].resident, rs[i].ms);
     fprintf(f, "}}\n"); if (f != stdout) fclose(f);
     return 0;
 }

@@ -2,9 +2,10 @@
 // element order (so the result feeds tfhe_b200_setup(..., key_space = TFHE_B200_DEVICE) and never exists on the host).
 // Follows BinFHEScheme::KeyGen (binfhe-base-scheme.cpp:38-57): key-switching key (lwe-pke.cpp:218-295), RingGSW
 // bootstrapping key for CGGI (rgsw-acc-cggi.cpp:43-75, 213-240) and DM (rgsw-acc-dm.cpp:44-76, 153-209).
-// Randomness: Philox4x32-10 counter streams keyed by the caller's seed; uniform residues by Lemire's multiply-shift
-// with rejection (unbiased), errors from an inversion table of the discrete Gaussian D_{Z, 3.19} (64-bit cumulative
-// probabilities).  Key generation is randomised, so it cannot be bit-compared with the reference: the tests check
+// Randomness: ChaCha20 in counter mode under a 256-bit key (from the caller or the operating system), separate derived
+// keys for the public masks and the secret errors (the reference uses a BLAKE2-based PRNG seeded from the OS,
+// core/include/math/distributiongenerator.h:86-130); uniform residues by Lemire's multiply-shift with rejection
+// (unbiased), errors from an inversion table of the discrete Gaussian D_{Z, 3.19} (64-bit cumulative probabilities).  Key generation is randomised, so it cannot be bit-compared with the reference: the tests check
 // decryption correctness of everything evaluated under these keys and the noise distribution of the key material.
 #include <cmath>
 #include <cstdio>
@@ -18,22 +19,48 @@ namespace tfhe_b200 {
 
 namespace {
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+// ChaCha20 block function (RFC 8439 state layout: constants | 256-bit key | 128 bits of counter / nonce) used as a
+// counter-mode PRF: every random element is a function of (key, stream, index, attempt), so the result does not depend
+// on the launch shape, and with a 256-bit key from a CSPRNG the published masks reveal nothing about the error stream
+// (the evaluation keys go to an untrusted evaluator: a generator that can be inverted or whose seed can be searched
+// exposes every error term and with it the secret key).
+struct PrfKey {
+    u32 k[8];
+};
+__host__ __device__ __forceinline__ u32 rotl32(u32 x, int r) {
+    return (x << r) | (x >> (32 - r));
+}
+#define CHACHA_QR(a, b, c, d)                    \
+    a += b; d ^= a; d = rotl32(d, 16);           \
+    c += d; b ^= c; b = rotl32(b, 12);           \
+    a += b; d ^= a; d = rotl32(d, 8);            \
+    c += d; b ^= c; b = rotl32(b, 7);
+// first 128 bits of the ChaCha20 block with counter/nonce words (c0, c1, c2, c3)
+__host__ __device__ __forceinline__ void chacha20_block(const PrfKey& K, u32 c0, u32 c1, u32 c2, u32 c3, u32 out[16]) {
+    u32 x[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, K.k[0], K.k[1], K.k[2], K.k[3],
+                 K.k[4], K.k[5], K.k[6], K.k[7], c0, c1, c2, c3};
+    u32 w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        w[i] = x[i];
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        const u32 hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const u32 hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
+        CHACHA_QR(w[0], w[4], w[8], w[12]) CHACHA_QR(w[1], w[5], w[9], w[13])
+        CHACHA_QR(w[2], w[6], w[10], w[14]) CHACHA_QR(w[3], w[7], w[11], w[15])
+        CHACHA_QR(w[0], w[5], w[10], w[15]) CHACHA_QR(w[1], w[6], w[11], w[12])
+        CHACHA_QR(w[2], w[7], w[8], w[13]) CHACHA_QR(w[3], w[4], w[9], w[14])
     }
-    return c;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        out[i] = w[i] + x[i];
 }
 // 128 random bits for (stream, index, attempt)
-__device__ __forceinline__ uint4 rnd128(u64 seed, u32 stream, u64 idx, u32 attempt) {
-    return philox4x32_10(make_uint4((u32)idx, (u32)(idx >> 32), stream, attempt), make_uint2((u32)seed, (u32)(seed >> 32)));
+__device__ __forceinline__ uint4 rnd128(const PrfKey& key, u32 stream, u64 idx, u32 attempt) {
+    u32 o[16];
+    chacha20_block(key, (u32)idx, (u32)(idx >> 32), stream, attempt, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
 }
-__device__ __forceinline__ u64 uniform_mod(u64 seed, u32 stream, u64 idx, u64 m) {
+__device__ __forceinline__ u64 uniform_mod(const PrfKey& seed, u32 stream, u64 idx, u64 m) {
     for (u32 attempt = 0;; attempt++) {
         const uint4 r = rnd128(seed, stream, idx, attempt);
         const u64 x = ((u64)r.y << 32) | r.x;
@@ -47,7 +74,7 @@ __device__ __forceinline__ u64 uniform_mod(u64 seed, u32 stream, u64 idx, u64 m)
     }
 }
 // discrete Gaussian: cdt[k] = floor(2^64 * P(|X| <= k)), the last entry saturated
-__device__ __forceinline__ int gauss(u64 seed, u32 stream, u64 idx, const u64* cdt, int len) {
+__device__ __forceinline__ int gauss(const PrfKey& seed, u32 stream, u64 idx, const u64* cdt, int len) {
     const uint4 r = rnd128(seed, stream, idx, 0);
     const u64 x = ((u64)r.y << 32) | r.x;
     int k = 0;
@@ -97,7 +124,8 @@ struct BKArgs {
     const u64* WM;               // twiddles, Montgomery form
     const u64* psiM;             // psi^x, x < 2N, Montgomery form (DM monomials)
     const u64* cdt;
-    u64 seed, baseG;
+    PrfKey key_mask, key_err;    // independent PRF keys for the public masks and the secret errors
+    u64 baseG;
     u32 n, N, d2, throwd, method, baseR, digitsR, q;
     int cdt_len;
     ModCtx<u64> M;
@@ -143,11 +171,11 @@ __global__ void bk_gen_kernel(BKArgs A) {
     for (u32 x = 0; x < (r >> 1) + A.throwd; x++)
         G = (u64)(((unsigned __int128)G * (A.baseG % Q)) % Q);
     for (u32 k = threadIdx.x; k < N; k += blockDim.x)
-        se[k] = signed_mod(gauss(A.seed, STREAM_BK_E, rowid * N + k, A.cdt, A.cdt_len), Q);
+        se[k] = signed_mod(gauss(A.key_err, STREAM_BK_E, rowid * N + k, A.cdt, A.cdt_len), Q);
     ntt_forward_smem(se, A.WM, N, A.M);
     const u32 logN = 31 - __clz(N);
     for (u32 k = threadIdx.x; k < N; k += blockDim.x) {
-        const u64 a = uniform_mod(A.seed, STREAM_BK_A, rowid * N + k, Q);
+        const u64 a = uniform_mod(A.key_mask, STREAM_BK_A, rowid * N + k, Q);
         u64 msg = 0;
         if (has_msg) {
             if (A.method == TFHE_B200_METHOD_GINX)
@@ -176,7 +204,8 @@ struct KSKArgs {
     const signed char* sk_lwe;
     const signed char* sk_ring;
     const u64* cdt;
-    u64 seed, qKS;
+    PrfKey key_mask, key_err;
+    u64 qKS;
     u32 n, N, baseKS, dKS;
     int cdt_len;
 };
@@ -187,7 +216,7 @@ __global__ void ksk_gen_kernel(KSKArgs A) {
     u64* row = A.ksk + rowid * (A.n + 1);
     u64 part = 0;
     for (u32 t = threadIdx.x; t < A.n; t += blockDim.x) {
-        const u64 a = uniform_mod(A.seed, STREAM_KSK_A, rowid * A.n + t, qKS);
+        const u64 a = uniform_mod(A.key_mask, STREAM_KSK_A, rowid * A.n + t, qKS);
         row[t] = a;
         const int s = A.sk_lwe[t];
         if (s == 1)
@@ -210,7 +239,7 @@ __global__ void ksk_gen_kernel(KSKArgs A) {
         u64 msg = (u64)(((unsigned __int128)(j % qKS) * dig) % qKS);
         const int s = A.sk_ring[i];
         msg = s == 0 ? 0 : (s == 1 ? msg : (msg ? qKS - msg : 0));
-        const u64 e = signed_mod(gauss(A.seed, STREAM_KSK_E, rowid, A.cdt, A.cdt_len), qKS);
+        const u64 e = signed_mod(gauss(A.key_err, STREAM_KSK_E, rowid, A.cdt, A.cdt_len), qKS);
         row[A.n] = (red[0] + e + msg) % qKS;
     }
 }
@@ -261,9 +290,19 @@ const char* keygen_last_error() {
         }                                                                                               \
     } while (0)
 
-int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const signed char* sk_ring, u64 seed, int device,
-                  u64* bk_dev, u64* ksk_dev) {
+int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const signed char* sk_ring,
+                  const unsigned char key[32], int device, u64* bk_dev, u64* ksk_dev) {
     int rc = 0;
+    // two independent sub-keys (mask stream, error stream) derived from the caller's 256-bit key: one ChaCha20 block under
+    // the master key with a derivation label as nonce yields 512 bits
+    PrfKey master, key_mask, key_err;
+    memcpy(master.k, key, 32);
+    {
+        u32 o[16];
+        chacha20_block(master, 0x6b646600u /* "kdf" */, 0x62323030u /* "b200" */, 0x74666865u /* "tfhe" */, 0, o);
+        memcpy(key_mask.k, o, 32);
+        memcpy(key_err.k, o + 8, 32);
+    }
     const u32 N = p.N, n = p.n;
     const ModCtx<u64> M = make_modctx<u64>(p.Q);
     const u32 logN = 31 - __builtin_clz(N);
@@ -302,7 +341,7 @@ int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const si
     KG_TRY(cudaGetLastError());
     {
         KSKArgs a;
-        a.ksk = ksk_dev; a.sk_lwe = d_s; a.sk_ring = d_sN; a.cdt = d_cdt; a.seed = seed; a.qKS = p.qKS;
+        a.ksk = ksk_dev; a.sk_lwe = d_s; a.sk_ring = d_sN; a.cdt = d_cdt; a.key_mask = key_mask; a.key_err = key_err; a.qKS = p.qKS;
         a.n = n; a.N = N; a.baseKS = p.baseKS; a.dKS = p.dKS; a.cdt_len = (int)cdt.size();
         const u64 rows = (u64)N * p.baseKS * p.dKS;
         ksk_gen_kernel<<<(unsigned)rows, 128, 0, st>>>(a);
@@ -310,7 +349,7 @@ int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const si
     }
     {
         BKArgs a;
-        a.bk = bk_dev; a.sk_lwe = d_s; a.skM = d_skM; a.WM = d_W; a.psiM = d_psi; a.cdt = d_cdt; a.seed = seed;
+        a.bk = bk_dev; a.sk_lwe = d_s; a.skM = d_skM; a.WM = d_W; a.psiM = d_psi; a.cdt = d_cdt; a.key_mask = key_mask; a.key_err = key_err;
         a.baseG = p.baseG; a.n = n; a.N = N; a.method = p.method; a.baseR = p.baseR; a.digitsR = p.digitsR;
         a.q = (u32)p.q; a.cdt_len = (int)cdt.size(); a.M = M;
         u64 rows;
