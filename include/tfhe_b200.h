@@ -83,6 +83,30 @@ typedef struct tfhe_b200_stats {
  * -------------------------------------------------------------------------------------------------------- */
 int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* bk, size_t bk_words, const uint64_t* ksk,
                     size_t ksk_words, int key_space, int first_device, int num_gpus, tfhe_b200_handle** out);
+/* SURVEY.md section 8(f) rank 2 -- GPUSetup straight from OpenFHE's serialized keys.  bk_stream / ksk_stream are the
+ * byte streams Serial::SerializeToFile(path, cc.GetRefreshKey() / cc.GetSwitchKey(), SerType::BINARY) writes (cereal
+ * portable binary; examples/boolean-serial-binary.cpp:76-88, core/include/utils/serial.h:99-115), e.g. the mmap'ed files.
+ * The reference deserialises them into a tree of shared_ptr<RingGSWEvalKeyImpl> / NativePoly objects
+ * (boolean-serial-binary.cpp:115-131) that its GPUSetup then copies coefficient by coefficient
+ * (lib/bootstrapping.cu:933-975); here the streams are indexed once and the raw coefficients are gathered from them
+ * directly into the pinned upload chunks -- no OpenFHE object is built and no flat copy of the keys exists on the host.
+ * `params` must describe the same key set (checked: dimensions, N, Q, psi, n, qKS, baseKS, dKS).  The resulting handle
+ * is indistinguishable from one made by tfhe_b200_setup on the flattened keys. */
+int tfhe_b200_setup_from_serialized(const tfhe_b200_params* params, const void* bk_stream, size_t bk_bytes,
+                                    const void* ksk_stream, size_t ksk_bytes, int first_device, int num_gpus,
+                                    tfhe_b200_handle** out);
+/* What the two streams hold (host only, no GPU needed): m_key dimensions ([1][2][n] for CGGI, [n][baseR][digitsR] for
+ * DM), RGSW rows per evaluation key, ring dimension, moduli, the root of unity, and the sizes of the flat arrays. */
+typedef struct tfhe_b200_serialized_info_t {
+    uint64_t bk_dim[3], bk_rows, N, Q, psi;
+    uint64_t ks_N, baseKS, dKS, n, qKS;
+    size_t bk_words, ksk_words;
+} tfhe_b200_serialized_info_t;
+int tfhe_b200_serialized_info(const void* bk_stream, size_t bk_bytes, const void* ksk_stream, size_t ksk_bytes,
+                              tfhe_b200_serialized_info_t* info);
+/* The streams flattened into the element order of tfhe_b200_setup (host only; sizes from tfhe_b200_serialized_info). */
+int tfhe_b200_flatten_serialized(const void* bk_stream, size_t bk_bytes, const void* ksk_stream, size_t ksk_bytes,
+                                 uint64_t* bk_out, size_t bk_words, uint64_t* ksk_out, size_t ksk_words);
 int tfhe_b200_clean(tfhe_b200_handle* h);
 const char* tfhe_b200_last_error(void);
 int tfhe_b200_num_gpus(const tfhe_b200_handle* h);

@@ -380,6 +380,11 @@ class Ref:
         self._chk(self.L.ref_export_ksk(self.h, _p(ksk)))
         return sk, bk, ksk
 
+    def serialize_keys(self, bk_path, ksk_path):
+        """Serial::SerializeToFile(path, cc.GetRefreshKey() / cc.GetSwitchKey(), SerType::BINARY), the reference's own
+        serialization (examples/boolean-serial-binary.cpp:76-88)."""
+        self._chk(self.L.ref_serialize_keys(self.h, bk_path.encode(), ksk_path.encode()))
+
     def encrypt(self, m, p, mod):
         ct = np.zeros(self.n + 1, dtype=np.uint64)
         self._chk(self.L.ref_encrypt(self.h, C.c_int64(int(m)), C.c_uint64(p), C.c_uint64(mod), _p(ct)))

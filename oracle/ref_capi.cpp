@@ -14,7 +14,7 @@
 //     libtfhe_ref_dropin.so they run on our engine through tfhe_gpu_b200/adapter/binfhe_b200_shim.cpp.
 //
 // Ciphertext wire format everywhere: (n+1) u64 per ciphertext = a[0..n-1], b.  The modulus is passed beside it.
-#include "binfhecontext.h"
+#include "binfhecontext-ser.h"   // binfhecontext.h + cereal registration of the key types (serialization fixtures)
 #ifdef TFHE_B200_DROPIN
 #include "binfhe_b200.hpp"   // fused C++ adapter (only in the drop-in build, which links libtfhe_b200.so)
 #endif
@@ -699,6 +699,20 @@ int fused_eval_decomp(void* h, void* f, int batch, const u64* ct, u64 mod, int m
     REF_CATCH(-1)
 }
 #endif
+
+// Serialises the refreshing key and the key-switching key exactly as the reference's own example does
+// (examples/boolean-serial-binary.cpp:76-88): Serial::SerializeToFile(..., SerType::BINARY), i.e. cereal's portable
+// binary archive of RingGSWACCKey / LWESwitchingKey.  Fixtures for the serialized-key reader of the engine.
+int ref_serialize_keys(void* h, const char* bk_path, const char* ksk_path) {
+    REF_TRY
+    auto* c = (RefCtx*)h;
+    if (!Serial::SerializeToFile(bk_path, c->cc.GetRefreshKey(), SerType::BINARY))
+        throw std::runtime_error("cannot write the refreshing key");
+    if (!Serial::SerializeToFile(ksk_path, c->cc.GetSwitchKey(), SerType::BINARY))
+        throw std::runtime_error("cannot write the switching key");
+    return 0;
+    REF_CATCH(-1)
+}
 
 int ref_num_threads() {
     return omp_get_max_threads();

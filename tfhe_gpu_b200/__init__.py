@@ -21,4 +21,6 @@ from .context import (  # noqa: F401
     lib_path,
     load_library,
     gpu_keygen,
+    serialized_info,
+    flatten_serialized,
 )

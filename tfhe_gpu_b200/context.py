@@ -88,7 +88,8 @@ EXPORTS = [
     "tfhe_b200_ksk_words", "tfhe_b200_kernel_variant", "tfhe_b200_set_option", "tfhe_b200_eval_acc",
     "tfhe_b200_mkmswitch", "tfhe_b200_mul_matrix", "tfhe_b200_eval_bin_gate", "tfhe_b200_bootstrap_func",
     "tfhe_b200_eval_func", "tfhe_b200_eval_floor", "tfhe_b200_eval_sign", "tfhe_b200_eval_decomp",
-    "tfhe_b200_eval_bin_gate_v", "tfhe_b200_eval_circuit", "tfhe_b200_keygen", "tfhe_b200_keygen_test_seed", "tfhe_b200_add_key_set", "tfhe_b200_num_key_sets",
+    "tfhe_b200_eval_bin_gate_v", "tfhe_b200_eval_circuit", "tfhe_b200_keygen", "tfhe_b200_keygen_test_seed", "tfhe_b200_setup_from_serialized",
+    "tfhe_b200_serialized_info", "tfhe_b200_flatten_serialized", "tfhe_b200_add_key_set", "tfhe_b200_num_key_sets",
 ]
 
 
@@ -191,6 +192,47 @@ def gpu_keygen(params, sk_lwe, sk_ring, key=None, device=0, seed=None):
     return bk, ksk
 
 
+class SerializedInfo(C.Structure):
+    """tfhe_b200_serialized_info_t."""
+
+    _fields_ = [("bk_dim", C.c_uint64 * 3), ("bk_rows", C.c_uint64), ("N", C.c_uint64), ("Q", C.c_uint64),
+                ("psi", C.c_uint64), ("ks_N", C.c_uint64), ("baseKS", C.c_uint64), ("dKS", C.c_uint64),
+                ("n", C.c_uint64), ("qKS", C.c_uint64), ("bk_words", C.c_size_t), ("ksk_words", C.c_size_t)]
+
+
+def _stream(x):
+    """bytes / bytearray / mmap / uint8 numpy array -> (pointer, length, keep-alive object)."""
+    a = np.frombuffer(x, dtype=np.uint8) if not isinstance(x, np.ndarray) else np.ascontiguousarray(x, dtype=np.uint8)
+    return C.c_void_p(a.ctypes.data), C.c_size_t(a.size), a
+
+
+def serialized_info(bk_stream, ksk_stream):
+    """What OpenFHE's serialized refreshing / switching key streams hold (tfhe_b200_serialized_info; host only)."""
+    L = load_library()
+    bp, bn, _b = _stream(bk_stream)
+    kp, kn, _k = _stream(ksk_stream)
+    info = SerializedInfo()
+    rc = L.tfhe_b200_serialized_info(bp, bn, kp, kn, C.byref(info))
+    if rc != 0:
+        raise TfheB200Error(rc, L.tfhe_b200_last_error().decode())
+    return info
+
+
+def flatten_serialized(bk_stream, ksk_stream):
+    """The serialized streams as the flat uint64 arrays GPUSetup takes (tfhe_b200_flatten_serialized; host only)."""
+    L = load_library()
+    info = serialized_info(bk_stream, ksk_stream)
+    bp, bn, _b = _stream(bk_stream)
+    kp, kn, _k = _stream(ksk_stream)
+    bk = np.empty(info.bk_words, dtype=np.uint64)
+    ksk = np.empty(info.ksk_words, dtype=np.uint64)
+    rc = L.tfhe_b200_flatten_serialized(bp, bn, kp, kn, C.c_void_p(bk.ctypes.data), C.c_size_t(bk.size),
+                                        C.c_void_p(ksk.ctypes.data), C.c_size_t(ksk.size))
+    if rc != 0:
+        raise TfheB200Error(rc, L.tfhe_b200_last_error().decode())
+    return bk, ksk
+
+
 class BinFHEContextB200:
     """GPU half of the reference's BinFHEContext.  Keys come in as the flat arrays the reference's own GPUSetup
     flattens them to (bootstrapping.cu:933-975); see include/tfhe_b200.h for the element order."""
@@ -226,6 +268,27 @@ class BinFHEContextB200:
         h = C.c_void_p()
         rc = L.tfhe_b200_setup(C.byref(p), b.ptr, C.c_size_t(int(np.prod(b.shape))), k.ptr,
                                C.c_size_t(int(np.prod(k.shape))), b.space, first_device, numGPUs, C.byref(h))
+        if rc != 0:
+            raise TfheB200Error(rc, L.tfhe_b200_last_error().decode())
+        self._h, self.params, self.first_device = h, p, first_device
+        return self
+
+    def GPUSetupFromSerialized(self, params, bk_stream, ksk_stream, numGPUs=0, first_device=0, keep_generic=None):
+        """GPUSetup from the byte streams OpenFHE's Serial::SerializeToFile(..., SerType::BINARY) writes for
+        cc.GetRefreshKey() / cc.GetSwitchKey() (examples/boolean-serial-binary.cpp:76-88): bytes, mmap objects or uint8
+        arrays.  No flat copy of the keys is made on the host (tfhe_b200_setup_from_serialized)."""
+        L = load_library()
+        if self._h is not None:
+            self.GPUClean()
+        p = params if isinstance(params, Params) else Params.from_dict(
+            params.as_dict() if hasattr(params, "as_dict") else params)
+        if keep_generic is not None:
+            p = Params.from_dict(p.as_dict())
+            p.flags = (p.flags | 1) if keep_generic else (p.flags & ~1)
+        bp, bn, _b = _stream(bk_stream)
+        kp, kn, _k = _stream(ksk_stream)
+        h = C.c_void_p()
+        rc = L.tfhe_b200_setup_from_serialized(C.byref(p), bp, bn, kp, kn, first_device, numGPUs, C.byref(h))
         if rc != 0:
             raise TfheB200Error(rc, L.tfhe_b200_last_error().decode())
         self._h, self.params, self.first_device = h, p, first_device

@@ -417,32 +417,89 @@ static int build_tables(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M) {
     return 0;
 }
 
-// upload + re-encode the keys on device 0
+// Host-side producer of the two flat key arrays (element order of tfhe_b200_setup), chunk by chunk: either the caller's
+// flat arrays, or an index over OpenFHE's serialized streams (serial_reader.cu) -- the staging loop below does not care.
+namespace {
+struct KeySource {
+    virtual ~KeySource() {}
+    virtual void bk_words(u64* dst, size_t off, size_t cnt) const = 0;
+    virtual void ksk_rows(u64* dst, size_t row0, size_t nrows, u32 words) const = 0;
+};
+struct FlatKeys : KeySource {
+    const u64 *bk, *ksk;
+    FlatKeys(const u64* b, const u64* k) : bk(b), ksk(k) {}
+    void bk_words(u64* dst, size_t off, size_t cnt) const override { par_memcpy(dst, bk + off, cnt * 8); }
+    void ksk_rows(u64* dst, size_t row0, size_t nrows, u32 words) const override {
+        par_memcpy(dst, ksk + row0 * words, nrows * words * 8);
+    }
+};
+struct SerializedKeys : KeySource {
+    SerializedAccKey acc;
+    SerializedSwitchKey sw;
+    void bk_words(u64* dst, size_t off, size_t cnt) const override {
+        const size_t blk = (size_t)acc.N * 16;   // a few polynomials per task
+        const long nblk = (long)((cnt + blk - 1) / blk);
+#pragma omp parallel for num_threads(4) schedule(static) if (nblk > 8)
+        for (long b = 0; b < nblk; b++) {
+            const size_t o = (size_t)b * blk;
+            acc.gather(dst + o, off + o, std::min(blk, cnt - o));
+        }
+    }
+    void ksk_rows(u64* dst, size_t row0, size_t nrows, u32 words) const override {
+        const size_t blk = 256;
+        const long nblk = (long)((nrows + blk - 1) / blk);
+#pragma omp parallel for num_threads(4) schedule(static) if (nblk > 8)
+        for (long b = 0; b < nblk; b++) {
+            const size_t o = (size_t)b * blk;
+            sw.gather_rows(dst + o * words, row0 + o, std::min(blk, nrows - o));
+        }
+    }
+};
+}  // namespace
+
+// upload + re-encode the keys on device 0.  Device-resident keys (key_space = DEVICE: bk_dev / ksk_dev) are converted in
+// place; host keys stream through two pinned 32 MiB chunks: the host fills chunk c+1 (memcpy from the caller's arrays,
+// or a gather from the serialized stream) while the GPU copies and converts chunk c.
 template <typename T>
-static int encode_keys(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M, const u64* bk, const u64* ksk, int key_space) {
+static int encode_keys(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M, const KeySource* src, const u64* bk, const u64* ksk,
+                       int key_space) {
     const tfhe_b200_params& p = h->p;
     const u64 Q = p.Q;
     u64 ninv = h_powmod(p.N, Q - 2, Q);
     u64 R = (u64)M.oneM;
     T ninvM2 = (T)h_mulmod(h_mulmod(ninv, R, Q), R, Q);  // N^-1 * R^2: mont_mul(x, .) = x * N^-1 * R
-    const size_t stage_words = (size_t)4 << 20;           // 32 MiB staging for host-resident keys
-    u64* stage = nullptr;
+    const size_t stage_words = (size_t)4 << 20;           // 32 MiB staging chunks for host-resident keys
+    u64* stage[2] = {nullptr, nullptr};                   // device
+    u64* hstage[2] = {nullptr, nullptr};                  // pinned host
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     if (key_space == TFHE_B200_HOST)
-        CUDA_TRY(cudaMalloc((void**)&stage, stage_words * sizeof(u64)));
+        for (int k = 0; k < 2; k++) {
+            CUDA_TRY(cudaMalloc((void**)&stage[k], stage_words * sizeof(u64)));
+            CUDA_TRY(cudaHostAlloc((void**)&hstage[k], stage_words * sizeof(u64), cudaHostAllocDefault));
+            CUDA_TRY(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+        }
+    int chunk = 0;
+    // fills pinned slot, uploads it and returns the device staging pointer; the caller launches the conversion and then
+    // calls done(slot)
+    auto upload = [&](int slot, size_t words) -> int {
+        CUDA_TRY(cudaMemcpyAsync(stage[slot], hstage[slot], words * sizeof(u64), cudaMemcpyHostToDevice, d.stream));
+        return 0;
+    };
 
     // ---- bootstrapping key, generic layout (same element order as the source) ----
-    const bool need_generic = true;
-    if (need_generic) {
-        CUDA_TRY(cudaMalloc(&d.bk_generic, h->bk_words * sizeof(T)));
-        if (key_space == TFHE_B200_DEVICE)
-            CUDA_TRY(launch_bk_convert_generic<T>((T*)d.bk_generic, bk, h->bk_words, M, ninvM2, d.stream));
-        else {
-            for (size_t off = 0; off < h->bk_words; off += stage_words) {
-                size_t cnt = h->bk_words - off < stage_words ? h->bk_words - off : stage_words;
-                CUDA_TRY(cudaMemcpyAsync(stage, bk + off, cnt * sizeof(u64), cudaMemcpyHostToDevice, d.stream));
-                CUDA_TRY(launch_bk_convert_generic<T>((T*)d.bk_generic + off, stage, cnt, M, ninvM2, d.stream));
-                CUDA_TRY(cudaStreamSynchronize(d.stream));
-            }
+    CUDA_TRY(cudaMalloc(&d.bk_generic, h->bk_words * sizeof(T)));
+    if (key_space == TFHE_B200_DEVICE)
+        CUDA_TRY(launch_bk_convert_generic<T>((T*)d.bk_generic, bk, h->bk_words, M, ninvM2, d.stream));
+    else {
+        for (size_t off = 0; off < h->bk_words; off += stage_words, chunk++) {
+            const int slot = chunk & 1;
+            const size_t cnt = std::min(h->bk_words - off, stage_words);
+            CUDA_TRY(cudaEventSynchronize(ev[slot]));          // the previous user of this slot has been consumed
+            src->bk_words(hstage[slot], off, cnt);
+            int r = upload(slot, cnt);
+            if (r) return r;
+            CUDA_TRY(launch_bk_convert_generic<T>((T*)d.bk_generic + off, stage[slot], cnt, M, ninvM2, d.stream));
+            CUDA_TRY(cudaEventRecord(ev[slot], d.stream));
         }
     }
     // ---- key switching key: narrowest word, 16-byte padded rows ----
@@ -454,19 +511,28 @@ static int encode_keys(tfhe_b200_handle* h, Dev& d, const ModCtx<T>& M, const u6
             CUDA_TRY(launch_ksk_convert(d.ksk, h->ksk_bytes, h->row_stride, ksk, rows, words, d.stream));
         else {
             const size_t rows_per = stage_words / words;
-            for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
-                size_t cnt = rows - r0 < rows_per ? rows - r0 : rows_per;
-                CUDA_TRY(cudaMemcpyAsync(stage, ksk + r0 * words, cnt * words * sizeof(u64), cudaMemcpyHostToDevice,
-                                         d.stream));
+            for (size_t r0 = 0; r0 < rows; r0 += rows_per, chunk++) {
+                const int slot = chunk & 1;
+                const size_t cnt = std::min(rows - r0, rows_per);
+                CUDA_TRY(cudaEventSynchronize(ev[slot]));
+                src->ksk_rows(hstage[slot], r0, cnt, words);
+                int r = upload(slot, cnt * words);
+                if (r) return r;
                 CUDA_TRY(launch_ksk_convert((unsigned char*)d.ksk + r0 * h->row_stride * h->ksk_bytes, h->ksk_bytes,
-                                            h->row_stride, stage, cnt, words, d.stream));
-                CUDA_TRY(cudaStreamSynchronize(d.stream));
+                                            h->row_stride, stage[slot], cnt, words, d.stream));
+                CUDA_TRY(cudaEventRecord(ev[slot], d.stream));
             }
         }
     }
     CUDA_TRY(cudaStreamSynchronize(d.stream));
-    if (stage)
-        CUDA_TRY(cudaFree(stage));
+    for (int k = 0; k < 2; k++) {
+        if (stage[k])
+            CUDA_TRY(cudaFree(stage[k]));
+        if (hstage[k])
+            CUDA_TRY(cudaFreeHost(hstage[k]));
+        if (ev[k])
+            CUDA_TRY(cudaEventDestroy(ev[k]));
+    }
     return 0;
 }
 
@@ -649,11 +715,10 @@ extern "C" int tfhe_b200_clean(tfhe_b200_handle* h) {
     return 0;
 }
 
-extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* bk, size_t bk_words, const uint64_t* ksk,
-                               size_t ksk_words, int key_space, int first_device, int num_gpus,
-                               tfhe_b200_handle** out) {
-    if (!params || !bk || !ksk || !out)
-        FAIL(TFHE_B200_EINVAL, "setup: null argument (the reference throws 'Need to call BTKeyGen before calling GPUSetup')");
+// `src` produces host-resident keys chunk by chunk (key_space = HOST); bk / ksk are the device arrays for key_space = DEVICE
+static int setup_impl(const tfhe_b200_params* params, const KeySource* src, const uint64_t* bk, size_t bk_words,
+                      const uint64_t* ksk, size_t ksk_words, int key_space, int first_device, int num_gpus,
+                      tfhe_b200_handle** out) {
     const tfhe_b200_params& p = *params;
     if (p.N < 16 || (p.N & (p.N - 1)) || p.N > 4096)
         FAIL(TFHE_B200_ENOTSUP, "setup: ring dimension N must be a power of two in [16, 4096]");
@@ -783,8 +848,8 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
         Dev& d0 = h->devs[0];
         auto enc = [&]() -> int {
             CUDA_TRY(cudaSetDevice(d0.id));
-            int r = h->is64 ? encode_keys<u64>(h, d0, h->m64, bk, ksk, key_space)
-                            : encode_keys<u32>(h, d0, h->m32, bk, ksk, key_space);
+            int r = h->is64 ? encode_keys<u64>(h, d0, h->m64, src, bk, ksk, key_space)
+                            : encode_keys<u32>(h, d0, h->m32, src, bk, ksk, key_space);
             if (r)
                 return r;
             // constants of the top-digit elimination: B^(l-top) (l < top) and N * B^-top, Montgomery form (the kernels
@@ -889,6 +954,90 @@ extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* b
     }
     *out = h;
     return 0;
+}
+
+extern "C" int tfhe_b200_setup(const tfhe_b200_params* params, const uint64_t* bk, size_t bk_words, const uint64_t* ksk,
+                               size_t ksk_words, int key_space, int first_device, int num_gpus,
+                               tfhe_b200_handle** out) {
+    if (!params || !bk || !ksk || !out)
+        FAIL(TFHE_B200_EINVAL, "setup: null argument (the reference throws 'Need to call BTKeyGen before calling GPUSetup')");
+    FlatKeys src(bk, ksk);
+    return setup_impl(params, &src, bk, bk_words, ksk, ksk_words, key_space, first_device, num_gpus, out);
+}
+
+// ---- keys straight from OpenFHE's serialized streams ------------------------------------------------
+static int index_streams(const void* bk_stream, size_t bk_bytes, const void* ksk_stream, size_t ksk_bytes,
+                         SerializedKeys* sk) {
+    if (!bk_stream || !ksk_stream || !bk_bytes || !ksk_bytes)
+        FAIL(TFHE_B200_EINVAL, "serialized keys: null or empty stream");
+    std::string err;
+    int rc = index_serialized_acc_key(bk_stream, bk_bytes, &sk->acc, &err);
+    if (rc == 0)
+        rc = index_serialized_switch_key(ksk_stream, ksk_bytes, &sk->sw, &err);
+    if (rc)
+        g_err = "serialized keys: " + err;
+    return rc;
+}
+
+extern "C" int tfhe_b200_serialized_info(const void* bk_stream, size_t bk_bytes, const void* ksk_stream, size_t ksk_bytes,
+                                         tfhe_b200_serialized_info_t* info) {
+    if (!info)
+        FAIL(TFHE_B200_EINVAL, "serialized keys: null info");
+    SerializedKeys sk;
+    int rc = index_streams(bk_stream, bk_bytes, ksk_stream, ksk_bytes, &sk);
+    if (rc)
+        return rc;
+    memset(info, 0, sizeof(*info));
+    for (int k = 0; k < 3; k++)
+        info->bk_dim[k] = sk.acc.dim[k];
+    info->bk_rows = sk.acc.rows; info->N = sk.acc.N; info->Q = sk.acc.Q; info->psi = sk.acc.psi;
+    info->ks_N = sk.sw.N; info->baseKS = sk.sw.baseKS; info->dKS = sk.sw.dKS; info->n = sk.sw.n; info->qKS = sk.sw.qKS;
+    info->bk_words = sk.acc.poly_off.size() * sk.acc.N;
+    info->ksk_words = sk.sw.rowA_off.size() * (sk.sw.n + 1);
+    return 0;
+}
+
+extern "C" int tfhe_b200_flatten_serialized(const void* bk_stream, size_t bk_bytes, const void* ksk_stream,
+                                            size_t ksk_bytes, uint64_t* bk_out, size_t bk_words, uint64_t* ksk_out,
+                                            size_t ksk_words) {
+    if (!bk_out || !ksk_out)
+        FAIL(TFHE_B200_EINVAL, "serialized keys: null output");
+    SerializedKeys sk;
+    int rc = index_streams(bk_stream, bk_bytes, ksk_stream, ksk_bytes, &sk);
+    if (rc)
+        return rc;
+    if (bk_words != sk.acc.poly_off.size() * sk.acc.N || ksk_words != sk.sw.rowA_off.size() * (sk.sw.n + 1))
+        FAIL(TFHE_B200_EINVAL, "serialized keys: output sizes do not match the streams (see tfhe_b200_serialized_info)");
+    sk.bk_words(bk_out, 0, bk_words);
+    sk.ksk_rows(ksk_out, 0, sk.sw.rowA_off.size(), (u32)sk.sw.n + 1);
+    return 0;
+}
+
+extern "C" int tfhe_b200_setup_from_serialized(const tfhe_b200_params* params, const void* bk_stream, size_t bk_bytes,
+                                               const void* ksk_stream, size_t ksk_bytes, int first_device, int num_gpus,
+                                               tfhe_b200_handle** out) {
+    if (!params || !out)
+        FAIL(TFHE_B200_EINVAL, "setup: null argument");
+    SerializedKeys sk;
+    int rc = index_streams(bk_stream, bk_bytes, ksk_stream, ksk_bytes, &sk);
+    if (rc)
+        return rc;
+    // the streams must describe exactly the key set the parameters name
+    const tfhe_b200_params& p = *params;
+    const bool ginx = p.method == TFHE_B200_METHOD_GINX;
+    const u64 want_rows = ginx ? 2 * (u64)(p.digitsG - p.numDigitsToThrow) : 2 * (u64)p.digitsG;
+    const bool dims_ok = ginx ? (sk.acc.dim[0] == 1 && sk.acc.dim[1] == 2 && sk.acc.dim[2] == p.n)
+                              : (sk.acc.dim[0] == p.n && sk.acc.dim[1] == p.baseR && sk.acc.dim[2] == p.digitsR);
+    if (!dims_ok || sk.acc.rows != want_rows || sk.acc.N != p.N || sk.acc.Q != p.Q)
+        FAIL(TFHE_B200_EINVAL, "setup: the serialized refreshing key does not match the parameter set (dimensions, ring "
+                               "dimension or modulus)");
+    if (sk.acc.psi && sk.acc.psi != p.psi)
+        FAIL(TFHE_B200_EINVAL, "setup: the serialized refreshing key was transformed with another root of unity than "
+                               "params.psi");
+    if (sk.sw.N != p.N || sk.sw.baseKS != p.baseKS || sk.sw.dKS != p.dKS || sk.sw.n != p.n || sk.sw.qKS != p.qKS)
+        FAIL(TFHE_B200_EINVAL, "setup: the serialized switching key does not match the parameter set");
+    return setup_impl(params, &sk, nullptr, bk_words_of(&p), nullptr, ksk_words_of(&p), TFHE_B200_HOST, first_device,
+                      num_gpus, out);
 }
 
 // SURVEY 8(f) rank 4 -- BinFHEContext::BTKeyGen with timeOptimization fills m_BTKey_map with one RingGSWBTKey (BK and

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -101,6 +102,27 @@ bool cggi64w_supported(const tfhe_b200_params& p);
 bool cggi64w_plain_supported(const tfhe_b200_params& p);
 void cggi64w_build_tables(const tfhe_b200_params& p, std::vector<u64>& twU, std::vector<u64>& twB, std::vector<u64>& twC);
 cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s, int sm_count = 0, int group = 0);
+
+// Serialized-key reader (serial_reader.cu): an index over OpenFHE's cereal portable-binary stream of a RingGSWACCKey /
+// LWESwitchingKey -- where every polynomial / key-switching row lives in the byte stream -- plus gather functions that
+// produce chunks of the flat element order tfhe_b200_setup takes.  No OpenFHE object is built.
+struct SerializedAccKey {
+    const unsigned char* base = nullptr;
+    u64 dim[3] = {0, 0, 0};          // m_key dimensions ([1][2][n] for CGGI, [n][baseR][digitsR] for DM)
+    u64 rows = 0;                    // RGSW rows per evaluation key (d)
+    u64 N = 0, Q = 0, psi = 0;
+    std::vector<size_t> poly_off;    // byte offset of the N raw coefficients of polynomial p ((size_t)-1: null entry)
+    void gather(u64* dst, size_t off_words, size_t cnt_words) const;
+};
+struct SerializedSwitchKey {
+    const unsigned char* base = nullptr;
+    u64 N = 0, baseKS = 0, dKS = 0, n = 0, qKS = 0;
+    std::vector<size_t> rowA_off;    // [N * baseKS * dKS] byte offset of the n mask words
+    std::vector<size_t> rowB_off;    // [N * baseKS]       byte offset of the dKS b words
+    void gather_rows(u64* dst, size_t row0, size_t nrows) const;
+};
+int index_serialized_acc_key(const void* data, size_t bytes, SerializedAccKey* out, std::string* err);
+int index_serialized_switch_key(const void* data, size_t bytes, SerializedSwitchKey* out, std::string* err);
 
 // GPU key generation (keygen.cu)
 int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const signed char* sk_ring,
