@@ -81,7 +81,11 @@ __device__ __forceinline__ void tma_bulk_g2s(u32 dst, const void* src, u32 bytes
 // last pair of warps only helps in the pointwise stage.  The critical path of a rotation step is 1 inverse + 1 forward
 // transform + N / (64 DK) pointwise iterations instead of 1 + (DK-1) + N/64.  Chosen for batches of at most one
 // ciphertext per SM.
-template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false>
+//
+// SWEEP = true (28-bit moduli): one reduction sweep between the two passes of every forward transform, see
+// sweep_below_2q in ntt32.cuh; everything else is unchanged (the pointwise bounds hold for Q < 2^28: lazy rows < 12 Q,
+// eight of them times a key word < Q stay below 2^63, and the two reduced sums times the monomial factors below Q 2^32).
+template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, bool SWEEP = false>
 __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
     br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
     using K = KCfg<LOGN, DK, G>;
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
         for (int r = 0; r < 32; r++)
             v[r] = c[r];
         fwd_passA(v, A, Q, Q2);
+        if (SWEEP)
+            sweep_below_2q(v, Q2);
         u32* reg = Dsm + (size_t)g * D * RS + (size_t)(j + 2 * (DK - 1)) * RS;
 #pragma unroll
         for (int r = 0; r < 32; r++)
@@ -273,6 +279,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
             }
             fwd_passA(v, A, Q, Q2);
+            if (SWEEP)
+                sweep_below_2q(v, Q2);
             u32* reg = myD + (size_t)(j + 2 * l) * RS;
             // transpose A layout -> B layout through the (padded) region
 #pragma unroll
@@ -510,12 +518,17 @@ bool cggi32_supported(const tfhe_b200_params& p) {
         return false;
     if (p.N != 512 && p.N != 1024)
         return false;
-    if (p.Q >= (1ULL << 32) / 22)  // lazy forward NTT bound: values < 22 Q must fit 32 bits
-        return false;
     if (p.digitsG <= p.numDigitsToThrow)
         return false;
     const u32 dk = p.digitsG - p.numDigitsToThrow;
-    const bool inst = p.N == 1024 ? (dk >= 2 && dk <= 6) : (dk == 2 || dk == 3 || dk == 4 || dk == 6);
+    bool inst = p.N == 1024 ? (dk >= 2 && dk <= 6) : (dk == 2 || dk == 3 || dk == 4 || dk == 6);
+    if (cggi32_needs_sweep(p.Q)) {
+        // lazy forward NTT bound: values < 22 Q must fit 32 bits; 28-bit moduli run the variant with a mid-transform
+        // sweep (12 Q per pass), instantiated for N = 1024 with three or four kept digits (MEDIUM, SIGNED_MOD_TEST)
+        if (p.Q >= (1ULL << 28))
+            return false;
+        inst = p.N == 1024 && (dk == 3 || dk == 4);
+    }
     if (!inst)
         return false;
     // digits are extracted from the low 32 bits of (centred value + offset): every digit window must lie inside them
@@ -635,6 +648,21 @@ static cudaError_t launch_t2(const CGGI32Args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// 28-bit moduli: throughput shape only (N = 1024, four ciphertexts per CTA)
+template <int DK, bool SKIP>
+static cudaError_t launch_sweep(const CGGI32Args& a, cudaStream_t s) {
+    using K = KCfg<10, DK, 4>;
+    const size_t smem = K::smem_bytes((int)a.c.n);
+    if (smem > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<10, DK, 4, SKIP, false, false, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    br_cggi32_kernel<10, DK, 4, SKIP, false, false, true><<<(a.c.batch + 3) / 4, K::NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
 // latency layout: one ciphertext per CTA, 2*DK warps
 template <int LOGN, int DK>
 static cudaError_t launch_lat(const CGGI32Args& a, cudaStream_t s) {
@@ -681,6 +709,13 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
     const int dk = (int)c.digitsKept;
+    if (cggi32_needs_sweep(t.mod.Q)) {   // 28-bit modulus: see cggi32_supported
+        if (c.logN == 10 && dk == 3)
+            return t.skip_top ? launch_sweep<3, true>(a, s) : launch_sweep<3, false>(a, s);
+        if (c.logN == 10 && dk == 4)
+            return t.skip_top ? launch_sweep<4, true>(a, s) : launch_sweep<4, false>(a, s);
+        return cudaErrorInvalidConfiguration;
+    }
 #define CASE(LOGN, DK, GG) \
     if (c.logN == LOGN && dk == DK && group == GG) return launch_t<LOGN, DK, GG>(a, s, t.skip_top);
     if (c.logN == 10) {

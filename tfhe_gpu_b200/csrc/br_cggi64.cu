@@ -559,8 +559,11 @@ cudaError_t launch_t(const CGGI64Args& a, cudaStream_t s) {
 bool cggi64_supported(const tfhe_b200_params& p) {
     if (p.method != TFHE_B200_METHOD_GINX || p.N != 2048)
         return false;
-    // Q < 2^54: lazy transform outputs (< 29 Q) must split into 27-bit limbs with x1 + x0 < 2^32 (see L3)
-    if (p.Q < (1ULL << 31) || p.Q >= (1ULL << 54))
+    // Q < 2^54: lazy transform outputs (< 29 Q) must split into 27-bit limbs with x1 + x0 < 2^32 (see L3).  There is no
+    // lower bound: the 27- and 29-bit moduli of the N = 2048 sets (STD256 / STD256Q and their _OPT variants,
+    // binfhecontext.cpp:147-148,153-154) run here as well, in 64-bit words (tfhe_b200_setup selects the 64-bit engine
+    // for them), which beats the generic 32-bit kernel they would otherwise fall back to.
+    if (p.Q >= (1ULL << 54))
         return false;
     const u32 dk = p.digitsG - p.numDigitsToThrow;
     return dk >= 1 && dk <= 4;

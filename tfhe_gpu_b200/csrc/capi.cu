@@ -759,7 +759,8 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
 
     auto* h = new tfhe_b200_handle();
     h->p = p;
-    h->is64 = p.Q >= (1ULL << 31);
+    // 64-bit words for Q >= 2^31 -- and for the small-modulus N = 2048 rings, whose only specialised kernel is the 64-bit one
+    h->is64 = p.Q >= (1ULL << 31) || (cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64"));
     while ((1u << h->logN) < p.N)
         h->logN++;
     h->d = (p.method == TFHE_B200_METHOD_GINX) ? 2 * (p.digitsG - p.numDigitsToThrow) : 2 * p.digitsG;
@@ -1168,7 +1169,7 @@ static void tail_shapes(const tfhe_b200_handle* h, int* per_cta, int* tail_per_s
         return;
     const u32 dk = h->d / 2;
     if (h->have_cggi32) {
-        if (h->logN == 10 && dk == 4) {   // CTAs of 4; CTAs of 2 (<= 2 per SM) and the latency layout (<= 1 per SM)
+        if (h->logN == 10 && dk == 4 && !cggi32_needs_sweep(h->p.Q)) {   // CTAs of 4; CTAs of 2 (<= 2 per SM) and the latency layout (<= 1 per SM)
             *per_cta = 4;
             *tail_per_sm = 2;
         }

@@ -66,6 +66,19 @@ __device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u3
         }
     }
 }
+// Mid-transform sweep for 28-bit moduli: the lazy forward transform lets values grow by 2Q per stage, (2 + 2 s) Q after
+// s stages, and 22 Q must fit 32 bits -- true for the 27-bit primes only.  Bringing the values back below 2Q between the
+// two passes (three min-subtract steps per coefficient on the ALU pipe, none on the multiplier pipe) bounds both passes by
+// 12 Q, which admits every Q < 2^28 (MEDIUM, SIGNED_MOD_TEST: binfhecontext.cpp:140,155).
+__device__ __forceinline__ void sweep_below_2q(u32 (&v)[32], u32 Q2) {
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+        u32 x = v[r];                // < 12 Q
+        x = cond_sub(x, 4 * Q2);     // < 8 Q
+        x = cond_sub(x, 2 * Q2);     // < 4 Q
+        v[r] = cond_sub(x, Q2);      // < 2 Q
+    }
+}
 // forward pass B: strides 2^s, s = PB-1..0, per-thread twiddles
 template <int PB>
 __device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2,
