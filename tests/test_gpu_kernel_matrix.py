@@ -74,6 +74,103 @@ def test_dm32_small_ring(rng):
         g.GPUClean()
 
 
+Q28 = 268369921     # the 28-bit prime of MEDIUM / SIGNED_MOD_TEST (binfhecontext.cpp:140,155)
+Q29 = 536813569     # the 29-bit prime of STD256
+
+
+@pytest.mark.parametrize("N,Q,baseG,variant", [
+    (1024, Q27, 1 << 9, "dm_u32_ntt32"),            # three digits, top digit can wrap: plain path (STD128_AP set shape)
+    (512, Q27, 1 << 9, "dm_u32_ntt32"),             # TOY shape
+    (1024, Q28, 1 << 10, "dm_u32_ntt32_skiptop"),   # MEDIUM shape: elimination + mid-transform sweep
+    (1024, Q28, 1 << 7, "dm_u32_ntt32"),            # SIGNED_MOD_TEST shape: four digits, plain + sweep
+])
+def test_dm32_variants(N, Q, baseG, variant, rng):
+    """The AP/DM kernel beyond its headline shape: plain (no top-digit elimination) and 28-bit-modulus variants, on small
+    custom rings, gates / explicit accumulators / zero refresh digits, against the oracle and the generic kernel."""
+    p = po.Port.params_custom(6, N, N, Q, 128, baseG, 32, po.AP)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant == variant
+        q, n = p.q, p.n
+        c1 = rng.integers(0, q, (21, n + 1), dtype=np.uint64)              # ragged vs CTAs of 2, 4 and 8
+        c2 = rng.integers(0, q, (21, n + 1), dtype=np.uint64)
+        c1[1, :n] = 0
+        c2[1, :n] = 0
+        c1[2, :n] = 32
+        c2[2, :n] = 0
+        for gate in ("NAND", "XNOR_FAST"):
+            want = port.eval_bin_gate(bk, ksk, po.GATES[gate], c1, c2, q)
+            assert np.array_equal(g.EvalBinGate(gate, c1, c2), want), gate
+        Qm, QH = p.Q, p.Q >> 1
+        acc = rng.integers(0, Qm, (5, 2, N), dtype=np.uint64)
+        acc[0] = np.resize(np.array([0, 1, Qm - 1, QH - 1, QH, QH + 1, QH - 64, QH + 64], dtype=np.uint64), (2, N))
+        acc[1] = rng.integers(QH - 300, QH + 300, (2, N), dtype=np.uint64)     # where a wrapping top digit lives
+        am = rng.integers(0, q, (5, n), dtype=np.uint64)
+        want = port.eval_acc(bk, am, q, acc)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+        big = 4 * 148 + 2 * 148 - 5                                            # throughput + small-batch shapes
+        b1 = rng.integers(0, q, (big, n + 1), dtype=np.uint64)
+        b2 = rng.integers(0, q, (big, n + 1), dtype=np.uint64)
+        assert np.array_equal(g.EvalBinGate("OR", b1, b2), port.eval_bin_gate(bk, ksk, po.GATES["OR"], b1, b2, q))
+        g.set_option("force_generic", 1)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+    finally:
+        g.GPUClean()
+
+
+@pytest.mark.parametrize("baseG", [1 << 10, 1 << 7])                          # MEDIUM / SIGNED_MOD_TEST gadgets
+def test_cggi32_28bit_modulus_sweep(baseG, rng):
+    """28-bit moduli on the 32-bit CGGI kernel (mid-transform reduction sweep): extreme accumulator coefficients, gate and
+    LUT accumulators, against the oracle and the generic kernel."""
+    p = po.Port.params_custom(12, 1024, 1024, Q28, 128, baseG, 32, po.GINX)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant.startswith("cggi_u32_ntt32")
+        q, n, N = p.q, p.n, 1024
+        c1 = rng.integers(0, q, (11, n + 1), dtype=np.uint64)
+        c2 = rng.integers(0, q, (11, n + 1), dtype=np.uint64)
+        assert np.array_equal(g.EvalBinGate("NAND", c1, c2), port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, q))
+        tab = rng.integers(0, q, (11, q), dtype=np.uint64)
+        assert np.array_equal(g.BootstrapFunc(c1, q, tab, q), port.bootstrap_func(bk, ksk, c1, q, tab, q))
+        Qm, QH = p.Q, p.Q >> 1
+        acc = rng.integers(0, Qm, (6, 2, N), dtype=np.uint64)
+        acc[0] = np.resize(np.array([0, 1, Qm - 1, QH - 1, QH, QH + 1, QH - 64, QH + 64], dtype=np.uint64), (2, N))
+        acc[1] = Qm - 1
+        acc[2] = QH
+        am = rng.integers(0, q, (6, n), dtype=np.uint64)
+        want = port.eval_acc(bk, am, q, acc)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+        g.set_option("force_generic", 1)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+    finally:
+        g.GPUClean()
+
+
+def test_small_modulus_on_the_64bit_kernel(rng):
+    """N = 2048 rings with a modulus below 2^31 (the STD256 family) have no 32-bit kernel shape: they run on the 64-bit
+    kernels in 64-bit words."""
+    p = po.Port.params_custom(6, 2048, 2048, Q29, 128, 1 << 8, 32, po.GINX)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant.startswith("cggi_u64")
+        q, n = p.q, p.n
+        c1 = rng.integers(0, q, (7, n + 1), dtype=np.uint64)
+        c2 = rng.integers(0, q, (7, n + 1), dtype=np.uint64)
+        assert np.array_equal(g.EvalBinGate("NAND", c1, c2), port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, q))
+        acc = rng.integers(0, p.Q, (3, 2, 2048), dtype=np.uint64)
+        acc[0] = p.Q - 1
+        am = rng.integers(0, q, (3, n), dtype=np.uint64)
+        want = port.eval_acc(bk, am, q, acc)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+        g.set_option("force_generic", 1)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+    finally:
+        g.GPUClean()
+
+
 def test_top_digit_elimination_extreme_coefficients(rng):
     """Accumulator coefficients at the edges of the centred range (0, 1, Q-1, QHalf-1, QHalf, QHalf+1): where a wrapping
     top digit would break the elimination identity.  STD128-like gadget (B = 2^7, 4 digits: provably safe)."""

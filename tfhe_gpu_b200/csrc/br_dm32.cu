@@ -36,10 +36,17 @@ struct DM32Args {
 // LAT = true: latency layout for batches of at most one ciphertext per SM (same idea as br_cggi32.cu): G = 1, 2*DK
 // warps; warps 0 .. 2*(DK-1)-1 own one digit polynomial each (the DK-1 warps of a component run the inverse transform
 // redundantly, extract their own digit, do ONE forward transform), the last pair only helps in the pointwise stage.
-template <int LOGN, int DK, int G, bool LAT = false>
+//
+// PLAIN = true: no top-digit elimination, for gadgets whose top digit can wrap (baseG = 2^9 with a 27-bit modulus: the
+// named STD128_AP / STD128_APOPT sets and TOY): all DK digits of both components are transformed (2*DK forward
+// transforms per active step), the key keeps its own rows with row l' = 0 zeroed (rgsw-acc-dm.cpp:353 starts at 1), and
+// the pointwise result lands in rows 0 / 1, from where the inverse transform picks it up.
+// SWEEP = true: 28-bit moduli (MEDIUM, SIGNED_MOD_TEST), see sweep_below_2q in ntt32.cuh.
+template <int LOGN, int DK, int G, bool LAT = false, bool PLAIN = false, bool SWEEP = false>
 __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
     br_dm32_kernel(const __grid_constant__ DM32Args A) {
     using K = KCfg<LOGN, DK, G>;
+    static_assert(!(LAT && (PLAIN || SWEEP)), "latency layout exists for the top-digit-elimination path only");
     constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS;
     constexpr int NT = LAT ? 2 * DK * TPN : K::NT;
     constexpr int CT_THREADS = LAT ? NT : 2 * TPN;   // threads that serve one ciphertext
@@ -138,12 +145,14 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     };
 
     // evaluation-domain accumulator (scaled by N^-1, see br_cggi32.cu) of the initial accumulator -> top-digit region
-    if (!LAT || lw == 0) {
+    if (!PLAIN && (!LAT || lw == 0)) {
         u32 v[32];
 #pragma unroll
         for (int r = 0; r < 32; r++)
             v[r] = c[r];
         fwd_passA(v, A, Q, Q2);
+        if (SWEEP)
+            sweep_below_2q(v, Q2);
         u32* reg = myD + (size_t)(j + 2 * (DK - 1)) * RS;
 #pragma unroll
         for (int r = 0; r < 32; r++)
@@ -168,7 +177,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     const int bar_id = 1 + g;
     auto ct_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(CT_THREADS) : "memory"); };
     constexpr int MIT = N / CT_THREADS;             // pointwise iterations per thread (slots lt + CT_THREADS*it)
-    u32* top0 = myD + (size_t)(2 * (DK - 1)) * RS;  // evaluation-domain accumulator rows (a, b)
+    // evaluation-domain accumulator rows (a, b): the top-digit rows -- or rows 0 / 1 when every row is a digit row
+    u32* top0 = myD + (size_t)(PLAIN ? 0 : 2 * (DK - 1)) * RS;
 
     for (u32 s = 0; s < steps; s++) {
         const int row = kidx[g * steps + s];        // uniform over the ciphertext's threads
@@ -182,7 +192,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             cur[x] = __ldg(kp + (size_t)x * N);
         // ---- phase 1: digits 0..DK-2 of component j -> forward NTT -------------------------------------------------
 #pragma unroll 1
-        for (int l = (LAT ? lw : 0); l < (LAT ? (helper ? lw : lw + 1) : DK - 1); l++) {
+        for (int l = (LAT ? lw : 0); l < (LAT ? (helper ? lw : lw + 1) : (PLAIN ? DK : DK - 1)); l++) {
             u32 v[32];
             const u32 sh = gBits * l;
 #pragma unroll
@@ -192,6 +202,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
             }
             fwd_passA(v, A, Q, Q2);
+            if (SWEEP)
+                sweep_below_2q(v, Q2);
             u32* reg = myD + (size_t)(j + 2 * l) * RS;
 #pragma unroll
             for (int r = 0; r < 32; r++)
@@ -299,14 +311,47 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     }
 }
 
+// Shapes instantiated below: N = 1024 with four digits and top-digit elimination (STD128 / STD128_OPT with the DM
+// accumulator: the headline AP shape, with latency layouts), three digits plain (the named STD128_AP sets), three digits
+// with elimination + sweep (MEDIUM), four digits plain + sweep (SIGNED_MOD_TEST); N = 512 with three digits plain (TOY).
 bool dm32_supported(const tfhe_b200_params& p) {
-    if (p.method != TFHE_B200_METHOD_AP || p.N != 1024 || p.digitsG != 4 || p.numDigitsToThrow != 0)
+    if (p.method != TFHE_B200_METHOD_AP || p.numDigitsToThrow != 0)
         return false;
-    if (p.Q >= (1ULL << 32) / 22)
+    if (p.Q >= (1ULL << 28))
         return false;
     if ((u64)p.n * p.digitsR > 8192)
         return false;
-    return cggi32_skip_top_ok(p);
+    u32 gbits = 0;
+    while ((1ULL << gbits) < p.baseG)
+        gbits++;
+    if ((1ULL << gbits) != p.baseG || gbits * p.digitsG > 32)
+        return false;
+    const bool skip = cggi32_skip_top_ok(p), sweep = cggi32_needs_sweep(p.Q);
+    if (p.N == 1024 && p.digitsG == 4 && skip && !sweep)
+        return true;
+    if (p.N == 1024 && p.digitsG == 3 && !skip && !sweep)
+        return true;
+    if (p.N == 1024 && p.digitsG == 3 && skip && sweep)
+        return true;
+    if (p.N == 1024 && p.digitsG == 4 && !skip && sweep)
+        return true;
+    if (p.N == 512 && p.digitsG == 3 && !skip && !sweep)
+        return true;
+    return false;
+}
+
+template <int LOGN, int DK, int G, bool PLAIN, bool SWEEP>
+static cudaError_t launch_dm_t(const DM32Args& a, cudaStream_t s) {
+    using K = KCfg<LOGN, DK, G>;
+    const size_t smem = (size_t)G * K::D * K::RS * 4 + (size_t)G * a.c.n * a.c.digitsR * 4 + 64;
+    if (smem > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(br_dm32_kernel<LOGN, DK, G, false, PLAIN, SWEEP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    br_dm32_kernel<LOGN, DK, G, false, PLAIN, SWEEP><<<(a.c.batch + G - 1) / G, K::NT, smem, s>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group) {
@@ -328,6 +373,21 @@ cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_
     a.dig_add = t.mod.Q - B / 2;
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
+    {
+        const bool sweep = cggi32_needs_sweep(t.mod.Q), plain = !t.skip_top;
+        const int dk = (int)c.digitsKept;
+        if (c.logN == 9 && dk == 3 && plain && !sweep)
+            return launch_dm_t<9, 3, 8, true, false>(a, s);
+        if (c.logN == 10 && dk == 3 && plain && !sweep)
+            return (sm_count > 0 && c.batch <= 2 * sm_count) ? launch_dm_t<10, 3, 2, true, false>(a, s)
+                                                             : launch_dm_t<10, 3, 4, true, false>(a, s);
+        if (c.logN == 10 && dk == 3 && !plain && sweep)
+            return launch_dm_t<10, 3, 4, false, true>(a, s);
+        if (c.logN == 10 && dk == 4 && plain && sweep)
+            return launch_dm_t<10, 4, 4, true, true>(a, s);
+        if (!(c.logN == 10 && dk == 4 && !plain && !sweep))
+            return cudaErrorInvalidConfiguration;
+    }
     constexpr int G = 4;   // 5 ciphertexts per CTA (168 registers, small spills) measured 43.7 k gates/s against 52.8 k
     using K = KCfg<10, 4, G>;
     const size_t smem = (size_t)G * K::D * K::RS * 4 + (size_t)G * c.n * c.digitsR * 4 + 64;

@@ -597,7 +597,7 @@ __global__ void bk_relayout_cggi64_kernel(u64* dst, const u64* src, u32 n, u32 d
 // [row][x(d/2)][slot][4] with word w = l'*2 + j.  The DM accumulator drops row l' = 0 (rgsw-acc-dm.cpp:353,357) and the
 // kernel eliminates the top digit, so:  l < top: BK' = [l' >= 1] BK_l' - B^(l-top) BK_top(jin);  l = top: N B^-top BK_top.
 __global__ void bk_relayout_dm32_kernel(u32* dst, const u32* src, size_t rows, u32 d, u32 N, ModCtx<u32> M,
-                                        const u32* cM) {
+                                        const u32* cM, int skip) {
     const size_t per_row = (size_t)d * 2 * N;
     const size_t total = rows * per_row;
     const u32 top = d / 2 - 1;
@@ -612,6 +612,10 @@ __global__ void bk_relayout_dm32_kernel(u32* dst, const u32* src, size_t rows, u
         u32 j = w % 2, lp = w / 2;
         const u32 jin = lp & 1, l = lp >> 1;
         const size_t base = row * per_row;
+        if (!skip) {   // plain path: the key's own rows, row l' = 0 never enters the sum (rgsw-acc-dm.cpp:353,357)
+            dst[idx] = lp >= 1 ? src[base + ((size_t)lp * 2 + j) * N + k] : 0;
+            continue;
+        }
         const u32 vt = src[base + ((size_t)(jin + 2 * top) * 2 + j) * N + k];
         const u32 t = M.mont_mul(vt, cM[l]);
         u32 val;
@@ -643,7 +647,7 @@ extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
     if (h->have_cggi32 && !h->force_generic)
         return h->skip_top ? "cggi_u32_ntt32_skiptop" : "cggi_u32_ntt32";
     if (h->have_dm32 && !h->force_generic)
-        return "dm_u32_ntt32_skiptop";
+        return h->skip_top ? "dm_u32_ntt32_skiptop" : "dm_u32_ntt32";
     if (h->have_cggi64 && !h->force_generic)
         return h->have_cggi64w ? (h->skip_top ? "cggi_u64_ntt16x128_skiptop" : "cggi_u64_ntt16x128")
                                : (h->skip_top ? "cggi_u64_ntt32x64_skiptop" : "cggi_u64_ntt32x64");
@@ -780,7 +784,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
     // TFHE_B200_NO_SKIPTOP=1 (debug) keeps the untransformed keys and the full set of forward transforms
     h->have_cggi64 = h->is64 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64");
     h->have_dm32 = !h->is64 && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
-    h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) ||
+    h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) || (h->have_dm32 && cggi32_skip_top_ok(p)) ||
                    (h->have_cggi64 && (cggi32_skip_top_ok(p) || cggi_skip_top_wrapfix_ok(p)))) &&
                   !getenv("TFHE_B200_NO_SKIPTOP");
     h->have_cggi64w = h->have_cggi64 && (h->skip_top ? cggi64w_supported(p) : cggi64w_plain_supported(p)) &&
@@ -896,7 +900,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
                 CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi32, h->bk_words * 4));
                 bk_relayout_dm32_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi32, (const u32*)d0.bk_generic,
                                                                         (size_t)p.n * p.baseR * p.digitsR, h->d, p.N,
-                                                                        h->m32, (const u32*)dcM);
+                                                                        h->m32, (const u32*)dcM, h->skip_top ? 1 : 0);
                 CUDA_TRY(cudaGetLastError());
             }
             CUDA_TRY(cudaStreamSynchronize(d0.stream));
@@ -1111,7 +1115,7 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
     else if (h->have_dm32 && !h->force_generic) {
         CGGI32Tables t;
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB;
-        t.skip_top = true;
+        t.skip_top = h->skip_top;
         CUDA_TRY(launch_br_dm32(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_cggi64w && !h->force_generic && !getenv("TFHE_B200_C64_NARROW")) {
@@ -1157,7 +1161,7 @@ static int throughput_group(const tfhe_b200_handle* h) {
     if (h->have_cggi32)
         return h->logN == 10 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4);
     if (h->have_dm32)
-        return 4;
+        return h->logN == 9 ? 8 : 4;
     if (h->have_cggi64)
         return dk <= 3 ? 2 : 1;
     return 1;
@@ -1175,8 +1179,10 @@ static void tail_shapes(const tfhe_b200_handle* h, int* per_cta, int* tail_per_s
         }
     }
     else if (h->have_dm32) {
-        *per_cta = 4;
-        *tail_per_sm = 2;
+        if (h->logN == 10 && dk == 4 && h->skip_top && !cggi32_needs_sweep(h->p.Q)) {   // the shape with latency layouts
+            *per_cta = 4;
+            *tail_per_sm = 2;
+        }
     }
     else if (h->have_cggi64w && dk <= 3 && !getenv("TFHE_B200_C64_NARROW")) {
         *per_cta = 2;                      // CTAs of 2 (16 warps); one ciphertext per CTA (<= 1 per SM)
