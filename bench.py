@@ -78,6 +78,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference's own GPU path (comparison build)")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-buffer e2e leg")
+    ap.add_argument("--no-imad-peak", action="store_true",
+                    help="use the recorded IMAD peak instead of running the microbenchmark (profiler runs)")
     return ap.parse_args()
 
 
@@ -546,7 +548,8 @@ def main():
         value = total_units / dt
         e2e_value = total_units / dt_e2e
         peaks, peaks_src = measured_peaks()
-        imad_peak, imad_src = imad_peak_live()
+        imad_peak, imad_src = ((IMAD_PEAK_FALLBACK, "recorded (profiles/r02_imad_peak.json)") if args.no_imad_peak
+                               else imad_peak_live())
         traffic = ncu_traffic()
         h2d, d2h = wl.io_bytes(count)
         line = {
