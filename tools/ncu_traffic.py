@@ -15,12 +15,20 @@ UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 KEYS = {"br_cggi32_kernel": "br_cggi32_kernel", "br_dm32_kernel": "br_dm32_kernel", "br_cggi64w_kernel": "br_cggi64w_kernel",
         "br_cggi64_kernel": "br_cggi64_kernel", "br_generic_kernel": "br_generic_kernel", "mkmswitch": "mkmswitch"}
 SHOW = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
-        "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_issued.avg.pct_of_peak_sustained_active",
-        "smsp__inst_executed.avg.per_cycle_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.avg.per_cycle_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg"]
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
 def main():
@@ -58,7 +66,7 @@ def main():
                 print(f"| {m} | {r[col[m]]} | {units[col[m]]} |")
         print()
         for frag, key in KEYS.items():
-            if frag in kname and rd is not None and wr is not None:
+            if frag in kname and rd is not None and wr is not None and rd == rd and wr == wr:   # NaN: incomplete capture
                 traffic[key] = {"bytes": rd + wr, "batch": batch, "kernel": kname[:120], "source": note}
                 break
     json.dump(traffic, open(out_json, "w"), indent=1)
