@@ -191,34 +191,14 @@ static cudaError_t launch_ks_t(const KSArgs& a, cudaStream_t s) {
 // into each other) and only the 4-row partial sums are unpacked into 32-bit column accumulators: 0.75 instructions
 // per table entry instead of ~3.  Row offsets (not digits) are precomputed in shared memory.
 // ---------------------------------------------------------------------------------------------------------
+// Gather-accumulate shared by the plain and the split packed kernels: rows r_lo + rg, r_lo + rg + RG, ... < rows of the
+// ciphertext's row list, four gathered rows in flight per trip, packed u16 pair sums unpacked into 32-bit column
+// accumulators, combined in `colsum` (shared memory).  Force-inlined: the plain kernel passes r_lo = 0 and compiles to
+// the same SASS as when this body was written out in it (checked with cuobjdump; its load scheduling is what makes it
+// fast).
 template <int S>
-__global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int TC, int RG) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 N = A.N, n = A.n, dKS = A.dKS;
-    const u32 rows = N * dKS;
-    u32* colsum = reinterpret_cast<u32*>(smem_raw);           // [row_stride]
-    u32* rowoff = colsum + A.row_stride;                      // [rows] table row index of every gathered row
-    __shared__ u64 b_ms;
-
-    const int ct = blockIdx.x;
-    const u64* ext = A.ext + (size_t)ct * (N + 1);
-    const double dQ = (double)A.Q, dqKS = (double)A.qKS;
-    for (u32 i = threadIdx.x; i <= N; i += blockDim.x) {
-        u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
-        if (i == N)
-            b_ms = v;
-        else {
-            for (u32 j = 0; j < dKS; j++) {
-                u32 a0 = (u32)(v % A.baseKS);
-                v /= A.baseKS;
-                rowoff[i * dKS + j] = (i * A.baseKS + a0) * dKS + j;
-            }
-        }
-    }
-    for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
-        colsum[k] = 0;
-    __syncthreads();
-
+__device__ __forceinline__ void ks16_gather(const KSArgs& A, int TC, int RG, const u32* rowoff, u32* colsum, u32 r_lo,
+                                            u32 rows) {
     const int tc = threadIdx.x % TC, rg = threadIdx.x / TC;
     const u32 CV = A.row_stride / 8;
     const uint4* tab = reinterpret_cast<const uint4*>(A.ksk);
@@ -229,107 +209,6 @@ __global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int T
 #pragma unroll
             for (int v = 0; v < 4; v++)
                 lo[s][v] = hi[s][v] = 0;
-        // rows rg, rg + RG, ... in groups of four
-        u32 r = rg;
-        for (; r + 3 * RG < rows; r += 4 * RG) {
-            const u32 o0 = rowoff[r], o1 = rowoff[r + RG], o2 = rowoff[r + 2 * RG], o3 = rowoff[r + 3 * RG];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const u32 cv = tc + s * TC;
-                if (cv < CV) {
-                    const uint4 a = __ldg(tab + (size_t)o0 * CV + cv), b = __ldg(tab + (size_t)o1 * CV + cv);
-                    const uint4 c = __ldg(tab + (size_t)o2 * CV + cv), d = __ldg(tab + (size_t)o3 * CV + cv);
-                    const u32 p[4] = {a.x + b.x + c.x + d.x, a.y + b.y + c.y + d.y, a.z + b.z + c.z + d.z,
-                                      a.w + b.w + c.w + d.w};
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        lo[s][v] += p[v] & 0xffffu;
-                        hi[s][v] += p[v] >> 16;
-                    }
-                }
-            }
-        }
-        for (; r < rows; r += RG) {
-            const u32 o0 = rowoff[r];
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                const u32 cv = tc + s * TC;
-                if (cv < CV) {
-                    const uint4 a = __ldg(tab + (size_t)o0 * CV + cv);
-                    const u32 p[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        lo[s][v] += p[v] & 0xffffu;
-                        hi[s][v] += p[v] >> 16;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            const u32 cv = tc + s * TC;
-            if (cv < CV) {
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    atomicAdd(&colsum[cv * 8 + 2 * v], lo[s][v]);
-                    atomicAdd(&colsum[cv * 8 + 2 * v + 1], hi[s][v]);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    u64* out = A.out + (size_t)ct * (n + 1);
-    const double dfmod = (double)A.fmod;
-    for (u32 k = threadIdx.x; k <= n; k += blockDim.x) {
-        u64 sum = (u64)colsum[k] % A.qKS;
-        u64 base = (k == n) ? b_ms : 0;
-        u64 v = base >= sum ? base - sum : base + A.qKS - sum;
-        out[k] = round_qQ(v, A.fmod, dfmod, dqKS);
-    }
-}
-
-// Split variant (small batches): gridDim.y CTAs share the rows of a ciphertext; kept as a separate kernel because the
-// plain kernel's load scheduling (four gathered rows in flight before the first add) is sensitive to any change of its
-// source: the templated merge of the two measured 3.09 ms instead of 2.22 ms per 16384 ciphertexts.
-template <int S>
-__global__ void __launch_bounds__(288) mkmswitch_packed16_split_kernel(KSArgs A, int TC, int RG) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 N = A.N, n = A.n, dKS = A.dKS;
-    u32* colsum = reinterpret_cast<u32*>(smem_raw);           // [row_stride]
-    u32* rowoff = colsum + A.row_stride;                      // [rows] table row index of every gathered row
-    __shared__ u64 b_ms;
-
-    const int ct = blockIdx.x;
-    const u64* ext = A.ext + (size_t)ct * (N + 1);
-    const double dQ = (double)A.Q, dqKS = (double)A.qKS;
-    const u32 ipc = (N + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * ipc;
-    const u32 i_hi = min(N, i_lo + ipc);
-    const u32 r_lo = i_lo * dKS, rows = i_hi * dKS;
-    for (u32 i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
-        u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
-        for (u32 j = 0; j < dKS; j++) {
-            u32 a0 = (u32)(v % A.baseKS);
-            v /= A.baseKS;
-            rowoff[i * dKS + j] = (i * A.baseKS + a0) * dKS + j;
-        }
-    }
-    if (threadIdx.x == blockDim.x - 1)   // a thread with the fewest loop trips
-        b_ms = round_qQ(ext[N], A.qKS, dqKS, dQ);
-    for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
-        colsum[k] = 0;
-    __syncthreads();
-
-    const int tc = threadIdx.x % TC, rg = threadIdx.x / TC;
-    const u32 CV = A.row_stride / 8;
-    const uint4* tab = reinterpret_cast<const uint4*>(A.ksk);
-    if (rg < RG) {
-        u32 lo[S][4], hi[S][4];
-#pragma unroll
-        for (int s = 0; s < S; s++)
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-                lo[s][v] = hi[s][v] = 0;
-        // rows r_lo + rg, r_lo + rg + RG, ... in groups of four
         u32 r = r_lo + rg;
         for (; r + 3 * RG < rows; r += 4 * RG) {
             const u32 o0 = rowoff[r], o1 = rowoff[r + RG], o2 = rowoff[r + 2 * RG], o3 = rowoff[r + 3 * RG];
@@ -377,6 +256,81 @@ __global__ void __launch_bounds__(288) mkmswitch_packed16_split_kernel(KSArgs A,
             }
         }
     }
+}
+
+template <int S>
+__global__ void __launch_bounds__(288) mkmswitch_packed16_kernel(KSArgs A, int TC, int RG) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 N = A.N, n = A.n, dKS = A.dKS;
+    const u32 rows = N * dKS;
+    u32* colsum = reinterpret_cast<u32*>(smem_raw);           // [row_stride]
+    u32* rowoff = colsum + A.row_stride;                      // [rows] table row index of every gathered row
+    __shared__ u64 b_ms;
+
+    const int ct = blockIdx.x;
+    const u64* ext = A.ext + (size_t)ct * (N + 1);
+    const double dQ = (double)A.Q, dqKS = (double)A.qKS;
+    for (u32 i = threadIdx.x; i <= N; i += blockDim.x) {
+        u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
+        if (i == N)
+            b_ms = v;
+        else {
+            for (u32 j = 0; j < dKS; j++) {
+                u32 a0 = (u32)(v % A.baseKS);
+                v /= A.baseKS;
+                rowoff[i * dKS + j] = (i * A.baseKS + a0) * dKS + j;
+            }
+        }
+    }
+    for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
+        colsum[k] = 0;
+    __syncthreads();
+
+    ks16_gather<S>(A, TC, RG, rowoff, colsum, 0, rows);
+    __syncthreads();
+    u64* out = A.out + (size_t)ct * (n + 1);
+    const double dfmod = (double)A.fmod;
+    for (u32 k = threadIdx.x; k <= n; k += blockDim.x) {
+        u64 sum = (u64)colsum[k] % A.qKS;
+        u64 base = (k == n) ? b_ms : 0;
+        u64 v = base >= sum ? base - sum : base + A.qKS - sum;
+        out[k] = round_qQ(v, A.fmod, dfmod, dqKS);
+    }
+}
+
+// Split variant (small batches): gridDim.y CTAs share the rows of a ciphertext.  A separate __global__ function around
+// the shared gather body: merging the two kernels behind one template flag changed the plain kernel's load scheduling
+// (3.09 ms instead of 2.22 ms per 16384 ciphertexts); with the body force-inlined into two kernels the plain one keeps
+// its SASS.
+template <int S>
+__global__ void __launch_bounds__(288) mkmswitch_packed16_split_kernel(KSArgs A, int TC, int RG) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 N = A.N, n = A.n, dKS = A.dKS;
+    u32* colsum = reinterpret_cast<u32*>(smem_raw);           // [row_stride]
+    u32* rowoff = colsum + A.row_stride;                      // [rows] table row index of every gathered row
+    __shared__ u64 b_ms;
+
+    const int ct = blockIdx.x;
+    const u64* ext = A.ext + (size_t)ct * (N + 1);
+    const double dQ = (double)A.Q, dqKS = (double)A.qKS;
+    const u32 ipc = (N + gridDim.y - 1) / gridDim.y, i_lo = blockIdx.y * ipc;
+    const u32 i_hi = min(N, i_lo + ipc);
+    const u32 r_lo = i_lo * dKS, rows = i_hi * dKS;
+    for (u32 i = i_lo + threadIdx.x; i < i_hi; i += blockDim.x) {
+        u64 v = round_qQ(ext[i], A.qKS, dqKS, dQ);
+        for (u32 j = 0; j < dKS; j++) {
+            u32 a0 = (u32)(v % A.baseKS);
+            v /= A.baseKS;
+            rowoff[i * dKS + j] = (i * A.baseKS + a0) * dKS + j;
+        }
+    }
+    if (threadIdx.x == blockDim.x - 1)   // a thread with the fewest loop trips
+        b_ms = round_qQ(ext[N], A.qKS, dqKS, dQ);
+    for (u32 k = threadIdx.x; k < A.row_stride; k += blockDim.x)
+        colsum[k] = 0;
+    __syncthreads();
+
+    ks16_gather<S>(A, TC, RG, rowoff, colsum, r_lo, rows);
     __syncthreads();
     {
         unsigned long long* part = reinterpret_cast<unsigned long long*>(A.partial) + (size_t)ct * A.row_stride;
