@@ -148,6 +148,50 @@ def test_cggi32_28bit_modulus_sweep(baseG, rng):
         g.GPUClean()
 
 
+Q37 = 137438822401  # STD192 (37-bit, 1 mod 4096)
+
+
+@pytest.mark.parametrize("Q,q,baseG,baseR", [(Q37, 1024, 1 << 14, 32),     # STD192 shape: three digits, two per CTA
+                                             (Q29, 2048, 1 << 8, 46),      # STD256 shape: four digits, 29-bit modulus
+                                             (Q54, 1024, 1 << 18, 32)])    # 54-bit modulus, three digits
+def test_dm64w_kernel(Q, q, baseG, baseR, rng):
+    """AP/DM on the N = 2048 rings (br_dm64w.cu): gates, explicit accumulators with extreme coefficients, zero refresh
+    digits, both CTA shapes, against the oracle and the generic kernel."""
+    p = po.Port.params_custom(5, 2048, q, Q, 64, baseG, baseR, po.AP)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant == "dm_u64_ntt16x128_skiptop"
+        n = p.n
+        c1 = rng.integers(0, q, (9, n + 1), dtype=np.uint64)                   # ragged vs CTAs of 2
+        c2 = rng.integers(0, q, (9, n + 1), dtype=np.uint64)
+        c1[1, :n] = 0
+        c2[1, :n] = 0                                                          # every refresh digit zero
+        c1[2, :n] = baseR
+        c2[2, :n] = 0                                                          # low digit zero, high digit non-zero
+        for gate in ("NAND", "XOR_FAST"):
+            want = port.eval_bin_gate(bk, ksk, po.GATES[gate], c1, c2, q)
+            assert np.array_equal(g.EvalBinGate(gate, c1, c2), want), gate
+        Qm, QH = p.Q, p.Q >> 1
+        acc = rng.integers(0, Qm, (5, 2, 2048), dtype=np.uint64)
+        acc[0] = np.resize(np.array([0, 1, Qm - 1, QH - 1, QH, QH + 1, QH - 64, QH + 64], dtype=np.uint64), (2, 2048))
+        acc[1] = Qm - 1
+        am = rng.integers(0, q, (5, n), dtype=np.uint64)
+        want = port.eval_acc(bk, am, q, acc)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+        g.set_option("group", 1)                                               # one ciphertext per CTA
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+        g.set_option("group", 0)
+        big = 2 * 148 + 148 - 9                                                # throughput part + latency-shaped tail
+        b1 = rng.integers(0, q, (big, n + 1), dtype=np.uint64)
+        b2 = rng.integers(0, q, (big, n + 1), dtype=np.uint64)
+        assert np.array_equal(g.EvalBinGate("OR", b1, b2), port.eval_bin_gate(bk, ksk, po.GATES["OR"], b1, b2, q))
+        g.set_option("force_generic", 1)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+    finally:
+        g.GPUClean()
+
+
 def test_small_modulus_on_the_64bit_kernel(rng):
     """N = 2048 rings with a modulus below 2^31 (the STD256 family) have no 32-bit kernel shape: they run on the 64-bit
     kernels in 64-bit words."""

@@ -177,6 +177,7 @@ struct tfhe_b200_handle {
     bool have_cggi32 = false;
     bool skip_top = false;
     bool have_dm32 = false;
+    bool have_dm64w = false;     // AP/DM on the N = 2048 rings (br_dm64w.cu), 64-bit words
     bool have_cggi64 = false;
     bool have_cggi64w = false;   // wide variant usable (skip-top path of a supported ring)
     std::vector<u64> twA64_host;
@@ -629,6 +630,34 @@ __global__ void bk_relayout_dm32_kernel(u32* dst, const u32* src, size_t rows, u
     }
 }
 
+// 64-bit AP/DM layout (br_dm64w.cu): source [row][l'(d)][j(2)][N], destination [row][x(d)][slot][2] with plane x = l' and
+// word c = j, packed as 27-bit limb pairs; top-digit elimination as in bk_relayout_dm32_kernel.
+__global__ void bk_relayout_dm64_kernel(u64* dst, const u64* src, size_t rows, u32 d, u32 N, ModCtx<u64> M,
+                                        const u64* cM) {
+    const size_t per_row = (size_t)d * 2 * N;
+    const size_t total = rows * per_row;
+    const u32 top = d / 2 - 1;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        size_t r = idx;
+        const u32 j = r % 2; r /= 2;
+        const u32 k = r % N; r /= N;
+        const u32 lp = r % d; r /= d;
+        const size_t base = r * per_row;
+        const u32 jin = lp & 1, l = lp >> 1;
+        const u64 vt = src[base + ((size_t)(jin + 2 * top) * 2 + j) * N + k];
+        const u64 t = M.mont_mul(vt, cM[l]);
+        u64 val;
+        if (l == top)
+            val = t;
+        else {
+            const u64 own = lp >= 1 ? src[base + ((size_t)lp * 2 + j) * N + k] : 0;
+            val = M.sub(own, t);
+        }
+        dst[idx] = (val & ((1ULL << 27) - 1)) | ((val >> 27) << 32);
+    }
+}
+
 extern "C" size_t tfhe_b200_bk_words(const tfhe_b200_params* p) {
     return p ? bk_words_of(p) : 0;
 }
@@ -648,6 +677,8 @@ extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
         return h->skip_top ? "cggi_u32_ntt32_skiptop" : "cggi_u32_ntt32";
     if (h->have_dm32 && !h->force_generic)
         return h->skip_top ? "dm_u32_ntt32_skiptop" : "dm_u32_ntt32";
+    if (h->have_dm64w && !h->force_generic)
+        return "dm_u64_ntt16x128_skiptop";
     if (h->have_cggi64 && !h->force_generic)
         return h->have_cggi64w ? (h->skip_top ? "cggi_u64_ntt16x128_skiptop" : "cggi_u64_ntt16x128")
                                : (h->skip_top ? "cggi_u64_ntt32x64_skiptop" : "cggi_u64_ntt32x64");
@@ -764,7 +795,8 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
     auto* h = new tfhe_b200_handle();
     h->p = p;
     // 64-bit words for Q >= 2^31 -- and for the small-modulus N = 2048 rings, whose only specialised kernel is the 64-bit one
-    h->is64 = p.Q >= (1ULL << 31) || (cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64"));
+    h->is64 = p.Q >= (1ULL << 31) || (cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64")) ||
+              (dm64w_supported(p) && !getenv("TFHE_B200_NO_DM64"));
     while ((1u << h->logN) < p.N)
         h->logN++;
     h->d = (p.method == TFHE_B200_METHOD_GINX) ? 2 * (p.digitsG - p.numDigitsToThrow) : 2 * p.digitsG;
@@ -784,7 +816,8 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
     // TFHE_B200_NO_SKIPTOP=1 (debug) keeps the untransformed keys and the full set of forward transforms
     h->have_cggi64 = h->is64 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64");
     h->have_dm32 = !h->is64 && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
-    h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) || (h->have_dm32 && cggi32_skip_top_ok(p)) ||
+    h->have_dm64w = h->is64 && dm64w_supported(p) && !getenv("TFHE_B200_NO_DM64");
+    h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) || (h->have_dm32 && cggi32_skip_top_ok(p)) || h->have_dm64w ||
                    (h->have_cggi64 && (cggi32_skip_top_ok(p) || cggi_skip_top_wrapfix_ok(p)))) &&
                   !getenv("TFHE_B200_NO_SKIPTOP");
     h->have_cggi64w = h->have_cggi64 && (h->skip_top ? cggi64w_supported(p) : cggi64w_plain_supported(p)) &&
@@ -833,7 +866,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
                 CUDA_TRY(cudaMalloc((void**)&d.twU64, h->twA64_host.size() * 8));
                 CUDA_TRY(cudaMemcpy(d.twU64, h->twA64_host.data(), h->twA64_host.size() * 8, cudaMemcpyHostToDevice));
             }
-            if (h->have_cggi64w) {
+            if (h->have_cggi64w || h->have_dm64w) {
                 std::vector<u64> tU, tB, tC;
                 cggi64w_build_tables(p, tU, tB, tC);
                 CUDA_TRY(cudaMalloc((void**)&d.twUw, tU.size() * 8));
@@ -877,7 +910,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
                 return 0;
             };
             void* dcM = nullptr;
-            if (h->have_cggi32 || h->have_cggi64 || h->have_dm32) {
+            if (h->have_cggi32 || h->have_cggi64 || h->have_dm32 || h->have_dm64w) {
                 r = upload_cM(&dcM);
                 if (r)
                     return r;
@@ -903,13 +936,20 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
                                                                         h->m32, (const u32*)dcM, h->skip_top ? 1 : 0);
                 CUDA_TRY(cudaGetLastError());
             }
+            if (h->have_dm64w) {
+                CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi64, h->bk_words * 8));
+                bk_relayout_dm64_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi64, (const u64*)d0.bk_generic,
+                                                                        (size_t)p.n * p.baseR * p.digitsR, h->d, p.N,
+                                                                        h->m64, (const u64*)dcM);
+                CUDA_TRY(cudaGetLastError());
+            }
             CUDA_TRY(cudaStreamSynchronize(d0.stream));
             if (dcM)
                 CUDA_TRY(cudaFree(dcM));
             // The generic layout is only the source of the specialised ones: release it once they exist, unless the
             // caller asked to keep the cross-check kernel available (params.flags bit 0 or TFHE_B200_KEEP_GENERIC=1;
             // set_option("force_generic") needs it).  STD128-AP: 2.1 GB, logQ = 17: 513 MB saved per GPU.
-            if (!h->keep_generic && (h->have_cggi32 || h->have_cggi64 || h->have_dm32)) {
+            if (!h->keep_generic && (h->have_cggi32 || h->have_cggi64 || h->have_dm32 || h->have_dm64w)) {
                 CUDA_TRY(cudaFree(d0.bk_generic));
                 d0.bk_generic = nullptr;
             }
@@ -934,7 +974,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
                     CUDA_TRY(cudaMalloc((void**)&d.bk_cggi32, h->bk_words * 4));
                     CUDA_TRY(cudaMemcpyPeerAsync(d.bk_cggi32, d.id, d0.bk_cggi32, d0.id, h->bk_words * 4, d.stream));
                 }
-                if (h->have_cggi64) {
+                if (h->have_cggi64 || h->have_dm64w) {
                     CUDA_TRY(cudaMalloc((void**)&d.bk_cggi64, h->bk_words * 8));
                     CUDA_TRY(cudaMemcpyPeerAsync(d.bk_cggi64, d.id, d0.bk_cggi64, d0.id, h->bk_words * 8, d.stream));
                 }
@@ -1118,6 +1158,11 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
         t.skip_top = h->skip_top;
         CUDA_TRY(launch_br_dm32(c, t, d.stream, d.sm_count, h->group));
     }
+    else if (h->have_dm64w && !h->force_generic) {
+        CGGI64WTables t;
+        t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twC = d.twCw; t.twB = d.twBw; t.twU = d.twUw;
+        CUDA_TRY(launch_br_dm64w(c, t, d.stream, d.sm_count, h->group));
+    }
     else if (h->have_cggi64w && !h->force_generic && !getenv("TFHE_B200_C64_NARROW")) {
         CGGI64WTables t;
         t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twC = d.twCw; t.twB = d.twBw; t.twU = d.twUw;
@@ -1162,6 +1207,8 @@ static int throughput_group(const tfhe_b200_handle* h) {
         return h->logN == 10 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4);
     if (h->have_dm32)
         return h->logN == 9 ? 8 : 4;
+    if (h->have_dm64w)
+        return dk <= 3 ? 2 : 1;
     if (h->have_cggi64)
         return dk <= 3 ? 2 : 1;
     return 1;
@@ -1184,7 +1231,7 @@ static void tail_shapes(const tfhe_b200_handle* h, int* per_cta, int* tail_per_s
             *tail_per_sm = 2;
         }
     }
-    else if (h->have_cggi64w && dk <= 3 && !getenv("TFHE_B200_C64_NARROW")) {
+    else if ((h->have_dm64w || (h->have_cggi64w && !getenv("TFHE_B200_C64_NARROW"))) && dk <= 3) {
         *per_cta = 2;                      // CTAs of 2 (16 warps); one ciphertext per CTA (<= 1 per SM)
         *tail_per_sm = 1;
     }

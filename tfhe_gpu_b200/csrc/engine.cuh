@@ -126,6 +126,10 @@ struct SerializedSwitchKey {
 int index_serialized_acc_key(const void* data, size_t bytes, SerializedAccKey* out, std::string* err);
 int index_serialized_switch_key(const void* data, size_t bytes, SerializedSwitchKey* out, std::string* err);
 
+// AP/DM on the N = 2048 rings (br_dm64w.cu): same tables as the wide CGGI kernel, key from bk_relayout_dm64_kernel
+bool dm64w_supported(const tfhe_b200_params& p);
+cudaError_t launch_br_dm64w(const BRCommon& c, const CGGI64WTables& t, cudaStream_t s, int sm_count = 0, int group = 0);
+
 // GPU key generation (keygen.cu)
 int keygen_device(const tfhe_b200_params& p, const signed char* sk_lwe, const signed char* sk_ring,
                   const unsigned char key[32], int device, u64* bk_dev, u64* ksk_dev);
