@@ -149,12 +149,12 @@ def test_cggi32_28bit_modulus_sweep(baseG, rng):
 
 
 Q37 = 137438822401  # STD192 (37-bit, 1 mod 4096)
-Q54b = 18014398509404161   # the 54-bit prime of the functional sets (same value as Q54 below)
+Q35 = 34359709697   # STD192Q (35-bit)
 
 
 @pytest.mark.parametrize("Q,q,baseG,baseR", [(Q37, 1024, 1 << 14, 32),     # STD192 shape: three digits, two per CTA
                                              (Q29, 2048, 1 << 8, 46),      # STD256 shape: four digits, 29-bit modulus
-                                             (Q54b, 1024, 1 << 18, 32)])   # 54-bit modulus, three digits
+                                             (Q35, 1024, 1 << 12, 32)])    # STD192Q_OPT shape
 def test_dm64w_kernel(Q, q, baseG, baseR, rng):
     """AP/DM on the N = 2048 rings (br_dm64w.cu): gates, explicit accumulators with extreme coefficients, zero refresh
     digits, both CTA shapes, against the oracle and the generic kernel."""
