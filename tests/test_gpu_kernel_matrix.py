@@ -152,9 +152,13 @@ Q37 = 137438822401  # STD192 (37-bit, 1 mod 4096)
 Q35 = 34359709697   # STD192Q (35-bit)
 
 
+Q50 = 1125899906826241   # STD128Q (50-bit)
+
+
 @pytest.mark.parametrize("Q,q,baseG,baseR", [(Q37, 1024, 1 << 14, 32),     # STD192 shape: three digits, two per CTA
                                              (Q29, 2048, 1 << 8, 46),      # STD256 shape: four digits, 29-bit modulus
-                                             (Q35, 1024, 1 << 12, 32)])    # STD192Q_OPT shape
+                                             (Q35, 1024, 1 << 12, 32),     # STD192Q_OPT shape
+                                             (Q50, 1024, 1 << 25, 32)])    # STD128Q shape: two digits, plain path
 def test_dm64w_kernel(Q, q, baseG, baseR, rng):
     """AP/DM on the N = 2048 rings (br_dm64w.cu): gates, explicit accumulators with extreme coefficients, zero refresh
     digits, both CTA shapes, against the oracle and the generic kernel."""
@@ -162,7 +166,7 @@ def test_dm64w_kernel(Q, q, baseG, baseR, rng):
     port = po.Port(p)
     sk, bk, ksk, g = _ctx(p, port)
     try:
-        assert g.kernel_variant == "dm_u64_ntt16x128_skiptop"
+        assert g.kernel_variant.startswith("dm_u64_ntt16x128")
         n = p.n
         c1 = rng.integers(0, q, (9, n + 1), dtype=np.uint64)                   # ragged vs CTAs of 2
         c2 = rng.integers(0, q, (9, n + 1), dtype=np.uint64)
@@ -177,6 +181,7 @@ def test_dm64w_kernel(Q, q, baseG, baseR, rng):
         acc = rng.integers(0, Qm, (5, 2, 2048), dtype=np.uint64)
         acc[0] = np.resize(np.array([0, 1, Qm - 1, QH - 1, QH, QH + 1, QH - 64, QH + 64], dtype=np.uint64), (2, 2048))
         acc[1] = Qm - 1
+        acc[2] = rng.integers(QH - 2000, QH, (2, 2048), dtype=np.uint64)       # where a wrapping top digit lives
         am = rng.integers(0, q, (5, n), dtype=np.uint64)
         want = port.eval_acc(bk, am, q, acc)
         assert np.array_equal(g.EvalAcc(am, q, acc), want)

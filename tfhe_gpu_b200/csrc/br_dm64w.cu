@@ -1,8 +1,9 @@
 // AP/DM blind rotation for the N = 2048 rings (any modulus below 2^54, in 64-bit words): the DM accumulator
 // (rgsw-acc-dm.cpp:80-110, 306-359) on the "wide" register-resident transform of br_cggi64w.cu (ntt64w.cuh: 128 threads x
-// 16 coefficients per polynomial, 16 warps per SM with two ciphertexts per CTA).  Covers the N = 2048 sets of the
-// reference's paramsMap under method AP whose top signed digit is exact (cggi32_skip_top_ok): STD192 / STD192_OPT /
-// STD192Q / STD192Q_OPT (three digits) and STD256 / STD256_OPT / STD256Q / STD256Q_OPT (four digits).
+// 16 coefficients per polynomial, 16 warps per SM with two ciphertexts per CTA).  Covers every N = 2048 set of the
+// reference's paramsMap under method AP: STD192 / STD192_OPT / STD192Q / STD192Q_OPT (three digits) and STD256 /
+// STD256_OPT / STD256Q / STD256Q_OPT (four digits) with top-digit elimination (their top signed digit is exact:
+// cggi32_skip_top_ok), STD128Q / STD128Q_OPT (two digits, the top one can wrap) on the plain path.
 //
 //   for i < n, for k < digitsR:  a0 = k-th base-baseR digit of (q - a_i) mod q;  if a0 == 0 skip
 //       acc[j] = sum_{l'=1}^{d-1} NTT(digit_l') * BK[i][a0][k][l'][j]            (REPLACE; row l' = 0 is dropped)
@@ -40,10 +41,13 @@ struct DM64WArgs {
     u64 Q2, dig_off, dig_add, ninvM, zero64;
 };
 
-template <int DK, int G>
+// PLAIN = true: no top-digit elimination (two digits whose top digit can wrap: STD128Q / STD128Q_OPT): all DK digits of
+// both components are transformed, the key keeps its own rows with row l' = 0 zeroed, the result lands in rows 0 / 1.
+template <int DK, int G, bool PLAIN = false>
 __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_dm64w_kernel(const __grid_constant__ DM64WArgs A) {
     using K = KW<DK, G>;
-    constexpr int D = K::D, NT = K::NT, NF = DK - 1;
+    constexpr int D = K::D, NT = K::NT, NF = PLAIN ? DK : DK - 1;
+    constexpr int RES = PLAIN ? 0 : 2 * (DK - 1);   // rows that receive the pointwise result (a, b)
     constexpr int CT_THREADS = 2 * TPN;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* Dsm = reinterpret_cast<u64*>(smem_raw);                                  // [G][D][N]
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_dm64w_kernel(const __grid
     __syncthreads();
 
     u64* myD = Dsm + (size_t)g * D * N;
-    u64* top0 = myD + (size_t)(2 * (DK - 1)) * N;      // evaluation-domain accumulator rows (a, b)
+    u64* top0 = myD + (size_t)RES * N;                 // evaluation-domain accumulator rows (a, b)
     u64* top = top0 + (size_t)j * N;
     const u64 QHalf = Q >> 1;
     const u32 gBits = C.gBits;
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_dm64w_kernel(const __grid
             v[r] = csub(v[r], Q16);   // 11 lazy stages: < 45 Q -> < 29 Q (27-bit limb split of the pointwise stage)
     };
 
-    {
+    if (!PLAIN) {
         // evaluation-domain accumulator (scaled by N^-1, see br_cggi32.cu) of the initial accumulator
         u64 v[CPT];
 #pragma unroll
@@ -146,8 +150,8 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_dm64w_kernel(const __grid
             v[r] = A.mod.mont_mul(v[r], A.ninvM);
         __syncwarp();
         store_C(v, top, T);
-        __syncthreads();
     }
+    __syncthreads();
 
     // rgsw-acc-dm.cpp:102-109: aI = (q - a_i) mod q with the scheme's q; digit k of aI in base baseR
     const u32 qs = (u32)C.q_lwe, baseR = C.baseR, digitsR = C.digitsR;
@@ -214,8 +218,8 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_dm64w_kernel(const __grid
                         a0s.mac(x, kw[l].x);
                         a1s.mac(x, kw[l].y);
                     }
-                    dreg[(size_t)(2 * (DK - 1)) * N] = redc128(a0s.value(), Q, qinv);
-                    dreg[(size_t)(2 * (DK - 1) + 1) * N] = redc128(a1s.value(), Q, qinv);
+                    dreg[(size_t)RES * N] = redc128(a0s.value(), Q, qinv);
+                    dreg[(size_t)(RES + 1) * N] = redc128(a1s.value(), Q, qinv);
                 }
             }
             ct_sync();
@@ -277,26 +281,30 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_dm64w_kernel(const __grid
     }
 }
 
-template <int DK, int G>
+template <int DK, int G, bool PLAIN = false>
 cudaError_t launch_dm_w(const DM64WArgs& a, cudaStream_t s) {
     using K = KW<DK, G>;
     if (K::smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(br_dm64w_kernel<DK, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::smem);
+    cudaError_t e = cudaFuncSetAttribute(br_dm64w_kernel<DK, G, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)K::smem);
     if (e != cudaSuccess)
         return e;
-    br_dm64w_kernel<DK, G><<<(a.c.batch + G - 1) / G, K::NT, K::smem, s>>>(a);
+    br_dm64w_kernel<DK, G, PLAIN><<<(a.c.batch + G - 1) / G, K::NT, K::smem, s>>>(a);
     return cudaGetLastError();
 }
 
 }  // namespace
 
-// N = 2048, method AP, three or four digits with an exact top digit (elimination without wrap repair), any Q < 2^54
+// N = 2048, method AP, any Q < 2^54: three or four digits with an exact top digit (elimination without wrap repair), or
+// two digits on the plain path (STD128Q: the top digit can wrap)
 bool dm64w_supported(const tfhe_b200_params& p) {
     if (p.method != TFHE_B200_METHOD_AP || p.N != 2048 || p.numDigitsToThrow != 0)
         return false;
     if (p.Q >= (1ULL << 54) || p.q == 0 || p.q > 4096 || p.baseR < 2 || p.digitsR == 0)
         return false;
+    if (p.digitsG == 2)
+        return true;   // plain or eliminated, as cggi32_skip_top_ok decides
     if (p.digitsG != 3 && p.digitsG != 4)
         return false;
     return cggi32_skip_top_ok(p);
@@ -322,6 +330,13 @@ cudaError_t launch_br_dm64w(const BRCommon& c, const CGGI64WTables& t, cudaStrea
     a.zero64 = 0;
     a.ninvM = to_mont<u64>(h_powmod((u64)w64::N, t.mod.Q - 2, t.mod.Q), t.mod);
     const bool one = group == 1 || (group == 0 && sm_count > 0 && c.batch <= sm_count);
+    if (c.digitsKept == 2) {
+        if (!t.plain)
+            return one ? launch_dm_w<2, 1>(a, s) : launch_dm_w<2, 2>(a, s);
+        return one ? launch_dm_w<2, 1, true>(a, s) : launch_dm_w<2, 2, true>(a, s);
+    }
+    if (t.plain)
+        return cudaErrorInvalidConfiguration;
     if (c.digitsKept == 3)
         return one ? launch_dm_w<3, 1>(a, s) : launch_dm_w<3, 2>(a, s);
     if (c.digitsKept == 4)

@@ -633,7 +633,7 @@ __global__ void bk_relayout_dm32_kernel(u32* dst, const u32* src, size_t rows, u
 // 64-bit AP/DM layout (br_dm64w.cu): source [row][l'(d)][j(2)][N], destination [row][x(d)][slot][2] with plane x = l' and
 // word c = j, packed as 27-bit limb pairs; top-digit elimination as in bk_relayout_dm32_kernel.
 __global__ void bk_relayout_dm64_kernel(u64* dst, const u64* src, size_t rows, u32 d, u32 N, ModCtx<u64> M,
-                                        const u64* cM) {
+                                        const u64* cM, int skip) {
     const size_t per_row = (size_t)d * 2 * N;
     const size_t total = rows * per_row;
     const u32 top = d / 2 - 1;
@@ -645,14 +645,18 @@ __global__ void bk_relayout_dm64_kernel(u64* dst, const u64* src, size_t rows, u
         const u32 lp = r % d; r /= d;
         const size_t base = r * per_row;
         const u32 jin = lp & 1, l = lp >> 1;
-        const u64 vt = src[base + ((size_t)(jin + 2 * top) * 2 + j) * N + k];
-        const u64 t = M.mont_mul(vt, cM[l]);
         u64 val;
-        if (l == top)
-            val = t;
+        if (!skip)   // plain path: the key's own rows, row l' = 0 never enters the sum (rgsw-acc-dm.cpp:353,357)
+            val = lp >= 1 ? src[base + ((size_t)lp * 2 + j) * N + k] : 0;
         else {
-            const u64 own = lp >= 1 ? src[base + ((size_t)lp * 2 + j) * N + k] : 0;
-            val = M.sub(own, t);
+            const u64 vt = src[base + ((size_t)(jin + 2 * top) * 2 + j) * N + k];
+            const u64 t = M.mont_mul(vt, cM[l]);
+            if (l == top)
+                val = t;
+            else {
+                const u64 own = lp >= 1 ? src[base + ((size_t)lp * 2 + j) * N + k] : 0;
+                val = M.sub(own, t);
+            }
         }
         dst[idx] = (val & ((1ULL << 27) - 1)) | ((val >> 27) << 32);
     }
@@ -678,7 +682,7 @@ extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
     if (h->have_dm32 && !h->force_generic)
         return h->skip_top ? "dm_u32_ntt32_skiptop" : "dm_u32_ntt32";
     if (h->have_dm64w && !h->force_generic)
-        return "dm_u64_ntt16x128_skiptop";
+        return h->skip_top ? "dm_u64_ntt16x128_skiptop" : "dm_u64_ntt16x128";
     if (h->have_cggi64 && !h->force_generic)
         return h->have_cggi64w ? (h->skip_top ? "cggi_u64_ntt16x128_skiptop" : "cggi_u64_ntt16x128")
                                : (h->skip_top ? "cggi_u64_ntt32x64_skiptop" : "cggi_u64_ntt32x64");
@@ -817,7 +821,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
     h->have_cggi64 = h->is64 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64");
     h->have_dm32 = !h->is64 && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
     h->have_dm64w = h->is64 && dm64w_supported(p) && !getenv("TFHE_B200_NO_DM64");
-    h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) || (h->have_dm32 && cggi32_skip_top_ok(p)) || h->have_dm64w ||
+    h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) || (h->have_dm32 && cggi32_skip_top_ok(p)) || (h->have_dm64w && cggi32_skip_top_ok(p)) ||
                    (h->have_cggi64 && (cggi32_skip_top_ok(p) || cggi_skip_top_wrapfix_ok(p)))) &&
                   !getenv("TFHE_B200_NO_SKIPTOP");
     h->have_cggi64w = h->have_cggi64 && (h->skip_top ? cggi64w_supported(p) : cggi64w_plain_supported(p)) &&
@@ -940,7 +944,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
                 CUDA_TRY(cudaMalloc((void**)&d0.bk_cggi64, h->bk_words * 8));
                 bk_relayout_dm64_kernel<<<148 * 8, 256, 0, d0.stream>>>(d0.bk_cggi64, (const u64*)d0.bk_generic,
                                                                         (size_t)p.n * p.baseR * p.digitsR, h->d, p.N,
-                                                                        h->m64, (const u64*)dcM);
+                                                                        h->m64, (const u64*)dcM, h->skip_top ? 1 : 0);
                 CUDA_TRY(cudaGetLastError());
             }
             CUDA_TRY(cudaStreamSynchronize(d0.stream));
@@ -1161,6 +1165,7 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
     else if (h->have_dm64w && !h->force_generic) {
         CGGI64WTables t;
         t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twC = d.twCw; t.twB = d.twBw; t.twU = d.twUw;
+        t.plain = !h->skip_top;
         CUDA_TRY(launch_br_dm64w(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_cggi64w && !h->force_generic && !getenv("TFHE_B200_C64_NARROW")) {
