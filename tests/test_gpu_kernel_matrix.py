@@ -198,24 +198,45 @@ def test_dm64w_kernel(Q, q, baseG, baseR, rng):
         g.GPUClean()
 
 
-def test_small_modulus_on_the_64bit_kernel(rng):
-    """N = 2048 rings with a modulus below 2^31 (the STD256 family) have no 32-bit kernel shape: they run on the 64-bit
-    kernels in 64-bit words."""
-    p = po.Port.params_custom(6, 2048, 2048, Q29, 128, 1 << 8, 32, po.GINX)
+Q27b = 134176769    # STD256Q (27-bit, 1 mod 4096)
+
+
+@pytest.mark.parametrize("Q,baseG", [(Q27b, 1 << 7), (Q29, 1 << 8)])          # STD256Q / STD256 gadgets
+def test_cggi32_n2048(Q, baseG, rng, monkeypatch):
+    """N = 2048 on the 32-bit CGGI kernel (64 threads x 32 coefficients per polynomial, cross-lane stage; sweeps for the
+    29-bit modulus): gates, per-ciphertext LUTs, explicit accumulators with extreme coefficients, ragged batches, against
+    the oracle, the generic kernel and the 64-bit kernel these rings ran on before."""
+    p = po.Port.params_custom(9, 2048, 2048, Q, 128, baseG, 46, po.GINX)
     port = po.Port(p)
     sk, bk, ksk, g = _ctx(p, port)
     try:
-        assert g.kernel_variant.startswith("cggi_u64")
-        q, n = p.q, p.n
-        c1 = rng.integers(0, q, (7, n + 1), dtype=np.uint64)
+        assert g.kernel_variant == "cggi_u32_ntt32_skiptop"
+        q, n, N = p.q, p.n, 2048
+        c1 = rng.integers(0, q, (7, n + 1), dtype=np.uint64)                  # ragged vs CTAs of 2
         c2 = rng.integers(0, q, (7, n + 1), dtype=np.uint64)
-        assert np.array_equal(g.EvalBinGate("NAND", c1, c2), port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, q))
-        acc = rng.integers(0, p.Q, (3, 2, 2048), dtype=np.uint64)
-        acc[0] = p.Q - 1
-        am = rng.integers(0, q, (3, n), dtype=np.uint64)
+        c1[0, :n] = 0
+        c2[0, :n] = 0
+        for gate in ("NAND", "XNOR_FAST"):
+            want = port.eval_bin_gate(bk, ksk, po.GATES[gate], c1, c2, q)
+            assert np.array_equal(g.EvalBinGate(gate, c1, c2), want), gate
+        tab = rng.integers(0, q, (7, q), dtype=np.uint64)
+        assert np.array_equal(g.BootstrapFunc(c1, q, tab, q), port.bootstrap_func(bk, ksk, c1, q, tab, q))
+        Qm, QH = p.Q, p.Q >> 1
+        acc = rng.integers(0, Qm, (5, 2, N), dtype=np.uint64)
+        acc[0] = np.resize(np.array([0, 1, Qm - 1, QH - 1, QH, QH + 1, QH - 64, QH + 64], dtype=np.uint64), (2, N))
+        acc[1] = Qm - 1
+        acc[2] = QH
+        am = rng.integers(0, q, (5, n), dtype=np.uint64)
         want = port.eval_acc(bk, am, q, acc)
         assert np.array_equal(g.EvalAcc(am, q, acc), want)
         g.set_option("force_generic", 1)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want)
+    finally:
+        g.GPUClean()
+    monkeypatch.setenv("TFHE_B200_NO_CGGI32", "1")                            # the same ring in 64-bit words
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant.startswith("cggi_u64")
         assert np.array_equal(g.EvalAcc(am, q, acc), want)
     finally:
         g.GPUClean()

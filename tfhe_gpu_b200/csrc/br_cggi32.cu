@@ -82,10 +82,16 @@ __device__ __forceinline__ void tma_bulk_g2s(u32 dst, const void* src, u32 bytes
 // transform + N / (64 DK) pointwise iterations instead of 1 + (DK-1) + N/64.  Chosen for batches of at most one
 // ciphertext per SM.
 //
-// SWEEP = true (28-bit moduli): one reduction sweep between the two passes of every forward transform, see
+// SWEEP = 1 (28-bit moduli): one reduction sweep between the two passes of every forward transform, see
 // sweep_below_2q in ntt32.cuh; everything else is unchanged (the pointwise bounds hold for Q < 2^28: lazy rows < 12 Q,
 // eight of them times a key word < Q stay below 2^63, and the two reduced sums times the monomial factors below Q 2^32).
-template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, bool SWEEP = false>
+// SWEEP = 2 (29-bit moduli, N = 2048 only): 8 Q is all that fits 32 bits, so a sweep follows every third lazy stage and
+// the transform ends below 2 Q (rows < 2 Q times key words < Q: eight of them stay below 2^63).
+//
+// LOGN = 11 (N = 2048: the STD256 family, binfhecontext.cpp:147-148,153-154): 64 threads x 32 coefficients per
+// polynomial, i.e. two warps per (ciphertext, component); the transposes are fenced by a 64-thread named barrier and one
+// cross-lane stage sits between the two in-thread passes (cross_stage in ntt32.cuh).
+template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, int SWEEP = 0>
 __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
     br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
     using K = KCfg<LOGN, DK, G>;
@@ -120,6 +126,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     const int lw = LAT ? tid / (2 * TPN) : 0;  // latency layout: the digit polynomial this warp transforms
     const bool helper = LAT && lw == DK - 1;   // latency layout: pointwise-only warps
     const int T = tid % TPN;               // thread index within the NTT
+    const int pbar = 1 + 2 * g + j;        // named barrier of this polynomial's threads (N = 2048 only)
+    const bool odd_lane = tid & 1;
     const int ct = blockIdx.x * G + g;
     const bool live = ct < C.batch;
     const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
@@ -224,14 +232,19 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 #pragma unroll
         for (int r = 0; r < 32; r++)
             v[r] = c[r];
-        fwd_passA(v, A, Q, Q2);
-        if (SWEEP)
+        if (SWEEP == 2)
+            fwd_passA_sw(v, A, Q, Q2);
+        else
+            fwd_passA(v, A, Q, Q2);
+        if (SWEEP == 1)
             sweep_below_2q(v, Q2);
+        if (SWEEP == 2)
+            sweep_8q(v, Q2);
         u32* reg = Dsm + (size_t)g * D * RS + (size_t)(j + 2 * (DK - 1)) * RS;
 #pragma unroll
         for (int r = 0; r < 32; r++)
             reg[pos_of(T + TPN * r)] = v[r];
-        __syncwarp();
+        poly_sync<TPN>(pbar);
         {
             const uint4* p4 = reinterpret_cast<const uint4*>(reg + 36 * T);
 #pragma unroll
@@ -240,12 +253,20 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 v[4 * x] = w.x; v[4 * x + 1] = w.y; v[4 * x + 2] = w.z; v[4 * x + 3] = w.w;
             }
         }
-        __syncwarp();
-        fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+        poly_sync<TPN>(pbar);
+        if (K::XS)
+            cross_stage<true>(v, tw[31], twp[31], Q, Q2, A.zero, odd_lane);
+        if (SWEEP == 2)
+            fwd_passB_sw(v, tw, twp, Q, Q2, A.zero);
+        else
+            fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
 #pragma unroll
-        for (int r = 0; r < 32; r++) {   // < 22Q -> canonical
+        for (int r = 0; r < 32; r++) {   // < 24Q (< 2Q with SWEEP = 2) -> canonical
             u32 x = v[r];
-            x = cond_sub(x, 16 * Q); x = cond_sub(x, 8 * Q); x = cond_sub(x, 4 * Q); x = cond_sub(x, Q2); x = cond_sub(x, Q);
+            if (SWEEP != 2) {
+                x = cond_sub(x, 16 * Q); x = cond_sub(x, 8 * Q); x = cond_sub(x, 4 * Q); x = cond_sub(x, Q2);
+            }
+            x = cond_sub(x, Q);
             // the key carries N^-1 (unscaled inverse transform), so delta = true_delta / N: keep acc_eval / N as well
             // (the transformed top row carries the compensating factor N, see bk_relayout_cggi32_kernel)
             v[r] = A.mod.mont_mul(x, A.ninvM);
@@ -278,15 +299,20 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 u32 Dv = (u32)(dv + (int)A.dig_off);
                 v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
             }
-            fwd_passA(v, A, Q, Q2);
-            if (SWEEP)
+            if (SWEEP == 2)
+                fwd_passA_sw(v, A, Q, Q2);
+            else
+                fwd_passA(v, A, Q, Q2);
+            if (SWEEP == 1)
                 sweep_below_2q(v, Q2);
+            if (SWEEP == 2)
+                sweep_8q(v, Q2);
             u32* reg = myD + (size_t)(j + 2 * l) * RS;
             // transpose A layout -> B layout through the (padded) region
 #pragma unroll
             for (int r = 0; r < 32; r++)
                 reg[pos_of(T + TPN * r)] = v[r];
-            __syncwarp();
+            poly_sync<TPN>(pbar);
             {
                 const uint4* p4 = reinterpret_cast<const uint4*>(reg + 36 * T);
 #pragma unroll
@@ -295,8 +321,13 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                     v[4 * x] = w.x; v[4 * x + 1] = w.y; v[4 * x + 2] = w.z; v[4 * x + 3] = w.w;
                 }
             }
-            __syncwarp();
-            fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+            poly_sync<TPN>(pbar);
+            if (K::XS)
+                cross_stage<true>(v, tw[31], twp[31], Q, Q2, A.zero, odd_lane);
+            if (SWEEP == 2)
+                fwd_passB_sw(v, tw, twp, Q, Q2, A.zero);
+            else
+                fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
             {
                 uint4* p4 = reinterpret_cast<uint4*>(reg + 36 * T);
 #pragma unroll
@@ -456,18 +487,20 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 }
             }
             inv_passB<PB>(v, tw, twp, Q, Q2, A.zero);
-            __syncwarp();
+            if (K::XS)
+                cross_stage<false>(v, tw[31], twp[31], Q, Q2, A.zero, odd_lane);
+            poly_sync<TPN>(pbar);
             {
                 uint4* p4 = reinterpret_cast<uint4*>(reg + 36 * Tv);
 #pragma unroll
                 for (int x = 0; x < 8; x++)
                     p4[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
             }
-            __syncwarp();
+            poly_sync<TPN>(pbar);
 #pragma unroll
             for (int r = 0; r < 32; r++)
                 v[r] = reg[pos_of(T + TPN * r)];
-            __syncwarp();
+            poly_sync<TPN>(pbar);
             inv_passA(v, A, Q, Q2);
 #pragma unroll
             for (int r = 0; r < 32; r++)
@@ -516,13 +549,22 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 bool cggi32_supported(const tfhe_b200_params& p) {
     if (p.method != TFHE_B200_METHOD_GINX)
         return false;
-    if (p.N != 512 && p.N != 1024)
+    if (p.N != 512 && p.N != 1024 && p.N != 2048)
         return false;
     if (p.digitsG <= p.numDigitsToThrow)
         return false;
     const u32 dk = p.digitsG - p.numDigitsToThrow;
     bool inst = p.N == 1024 ? (dk >= 2 && dk <= 6) : (dk == 2 || dk == 3 || dk == 4 || dk == 6);
-    if (cggi32_needs_sweep(p.Q)) {
+    if (p.N == 2048) {
+        // the STD256 family: four digits, top digit exact (elimination), two ciphertexts per CTA; 27-bit moduli on the
+        // plain lazy transform (24 Q < 2^32), 29-bit moduli with a sweep every third stage (8 Q < 2^32)
+        if (dk != 4 || p.numDigitsToThrow != 0 || !cggi32_skip_top_ok(p))
+            return false;
+        if (p.Q >= (1ULL << 32) / 24 && p.Q >= (1ULL << 32) / 8)
+            return false;
+        inst = true;
+    }
+    else if (cggi32_needs_sweep(p.Q)) {
         // lazy forward NTT bound: values < 22 Q must fit 32 bits; 28-bit moduli run the variant with a mid-transform
         // sweep (12 Q per pass), instantiated for N = 1024 with three or four kept digits (MEDIUM, SIGNED_MOD_TEST)
         if (p.Q >= (1ULL << 28))
@@ -538,7 +580,7 @@ bool cggi32_supported(const tfhe_b200_params& p) {
     if ((1ULL << gbits) != p.baseG || gbits * p.digitsG > 32)
         return false;
     // shared memory of the throughput shape: G * D digit regions + psi table + G * n rotation exponents
-    const u32 G = p.N == 1024 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4);
+    const u32 G = p.N == 2048 ? 2 : (p.N == 1024 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4));
     const size_t RS = p.N + p.N / 8 + (p.N == 512 ? 16 : 0);
     const size_t smem = (size_t)G * 2 * dk * RS * 4 + (size_t)2 * p.N * 4 + (size_t)G * ((p.n + 1) / 2 * 2) * 2 + 64;
     if (smem > 227 * 1024)
@@ -603,8 +645,9 @@ static u32 shoup_h(u64 w, u64 Q) {
 // twA: [fwd|inv][32][2] ; twB: [TPN][NTW][2]   (plain residues + Shoup companions, NOT Montgomery form)
 void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::vector<u32>& twB) {
     const u64 Q = p.Q, N = p.N;
-    const u32 logN = N == 512 ? 9 : 10;
-    const u32 TPN = N / 32, PB = logN - 5, NTW = 32 - (32 >> PB);
+    const u32 logN = N == 512 ? 9 : (N == 1024 ? 10 : 11);
+    const bool xs = logN == 11;   // N = 2048: five in-thread pass-B stages + the cross-lane stage (twiddle in slot 31)
+    const u32 TPN = N / 32, PB = xs ? 5 : logN - 5, NTW = xs ? 32 : 32 - (32 >> PB);
     std::vector<u64> W(N), WI(N);
     u64 psi = p.psi % Q, psii = h_powmod(psi, Q - 2, Q), x = 1, xi = 1;
     for (u64 k = 0; k < N; k++) {
@@ -631,6 +674,12 @@ void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::
                 twB[((size_t)T * NTW + off + xx) * 2 + 1] = shoup_h(w, Q);
             }
         }
+    if (xs)
+        for (u32 T = 0; T < TPN; T++) {   // stage with 32 groups of 64: the pair of lanes (2b, 2b+1) owns group b
+            u64 w = W[32 + (T >> 1)];
+            twB[((size_t)T * NTW + 31) * 2 + 0] = (u32)w;
+            twB[((size_t)T * NTW + 31) * 2 + 1] = shoup_h(w, Q);
+        }
 }
 
 template <int LOGN, int DK, int G, bool SKIP, bool TMA>
@@ -655,11 +704,26 @@ static cudaError_t launch_sweep(const CGGI32Args& a, cudaStream_t s) {
     const size_t smem = K::smem_bytes((int)a.c.n);
     if (smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<10, DK, 4, SKIP, false, false, true>,
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<10, DK, 4, SKIP, false, false, 1>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
-    br_cggi32_kernel<10, DK, 4, SKIP, false, false, true><<<(a.c.batch + 3) / 4, K::NT, smem, s>>>(a);
+    br_cggi32_kernel<10, DK, 4, SKIP, false, false, 1><<<(a.c.batch + 3) / 4, K::NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// N = 2048 (STD256 family): four digits with top-digit elimination, two ciphertexts per CTA (8 warps)
+template <int SW>
+static cudaError_t launch_n2048(const CGGI32Args& a, cudaStream_t s) {
+    using K = KCfg<11, 4, 2>;
+    const size_t smem = K::smem_bytes((int)a.c.n);
+    if (smem > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<11, 4, 2, true, false, false, SW>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    br_cggi32_kernel<11, 4, 2, true, false, false, SW><<<(a.c.batch + 1) / 2, K::NT, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -709,6 +773,11 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
     const int dk = (int)c.digitsKept;
+    if (c.logN == 11) {
+        if (dk != 4 || !t.skip_top)
+            return cudaErrorInvalidConfiguration;
+        return t.mod.Q < (1ULL << 32) / 24 ? launch_n2048<0>(a, s) : launch_n2048<2>(a, s);
+    }
     if (cggi32_needs_sweep(t.mod.Q)) {   // 28-bit modulus: see cggi32_supported
         if (c.logN == 10 && dk == 3)
             return t.skip_top ? launch_sweep<3, true>(a, s) : launch_sweep<3, false>(a, s);

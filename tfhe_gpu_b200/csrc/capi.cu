@@ -799,7 +799,9 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
     auto* h = new tfhe_b200_handle();
     h->p = p;
     // 64-bit words for Q >= 2^31 -- and for the small-modulus N = 2048 rings, whose only specialised kernel is the 64-bit one
-    h->is64 = p.Q >= (1ULL << 31) || (cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64")) ||
+    // (N = 2048 under AP: br_dm64w; under GINX with a modulus the 32-bit kernel cannot hold: br_cggi64 / br_cggi64w)
+    const bool c32 = p.Q < (1ULL << 31) && cggi32_supported(p) && !getenv("TFHE_B200_NO_CGGI32");
+    h->is64 = p.Q >= (1ULL << 31) || (!c32 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64")) ||
               (dm64w_supported(p) && !getenv("TFHE_B200_NO_DM64"));
     while ((1u << h->logN) < p.N)
         h->logN++;
@@ -816,7 +818,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
         h->m64 = make_modctx<u64>(p.Q);
     else
         h->m32 = make_modctx<u32>(p.Q);
-    h->have_cggi32 = !h->is64 && cggi32_supported(p);
+    h->have_cggi32 = !h->is64 && cggi32_supported(p) && !getenv("TFHE_B200_NO_CGGI32");
     // TFHE_B200_NO_SKIPTOP=1 (debug) keeps the untransformed keys and the full set of forward transforms
     h->have_cggi64 = h->is64 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64");
     h->have_dm32 = !h->is64 && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
@@ -1209,7 +1211,7 @@ static int throughput_group(const tfhe_b200_handle* h) {
     if (h->group > 0)
         return h->group;
     if (h->have_cggi32)
-        return h->logN == 10 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4);
+        return h->logN == 11 ? 2 : (h->logN == 10 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4));
     if (h->have_dm32)
         return h->logN == 9 ? 8 : 4;
     if (h->have_dm64w)

@@ -33,8 +33,9 @@ template <int LOGN, int DK, int G>
 struct KCfg {
     static constexpr int N = 1 << LOGN;
     static constexpr int TPN = N / 32;            // threads per NTT
-    static constexpr int PB = LOGN - 5;           // pass-B stages
-    static constexpr int NTW = 32 - (32 >> PB);   // per-thread twiddles
+    static constexpr bool XS = LOGN == 11;        // N = 2048: one cross-lane stage (stride 32) between the two passes
+    static constexpr int PB = XS ? 5 : LOGN - 5;  // in-thread pass-B stages
+    static constexpr int NTW = XS ? 32 : 32 - (32 >> PB);   // per-thread twiddles (N = 2048: slot 31 = the cross-stage twiddle)
     static constexpr int D = 2 * DK;              // digit polynomials
     static constexpr int RS = N + N / 8 + (LOGN == 9 ? 16 : 0);  // padded region stride (words)
     static constexpr int NT = G * 2 * TPN;        // threads per CTA
@@ -79,6 +80,96 @@ __device__ __forceinline__ void sweep_below_2q(u32 (&v)[32], u32 Q2) {
         v[r] = cond_sub(x, Q2);      // < 2 Q
     }
 }
+// ---- N = 2048 (64 threads x 32 coefficients per polynomial) ----------------------------------------------------------
+// 2048 = 32 x 2 x 32: five in-thread stages on either side of ONE stage (stride 32) that pairs the 32-blocks of two
+// neighbouring lanes.  Each lane computes half of its butterflies: the lane holding the lower block (U) takes indices
+// 16..31, its neighbour (V) takes 0..15; 16 shuffles bring the operands together, 16 more send the results home.
+// FWD: Cooley-Tukey with the pair's forward twiddle; the lower block lives in the EVEN lane.  Inverse (mirrored blocks,
+// see inv_passB): Gentleman-Sande with (V - U) * w for the same forward twiddle; the lower block lives in the ODD lane.
+template <bool FWD>
+__device__ __forceinline__ void cross_stage(u32 (&v)[32], u32 w, u32 wp, u32 Q, u32 Q2, u32 Z, bool odd_lane) {
+    const bool holdsU = FWD ? !odd_lane : odd_lane;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const u32 send = holdsU ? v[i] : v[16 + i];
+        const u32 recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        const u32 U = holdsU ? v[16 + i] : recv, V = holdsU ? recv : v[i];
+        u32 nu, nv;
+        if (FWD) {
+            const u32 t = shoup_mul(V, w, wp, Q);
+            nu = U + t + Z;
+            nv = U - t + Q2;
+        }
+        else {
+            nu = cond_sub(U + V + Z, Q2);
+            nv = shoup_mul(V - U + Q2, w, wp, Q);
+        }
+        const u32 back = __shfl_xor_sync(0xffffffffu, holdsU ? nv : nu, 1);
+        if (holdsU) {
+            v[16 + i] = nu;
+            v[i] = back;
+        }
+        else {
+            v[i] = nv;
+            v[16 + i] = back;
+        }
+    }
+}
+// values < 8 Q -> < 2 Q (29-bit moduli: 8 Q still fits 32 bits, three lazy stages between sweeps)
+__device__ __forceinline__ void sweep_8q(u32 (&v)[32], u32 Q2) {
+#pragma unroll
+    for (int r = 0; r < 32; r++)
+        v[r] = cond_sub(cond_sub(v[r], 2 * Q2), Q2);
+}
+// forward pass A with a sweep after its third stage (29-bit moduli)
+template <typename A>
+__device__ __forceinline__ void fwd_passA_sw(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
+    const u32 Z = args.zero;
+#pragma unroll
+    for (int s = 4; s >= 0; s--) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = (16 >> s) + (r >> (s + 1));
+            u32 t = shoup_mul(v[r + (1 << s)], args.twA_f[ti][0], args.twA_f[ti][1], Q);
+            u32 x = v[r];
+            v[r] = x + t + Z;
+            v[r + (1 << s)] = x - t + Q2;
+        }
+        if (s == 2)
+            sweep_8q(v, Q2);
+    }
+}
+// forward pass B (five stages) with a sweep after its second stage (the cross stage came first) and after the last
+__device__ __forceinline__ void fwd_passB_sw(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2,
+                                             u32 Z) {
+#pragma unroll
+    for (int s = 4; s >= 0; s--) {
+        const int off = (32 >> (s + 1)) - 1;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r & (1 << s))
+                continue;
+            const int ti = off + (r >> (s + 1));
+            u32 t = shoup_mul(v[r + (1 << s)], tw[ti], twp[ti], Q);
+            u32 x = v[r];
+            v[r] = x + t + Z;
+            v[r + (1 << s)] = x - t + Q2;
+        }
+        if (s == 3 || s == 0)
+            sweep_8q(v, Q2);
+    }
+}
+// the threads of one polynomial: a warp (or part of one) up to N = 1024, two warps (named barrier) for N = 2048
+template <int TPN>
+__device__ __forceinline__ void poly_sync(int bar_id) {
+    if (TPN <= 32)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TPN) : "memory");
+}
+
 // forward pass B: strides 2^s, s = PB-1..0, per-thread twiddles
 template <int PB>
 __device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2,
