@@ -83,11 +83,13 @@ Q29 = 536813569     # the 29-bit prime of STD256
     (512, Q27, 1 << 9, "dm_u32_ntt32"),             # TOY shape
     (1024, Q28, 1 << 10, "dm_u32_ntt32_skiptop"),   # MEDIUM shape: elimination + mid-transform sweep
     (1024, Q28, 1 << 7, "dm_u32_ntt32"),            # SIGNED_MOD_TEST shape: four digits, plain + sweep
+    (2048, 134176769, 1 << 7, "dm_u32_ntt32_skiptop"),   # STD256Q shape: N = 2048, 27-bit modulus
+    (2048, 536813569, 1 << 8, "dm_u32_ntt32_skiptop"),   # STD256 shape: N = 2048, 29-bit modulus (sweeps)
 ])
 def test_dm32_variants(N, Q, baseG, variant, rng):
     """The AP/DM kernel beyond its headline shape: plain (no top-digit elimination) and 28-bit-modulus variants, on small
     custom rings, gates / explicit accumulators / zero refresh digits, against the oracle and the generic kernel."""
-    p = po.Port.params_custom(6, N, N, Q, 128, baseG, 32, po.AP)
+    p = po.Port.params_custom(6, N, N, Q, 128, baseG, 46 if N == 2048 else 32, po.AP)
     port = po.Port(p)
     sk, bk, ksk, g = _ctx(p, port)
     try:

@@ -41,8 +41,10 @@ struct DM32Args {
 // named STD128_AP / STD128_APOPT sets and TOY): all DK digits of both components are transformed (2*DK forward
 // transforms per active step), the key keeps its own rows with row l' = 0 zeroed (rgsw-acc-dm.cpp:353 starts at 1), and
 // the pointwise result lands in rows 0 / 1, from where the inverse transform picks it up.
-// SWEEP = true: 28-bit moduli (MEDIUM, SIGNED_MOD_TEST), see sweep_below_2q in ntt32.cuh.
-template <int LOGN, int DK, int G, bool LAT = false, bool PLAIN = false, bool SWEEP = false>
+// SWEEP = 1: 28-bit moduli (MEDIUM, SIGNED_MOD_TEST), see sweep_below_2q in ntt32.cuh; SWEEP = 2: 29-bit moduli at N = 2048.
+// LOGN = 11 (N = 2048: the STD256 family under AP): 64 threads x 32 coefficients per polynomial with the cross-lane stage
+// and the 64-thread named barriers of br_cggi32.cu.
+template <int LOGN, int DK, int G, bool LAT = false, bool PLAIN = false, int SWEEP = 0>
 __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
     br_dm32_kernel(const __grid_constant__ DM32Args A) {
     using K = KCfg<LOGN, DK, G>;
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     const int tid = threadIdx.x;
     const int g = LAT ? 0 : tid / (2 * TPN), j = (tid / TPN) & 1, T = tid % TPN;
     const int lw = LAT ? tid / (2 * TPN) : 0;     // latency layout: digit polynomial of this warp
+    const int pbar = 1 + G + 2 * g + j;           // named barrier of this polynomial's threads (N = 2048 only)
+    const bool odd_lane = tid & 1;
     const bool helper = LAT && lw == DK - 1;      // latency layout: pointwise-only warps
     const int ct = blockIdx.x * G + g;
     const bool live = ct < C.batch;
@@ -150,21 +154,34 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 #pragma unroll
         for (int r = 0; r < 32; r++)
             v[r] = c[r];
-        fwd_passA(v, A, Q, Q2);
-        if (SWEEP)
+        if (SWEEP == 2)
+            fwd_passA_sw(v, A, Q, Q2);
+        else
+            fwd_passA(v, A, Q, Q2);
+        if (SWEEP == 1)
             sweep_below_2q(v, Q2);
+        if (SWEEP == 2)
+            sweep_8q(v, Q2);
         u32* reg = myD + (size_t)(j + 2 * (DK - 1)) * RS;
 #pragma unroll
         for (int r = 0; r < 32; r++)
             reg[pos_of(T + TPN * r)] = v[r];
-        __syncwarp();
+        poly_sync<TPN>(pbar);
         load_B(v, reg, T);
-        __syncwarp();
-        fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+        poly_sync<TPN>(pbar);
+        if (K::XS)
+            cross_stage<true>(v, tw[31], twp[31], Q, Q2, A.zero, odd_lane);
+        if (SWEEP == 2)
+            fwd_passB_sw(v, tw, twp, Q, Q2, A.zero);
+        else
+            fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
 #pragma unroll
         for (int r = 0; r < 32; r++) {
             u32 x = v[r];
-            x = cond_sub(x, 16 * Q); x = cond_sub(x, 8 * Q); x = cond_sub(x, 4 * Q); x = cond_sub(x, Q2); x = cond_sub(x, Q);
+            if (SWEEP != 2) {
+                x = cond_sub(x, 16 * Q); x = cond_sub(x, 8 * Q); x = cond_sub(x, 4 * Q); x = cond_sub(x, Q2);
+            }
+            x = cond_sub(x, Q);
             v[r] = A.mod.mont_mul(x, A.ninvM);
         }
         store_B(v, reg, T);
@@ -174,7 +191,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     // The ciphertexts of a CTA share nothing but the tables: from here on every (ciphertext) pair of warps runs on its
     // own, synchronised by a named barrier, and a ciphertext whose refresh digit is zero skips the step entirely.
     const int lt = tid % CT_THREADS;                // thread within the ciphertext
-    const int bar_id = 1 + g;
+    const int bar_id = 1 + g;                       // ciphertext barriers 1..G, polynomial barriers (N = 2048) above them
     auto ct_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(CT_THREADS) : "memory"); };
     constexpr int MIT = N / CT_THREADS;             // pointwise iterations per thread (slots lt + CT_THREADS*it)
     // evaluation-domain accumulator rows (a, b): the top-digit rows -- or rows 0 / 1 when every row is a digit row
@@ -201,17 +218,27 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 u32 Dv = (u32)(dv + (int)A.dig_off);
                 v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
             }
-            fwd_passA(v, A, Q, Q2);
-            if (SWEEP)
+            if (SWEEP == 2)
+                fwd_passA_sw(v, A, Q, Q2);
+            else
+                fwd_passA(v, A, Q, Q2);
+            if (SWEEP == 1)
                 sweep_below_2q(v, Q2);
+            if (SWEEP == 2)
+                sweep_8q(v, Q2);
             u32* reg = myD + (size_t)(j + 2 * l) * RS;
 #pragma unroll
             for (int r = 0; r < 32; r++)
                 reg[pos_of(T + TPN * r)] = v[r];
-            __syncwarp();
+            poly_sync<TPN>(pbar);
             load_B(v, reg, T);
-            __syncwarp();
-            fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+            poly_sync<TPN>(pbar);
+            if (K::XS)
+                cross_stage<true>(v, tw[31], twp[31], Q, Q2, A.zero, odd_lane);
+            if (SWEEP == 2)
+                fwd_passB_sw(v, tw, twp, Q, Q2, A.zero);
+            else
+                fwd_passB<PB>(v, tw, twp, Q, Q2, A.zero);
             store_B(v, reg, T);
         }
         ct_sync();
@@ -265,13 +292,15 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             const int Tv = TPN - 1 - T;
             load_B(v, top0 + (size_t)j * RS, Tv);
             inv_passB<PB>(v, tw, twp, Q, Q2, A.zero);
-            __syncwarp();
+            if (K::XS)
+                cross_stage<false>(v, tw[31], twp[31], Q, Q2, A.zero, odd_lane);
+            poly_sync<TPN>(pbar);
             store_B(v, reg, Tv);
-            __syncwarp();
+            poly_sync<TPN>(pbar);
 #pragma unroll
             for (int r = 0; r < 32; r++)
                 v[r] = reg[pos_of(T + TPN * r)];
-            __syncwarp();
+            poly_sync<TPN>(pbar);
             inv_passA(v, A, Q, Q2);
 #pragma unroll
             for (int r = 0; r < 32; r++)
@@ -317,7 +346,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 bool dm32_supported(const tfhe_b200_params& p) {
     if (p.method != TFHE_B200_METHOD_AP || p.numDigitsToThrow != 0)
         return false;
-    if (p.Q >= (1ULL << 28))
+    if (p.Q >= (1ULL << 28) && p.N != 2048)
         return false;
     if ((u64)p.n * p.digitsR > 8192)
         return false;
@@ -327,6 +356,8 @@ bool dm32_supported(const tfhe_b200_params& p) {
     if ((1ULL << gbits) != p.baseG || gbits * p.digitsG > 32)
         return false;
     const bool skip = cggi32_skip_top_ok(p), sweep = cggi32_needs_sweep(p.Q);
+    if (p.N == 2048)   // the STD256 family: four digits, exact top digit; 27-bit moduli plain lazy, up to 29 bits with sweeps
+        return p.digitsG == 4 && skip && p.Q < (1ULL << 32) / 8 && (u64)p.n * p.digitsR <= 4096;
     if (p.N == 1024 && p.digitsG == 4 && skip && !sweep)
         return true;
     if (p.N == 1024 && p.digitsG == 3 && !skip && !sweep)
@@ -340,7 +371,7 @@ bool dm32_supported(const tfhe_b200_params& p) {
     return false;
 }
 
-template <int LOGN, int DK, int G, bool PLAIN, bool SWEEP>
+template <int LOGN, int DK, int G, bool PLAIN, int SWEEP>
 static cudaError_t launch_dm_t(const DM32Args& a, cudaStream_t s) {
     using K = KCfg<LOGN, DK, G>;
     const size_t smem = (size_t)G * K::D * K::RS * 4 + (size_t)G * a.c.n * a.c.digitsR * 4 + 64;
@@ -376,15 +407,20 @@ cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_
     {
         const bool sweep = cggi32_needs_sweep(t.mod.Q), plain = !t.skip_top;
         const int dk = (int)c.digitsKept;
+        if (c.logN == 11) {
+            if (dk != 4 || plain)
+                return cudaErrorInvalidConfiguration;
+            return t.mod.Q < (1ULL << 32) / 24 ? launch_dm_t<11, 4, 2, false, 0>(a, s) : launch_dm_t<11, 4, 2, false, 2>(a, s);
+        }
         if (c.logN == 9 && dk == 3 && plain && !sweep)
-            return launch_dm_t<9, 3, 8, true, false>(a, s);
+            return launch_dm_t<9, 3, 8, true, 0>(a, s);
         if (c.logN == 10 && dk == 3 && plain && !sweep)
-            return (sm_count > 0 && c.batch <= 2 * sm_count) ? launch_dm_t<10, 3, 2, true, false>(a, s)
-                                                             : launch_dm_t<10, 3, 4, true, false>(a, s);
+            return (sm_count > 0 && c.batch <= 2 * sm_count) ? launch_dm_t<10, 3, 2, true, 0>(a, s)
+                                                             : launch_dm_t<10, 3, 4, true, 0>(a, s);
         if (c.logN == 10 && dk == 3 && !plain && sweep)
-            return launch_dm_t<10, 3, 4, false, true>(a, s);
+            return launch_dm_t<10, 3, 4, false, 1>(a, s);
         if (c.logN == 10 && dk == 4 && plain && sweep)
-            return launch_dm_t<10, 4, 4, true, true>(a, s);
+            return launch_dm_t<10, 4, 4, true, 1>(a, s);
         if (!(c.logN == 10 && dk == 4 && !plain && !sweep))
             return cudaErrorInvalidConfiguration;
     }

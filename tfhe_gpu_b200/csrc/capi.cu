@@ -801,8 +801,9 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
     // 64-bit words for Q >= 2^31 -- and for the small-modulus N = 2048 rings, whose only specialised kernel is the 64-bit one
     // (N = 2048 under AP: br_dm64w; under GINX with a modulus the 32-bit kernel cannot hold: br_cggi64 / br_cggi64w)
     const bool c32 = p.Q < (1ULL << 31) && cggi32_supported(p) && !getenv("TFHE_B200_NO_CGGI32");
+    const bool d32 = p.Q < (1ULL << 31) && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
     h->is64 = p.Q >= (1ULL << 31) || (!c32 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64")) ||
-              (dm64w_supported(p) && !getenv("TFHE_B200_NO_DM64"));
+              (!d32 && dm64w_supported(p) && !getenv("TFHE_B200_NO_DM64"));
     while ((1u << h->logN) < p.N)
         h->logN++;
     h->d = (p.method == TFHE_B200_METHOD_GINX) ? 2 * (p.digitsG - p.numDigitsToThrow) : 2 * p.digitsG;
@@ -1213,7 +1214,7 @@ static int throughput_group(const tfhe_b200_handle* h) {
     if (h->have_cggi32)
         return h->logN == 11 ? 2 : (h->logN == 10 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4));
     if (h->have_dm32)
-        return h->logN == 9 ? 8 : 4;
+        return h->logN == 9 ? 8 : (h->logN == 11 ? 2 : 4);
     if (h->have_dm64w)
         return dk <= 3 ? 2 : 1;
     if (h->have_cggi64)
