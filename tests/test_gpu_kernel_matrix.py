@@ -161,9 +161,11 @@ Q50 = 1125899906826241   # STD128Q (50-bit)
                                              (Q29, 2048, 1 << 8, 46),      # STD256 shape: four digits, 29-bit modulus
                                              (Q35, 1024, 1 << 12, 32),     # STD192Q_OPT shape
                                              (Q50, 1024, 1 << 25, 32)])    # STD128Q shape: two digits, plain path
-def test_dm64w_kernel(Q, q, baseG, baseR, rng):
+def test_dm64w_kernel(Q, q, baseG, baseR, rng, monkeypatch):
     """AP/DM on the N = 2048 rings (br_dm64w.cu): gates, explicit accumulators with extreme coefficients, zero refresh
-    digits, both CTA shapes, against the oracle and the generic kernel."""
+    digits, both CTA shapes, against the oracle and the generic kernel.  (The 29-bit ring normally runs the 32-bit DM
+    kernel, test_dm32_variants; here it is kept on the 64-bit one.)"""
+    monkeypatch.setenv("TFHE_B200_NO_DM32", "1")
     p = po.Port.params_custom(5, 2048, q, Q, 64, baseG, baseR, po.AP)
     port = po.Port(p)
     sk, bk, ksk, g = _ctx(p, port)
