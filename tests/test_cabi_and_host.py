@@ -105,3 +105,30 @@ def test_shard_range_is_a_balanced_partition():
             for (s0, c0), (s1, _) in zip(parts, parts[1:]):
                 assert s0 + c0 == s1
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path on the host cores) needs no GPU: one JSON line with the
+    contract's keys, the thread count set explicitly even when the launcher exports OMP_NUM_THREADS=1 (torchrun does)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "toy",
+                          "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-sample", "16"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["n_gpus"] == 2
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    assert line["cpu_baseline"]["cores"] == cores
+    # the other ranks of a torchrun launch print nothing and exit 0
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "toy"],
+                         capture_output=True, text=True, timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
