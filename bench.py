@@ -301,7 +301,9 @@ class CpuArm:
         po = wl.po
         self.wl, self.po = wl, po
         self.ref = self.port = None
-        if po.have_ref():
+        # CiphertextMulMatrix has no CPU implementation in the reference (lwe-operation.cu is CUDA only; its example checks
+        # against a naive CPUGEMM, GEMM.cpp:110-120): the CPU arm of that config is the oracle port's restatement
+        if po.have_ref() and wl.kind != "mulmatrix":
             a = wl.ref_args
             self.ref = po.Ref.named(*a[1:]) if a[0] == "named" else po.Ref.func(*a[1:])
             self.ref.set_num_threads(HOST_CORES)
