@@ -339,8 +339,8 @@ class CpuArm:
 
     def default_sample(self):
         """About 10 s of CPU work, a whole number of units per thread."""
-        if self.wl.kind == "mulmatrix":
-            return 256
+        if self.wl.kind == "mulmatrix":   # the work per output grows with the matrix: same shape as the GPU arm
+            return self.wl.args.batch or self.wl.default_batch
         per_thread = max(1, min(64, int(round(10.0 / max(self.unit_s, 1e-3)))))
         return self.cores * per_thread
 
