@@ -39,6 +39,8 @@ struct CGGI32Args {
     u32 dig_add;         // Q - B/2 (digits are fed to the lazy NTT as r + Q)
     u32 ninvM;           // N^-1 in Montgomery form (SKIP: the evaluation-domain accumulator is kept scaled by N^-1)
     u32 zero;            // always 0: third IADD3 operand that keeps ptxas from turning adds into IMAD.IADD (fma-heavy pipe)
+    u32 kfixM;           // B^digits * N^-1 in Montgomery form (WRAP: correction of a wrapped top digit); last, so that the
+                         // parameter offsets of the other fields (and with them the SASS of the other variants) stay put
 };
 
 // ---- TMA bulk copies + mbarriers (key streaming of the TMA variant) ----------------------------------------------
@@ -88,20 +90,36 @@ __device__ __forceinline__ void tma_bulk_g2s(u32 dst, const void* src, u32 bytes
 // SWEEP = 2 (29-bit moduli, N = 2048 only): 8 Q is all that fits 32 bits, so a sweep follows every third lazy stage and
 // the transform ends below 2 Q (rows < 2 Q times key words < Q: eight of them stay below 2^63).
 //
+// WRAP = true (with SKIP): top-digit elimination for gadgets whose top digit CAN wrap (baseG = 2^9 on a 27-bit modulus:
+// TOY and the named STD128_AP sets; baseG = 2^7 on the 28-bit modulus: SIGNED_MOD_TEST), with the repair of br_cggi64.cu
+// ported to 32 bits.  The reference truncates the top digit to its gBits window, so for centred values within ~B/2 of
+// Q/2 the digits satisfy c = sum_l d_l B^l + B^d (cggi_skip_top_wrapfix_ok: the only possible discrepancy).  The
+// wrapped coefficients of a step (about one per polynomial for these sets) are flagged in a per-(ciphertext, component)
+// bitmap; before the pointwise stage the evaluation-domain accumulator row is corrected by -(B^d / N) * sum_k0
+// psi^((2 bitrev(slot) + 1) k0) (the transform of a monomial is a column of the psi-power table, kept pre-multiplied by
+// B^d / N in a second shared-memory table) and restored after it: 2 (DK - 1) + 2 transforms per step instead of
+// 2 DK + 2, still bit-exact.
+//
 // LOGN = 11 (N = 2048: the STD256 family, binfhecontext.cpp:147-148,153-154): 64 threads x 32 coefficients per
 // polynomial, i.e. two warps per (ciphertext, component); the transposes are fenced by a 64-thread named barrier and one
 // cross-lane stage sits between the two in-thread passes (cross_stage in ntt32.cuh).
-template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, int SWEEP = 0>
+template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, int SWEEP = 0, bool WRAP = false>
 __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
     br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
     using K = KCfg<LOGN, DK, G>;
     constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS;
     constexpr int NT = LAT ? 2 * DK * TPN : K::NT;
     static_assert(!LAT || (G == 1 && SKIP && !TMA && DK >= 2), "latency layout: one ciphertext per CTA, skip-top path");
+    static_assert(!WRAP || (SKIP && !TMA && !LAT), "wrap repair belongs to the top-digit-elimination path");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32* Dsm = reinterpret_cast<u32*>(smem_raw);                      // [G][D][RS]
     u32* psiM = Dsm + (size_t)G * D * RS;                             // [2N]
     unsigned short* es = reinterpret_cast<unsigned short*>(psiM + 2 * N);  // [G][n] rotation exponents
+    // WRAP: psi-power table pre-multiplied by B^d / N, wrapped-coefficient bitmaps [2][G][2][N/32], flags [2][G][2]
+    constexpr int WBW = N / 32;
+    u32* psiK = reinterpret_cast<u32*>(smem_raw + K::ring_offset((int)A.c.n));
+    u32* wbits = psiK + 2 * N;
+    u32* wany = wbits + 2 * G * 2 * WBW;
     // TMA variant: key ring [2][D][NT] uint4 and 4 mbarriers (full[2], empty[2]) behind the exponents, 128-byte aligned
     uint4* ring = reinterpret_cast<uint4*>(smem_raw + K::ring_offset((int)A.c.n));
     const u32 bar0 = smem_u32(ring + 2 * D * NT);
@@ -135,6 +153,12 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     // ---- one-time loads: psi-power table, rotation exponents, per-thread twiddles --------------------------
     for (int x = tid; x < 2 * N; x += NT)
         psiM[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))] = A.psi_pow[x];
+    if (WRAP) {
+        for (int x = tid; x < 2 * N; x += NT)
+            psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))] = A.mod.mont_mul(A.psi_pow[x], A.kfixM);
+        for (int x = tid; x < 2 * G * 2 * WBW + 2 * G * 2; x += NT)
+            wbits[x] = 0;   // bitmaps and flags of both parities (wany follows wbits)
+    }
     {
         // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
         const u32 mod = (u32)C.ct_mod, fac = (2 * N) / mod;
@@ -283,6 +307,24 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 
     // =========================================================================================================
     for (u32 i = 0; i < n; i++) {
+        if (WRAP) {
+            // flag the coefficients whose top digit the reference wraps: bit gBits * DK of the offset value
+            const u32 wsh = gBits * DK;
+            u32* wb = wbits + ((size_t)((i & 1) * G + g) * 2 + j) * WBW;
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
+                const u32 Dv = (u32)(dv + (int)A.dig_off);
+                if ((Dv >> wsh) & 1) {
+                    const u32 idx = T + TPN * r;
+                    atomicOr(wb + (idx >> 5), 1u << (idx & 31));
+                    any = true;
+                }
+            }
+            if (any)
+                wany[((i & 1) * G + g) * 2 + j] = 1;
+        }
         // ---- phase 1: decompose + forward NTT of the DK digit polynomials of component j ---------------------
 #ifdef CGGI32_UNROLL_L
 #pragma unroll
@@ -336,6 +378,55 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             }
         }
         __syncthreads();
+
+        // ---- wrap repair: correct the evaluation-domain accumulator rows of the polynomials with wrapped top digits ---
+        bool anyflag = false;
+        auto wrap_fix = [&](bool undo) {
+            const u32* fl = wany + (size_t)(i & 1) * G * 2;
+#pragma unroll 1
+            for (int gj = 0; gj < 2 * G; gj++) {
+                if (!fl[gj])
+                    continue;
+                const u32* wb = wbits + ((size_t)(i & 1) * G * 2 + gj) * WBW;
+                u32* row = Dsm + (size_t)(gj >> 1) * D * RS + (size_t)(2 * (DK - 1) + (gj & 1)) * RS;
+#pragma unroll 1
+                for (int k = tid; k < N; k += NT) {
+                    const u32 br = __brev((u32)k) >> (32 - LOGN);
+                    u32 sum = 0;
+#pragma unroll 1
+                    for (int wd = 0; wd < WBW; wd++) {
+                        u32 bits = wb[wd];
+                        while (bits) {
+                            const u32 k0 = 32 * wd + (__ffs(bits) - 1);
+                            bits &= bits - 1;
+                            const u32 x = ((2 * br + 1) * k0) & (2 * N - 1);
+                            sum = cond_sub(sum + psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))], Q);
+                        }
+                    }
+                    const u32 pk = pos_of(k);
+                    const u32 x = row[pk];
+                    row[pk] = undo ? cond_sub(x + sum, Q) : (x >= sum ? x - sum : x + Q - sum);
+                }
+            }
+        };
+        if (WRAP) {
+            const u32* fl = wany + (size_t)(i & 1) * G * 2;
+            u32 f = 0;
+#pragma unroll
+            for (int x = 0; x < 2 * G; x++)
+                f |= fl[x];
+            anyflag = f != 0;
+            // the other parity's bitmaps and flags are dead until the next step's detection: clear them now
+            u32* ob = wbits + (size_t)((i + 1) & 1) * G * 2 * WBW;
+            for (int x = tid; x < G * 2 * WBW; x += NT)
+                ob[x] = 0;
+            if (tid < 2 * G)
+                wany[((i + 1) & 1) * G * 2 + tid] = 0;
+            if (anyflag) {
+                wrap_fix(false);
+                __syncthreads();
+            }
+        }
 
         // ---- phase 2: pointwise MAC against the RGSW keys of step i, monomial factors, delta -> regions 0,1 ---
         // The key slice of evaluation slot k is 4*D words, stored as D "planes" of uint4 ([i][x][k][4]) so a warp
@@ -468,6 +559,10 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             }
         }
         __syncthreads();
+        if (WRAP && anyflag) {
+            wrap_fix(true);
+            __syncthreads();
+        }
 
         // ---- phase 3: inverse NTT (mirrored block) ------------------------------------------------------------
         // plain path: of delta_j, accumulated into c.  SKIP path: of the evaluation-domain accumulator itself,
@@ -712,6 +807,36 @@ static cudaError_t launch_sweep(const CGGI32Args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// top-digit elimination with wrap repair (see the kernel header): extra shared memory for the second psi table, the
+// bitmaps and the flags behind the rotation exponents
+template <int LOGN, int DK, int G, int SW>
+static cudaError_t launch_wrap(const CGGI32Args& a, cudaStream_t s) {
+    using K = KCfg<LOGN, DK, G>;
+    const size_t smem = K::ring_offset((int)a.c.n) + (size_t)2 * K::N * 4 + (size_t)2 * G * 2 * (K::N / 32) * 4 +
+                        (size_t)2 * G * 2 * 4 + 64;
+    if (smem > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G, true, false, false, SW, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    br_cggi32_kernel<LOGN, DK, G, true, false, false, SW, true><<<(a.c.batch + G - 1) / G, K::NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+// which parameter sets take that path: top digit not exact but repairable, one of the instantiated shapes
+bool cggi32_wrapfix_shape(const tfhe_b200_params& p) {
+    if (!cggi32_supported(p) || cggi32_skip_top_ok(p) || !cggi_skip_top_wrapfix_ok(p))
+        return false;
+    u32 gbits = 0;
+    while ((1ULL << gbits) < p.baseG)
+        gbits++;
+    if (gbits * p.digitsG >= 32)   // the wrap flag is bit gBits * digits of a 32-bit value
+        return false;
+    const bool sweep = cggi32_needs_sweep(p.Q);
+    return (p.N == 512 && p.digitsG == 3 && !sweep) || (p.N == 1024 && p.digitsG == 3 && !sweep) ||
+           (p.N == 1024 && p.digitsG == 4 && sweep);
+}
+
 // N = 2048 (STD256 family): four digits with top-digit elimination, two ciphertexts per CTA (8 warps)
 template <int SW>
 static cudaError_t launch_n2048(const CGGI32Args& a, cudaStream_t s) {
@@ -772,7 +897,17 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     a.dig_add = t.mod.Q - B / 2;
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
+    a.kfixM = to_mont<u32>(h_mulmod((u64)(pw % t.mod.Q), h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod.Q), t.mod);
     const int dk = (int)c.digitsKept;
+    if (t.wrap) {   // top-digit elimination with wrap repair: throughput shapes of the sets that need it
+        if (c.logN == 9 && dk == 3)
+            return launch_wrap<9, 3, 8, 0>(a, s);
+        if (c.logN == 10 && dk == 3 && !cggi32_needs_sweep(t.mod.Q))
+            return launch_wrap<10, 3, 4, 0>(a, s);
+        if (c.logN == 10 && dk == 4 && cggi32_needs_sweep(t.mod.Q))
+            return launch_wrap<10, 4, 4, 1>(a, s);
+        return cudaErrorInvalidConfiguration;
+    }
     if (c.logN == 11) {
         if (dk != 4 || !t.skip_top)
             return cudaErrorInvalidConfiguration;
