@@ -39,7 +39,7 @@ struct CGGI32Args {
     u32 dig_add;         // Q - B/2 (digits are fed to the lazy NTT as r + Q)
     u32 ninvM;           // N^-1 in Montgomery form (SKIP: the evaluation-domain accumulator is kept scaled by N^-1)
     u32 zero;            // always 0: third IADD3 operand that keeps ptxas from turning adds into IMAD.IADD (fma-heavy pipe)
-    u32 kfixM;           // B^digits * N^-1 in Montgomery form (WRAP: correction of a wrapped top digit); last, so that the
+    u32 kfixM;           // B^digits * N^-1, plain residue (WRAP: times the Montgomery-form psi powers = plain terms); last, so that the
                          // parameter offsets of the other fields (and with them the SASS of the other variants) stay put
 };
 
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             // flag the coefficients whose top digit the reference wraps: bit gBits * DK of the offset value
             const u32 wsh = gBits * DK;
             u32* wb = wbits + ((size_t)((i & 1) * G + g) * 2 + j) * WBW;
-            bool any = false;
+            u32 any = 0;
 #pragma unroll
             for (int r = 0; r < 32; r++) {
                 const int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
@@ -319,11 +319,11 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 if ((Dv >> wsh) & 1) {
                     const u32 idx = T + TPN * r;
                     atomicOr(wb + (idx >> 5), 1u << (idx & 31));
-                    any = true;
+                    any |= 1u << (idx >> 5);
                 }
             }
             if (any)
-                wany[((i & 1) * G + g) * 2 + j] = 1;
+                atomicOr(&wany[((i & 1) * G + g) * 2 + j], any);   // which bitmap words hold flags
         }
         // ---- phase 1: decompose + forward NTT of the DK digit polynomials of component j ---------------------
 #ifdef CGGI32_UNROLL_L
@@ -380,32 +380,37 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
         __syncthreads();
 
         // ---- wrap repair: correct the evaluation-domain accumulator rows of the polynomials with wrapped top digits ---
+        // One warp per flagged polynomial (they are independent); wany[gj] is a summary of which bitmap words are set, so
+        // the common case -- one or two wrapped coefficients -- costs two dependent shared-memory reads before the
+        // slot loop, whose iterations are independent.
         bool anyflag = false;
         auto wrap_fix = [&](bool undo) {
             const u32* fl = wany + (size_t)(i & 1) * G * 2;
+            const int lane = tid & 31;
 #pragma unroll 1
-            for (int gj = 0; gj < 2 * G; gj++) {
-                if (!fl[gj])
+            for (int gj = tid >> 5; gj < 2 * G; gj += NT / 32) {
+                u32 ws = fl[gj];
+                if (!ws)
                     continue;
                 const u32* wb = wbits + ((size_t)(i & 1) * G * 2 + gj) * WBW;
                 u32* row = Dsm + (size_t)(gj >> 1) * D * RS + (size_t)(2 * (DK - 1) + (gj & 1)) * RS;
-#pragma unroll 1
-                for (int k = tid; k < N; k += NT) {
-                    const u32 br = __brev((u32)k) >> (32 - LOGN);
-                    u32 sum = 0;
-#pragma unroll 1
-                    for (int wd = 0; wd < WBW; wd++) {
-                        u32 bits = wb[wd];
-                        while (bits) {
-                            const u32 k0 = 32 * wd + (__ffs(bits) - 1);
-                            bits &= bits - 1;
+                while (ws) {
+                    const u32 wd = __ffs(ws) - 1;
+                    ws &= ws - 1;
+                    u32 bits = wb[wd];
+                    while (bits) {
+                        const u32 k0 = 32 * wd + (__ffs(bits) - 1);
+                        bits &= bits - 1;
+#pragma unroll 4
+                        for (int k = lane; k < N; k += 32) {
+                            const u32 br = __brev((u32)k) >> (32 - LOGN);
                             const u32 x = ((2 * br + 1) * k0) & (2 * N - 1);
-                            sum = cond_sub(sum + psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))], Q);
+                            const u32 t = psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))];
+                            const u32 pk = pos_of(k);
+                            const u32 y = row[pk];
+                            row[pk] = undo ? cond_sub(y + t, Q) : (y >= t ? y - t : y + Q - t);
                         }
                     }
-                    const u32 pk = pos_of(k);
-                    const u32 x = row[pk];
-                    row[pk] = undo ? cond_sub(x + sum, Q) : (x >= sum ? x - sum : x + Q - sum);
                 }
             }
         };
@@ -897,7 +902,7 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     a.dig_add = t.mod.Q - B / 2;
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
-    a.kfixM = to_mont<u32>(h_mulmod((u64)(pw % t.mod.Q), h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod.Q), t.mod);
+    a.kfixM = (u32)h_mulmod((u64)(pw % t.mod.Q), h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod.Q);
     const int dk = (int)c.digitsKept;
     if (t.wrap) {   // top-digit elimination with wrap repair: throughput shapes of the sets that need it
         if (c.logN == 9 && dk == 3)
