@@ -94,11 +94,13 @@ __device__ __forceinline__ void tma_bulk_g2s(u32 dst, const void* src, u32 bytes
 // TOY and the named STD128_AP sets; baseG = 2^7 on the 28-bit modulus: SIGNED_MOD_TEST), with the repair of br_cggi64.cu
 // ported to 32 bits.  The reference truncates the top digit to its gBits window, so for centred values within ~B/2 of
 // Q/2 the digits satisfy c = sum_l d_l B^l + B^d (cggi_skip_top_wrapfix_ok: the only possible discrepancy).  The
-// wrapped coefficients of a step (about one per polynomial for these sets) are flagged in a per-(ciphertext, component)
-// bitmap; before the pointwise stage the evaluation-domain accumulator row is corrected by -(B^d / N) * sum_k0
-// psi^((2 bitrev(slot) + 1) k0) (the transform of a monomial is a column of the psi-power table, kept pre-multiplied by
-// B^d / N in a second shared-memory table) and restored after it: 2 (DK - 1) + 2 transforms per step instead of
-// 2 DK + 2, still bit-exact.
+// wrapped coefficients of a step (about one per polynomial for these sets) are listed per (ciphertext, component);
+// in the pointwise stage the accumulator-row OPERAND of a slot is corrected by -(B^d / N) * sum_k0 psi^((2 bitrev(slot)
+// + 1) k0) (the transform of a monomial is a column of the psi-power table, kept pre-multiplied by B^d / N in a second
+// shared-memory table) while the stored accumulator keeps accumulating delta: 2 (DK - 1) + 2 transforms per step
+// instead of 2 DK + 2, no extra pass and no extra barrier, still bit-exact.  (A first version corrected the rows in a
+// separate pass before and after the pointwise stage, as the 64-bit kernel does: two more CTA barriers per step and a
+// serial scan cost more than the two transforms it saved -- 63.9 k against 92.4 k STD128_AP gates/s.)
 //
 // LOGN = 11 (N = 2048: the STD256 family, binfhecontext.cpp:147-148,153-154): 64 threads x 32 coefficients per
 // polynomial, i.e. two warps per (ciphertext, component); the transposes are fenced by a 64-thread named barrier and one
@@ -115,11 +117,11 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     u32* Dsm = reinterpret_cast<u32*>(smem_raw);                      // [G][D][RS]
     u32* psiM = Dsm + (size_t)G * D * RS;                             // [2N]
     unsigned short* es = reinterpret_cast<unsigned short*>(psiM + 2 * N);  // [G][n] rotation exponents
-    // WRAP: psi-power table pre-multiplied by B^d / N, wrapped-coefficient bitmaps [2][G][2][N/32], flags [2][G][2]
-    constexpr int WBW = N / 32;
+    // WRAP: psi-power table pre-multiplied by B^d / N, per-(ciphertext, component) lists of the wrapped coefficients of the
+    // current step [G][2][N] (u16, full capacity: every coefficient may wrap) and their lengths [G][2]
     u32* psiK = reinterpret_cast<u32*>(smem_raw + K::ring_offset((int)A.c.n));
-    u32* wbits = psiK + 2 * N;
-    u32* wany = wbits + 2 * G * 2 * WBW;
+    u32* wcnt = psiK + 2 * N;
+    unsigned short* wlist = reinterpret_cast<unsigned short*>(wcnt + 2 * G);
     // TMA variant: key ring [2][D][NT] uint4 and 4 mbarriers (full[2], empty[2]) behind the exponents, 128-byte aligned
     uint4* ring = reinterpret_cast<uint4*>(smem_raw + K::ring_offset((int)A.c.n));
     const u32 bar0 = smem_u32(ring + 2 * D * NT);
@@ -156,8 +158,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     if (WRAP) {
         for (int x = tid; x < 2 * N; x += NT)
             psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))] = A.mod.mont_mul(A.psi_pow[x], A.kfixM);
-        for (int x = tid; x < 2 * G * 2 * WBW + 2 * G * 2; x += NT)
-            wbits[x] = 0;   // bitmaps and flags of both parities (wany follows wbits)
+        for (int x = tid; x < 2 * G; x += NT)
+            wcnt[x] = 0;
     }
     {
         // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
@@ -308,22 +310,22 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     // =========================================================================================================
     for (u32 i = 0; i < n; i++) {
         if (WRAP) {
-            // flag the coefficients whose top digit the reference wraps: bit gBits * DK of the offset value
+            // list the coefficients whose top digit the reference wraps: bit gBits * DK of the offset value.  The list of
+            // the previous step was last read before the barrier that ends its pointwise stage; the threads of a
+            // polynomial share a warp (N <= 1024), so a warp-level fence orders the reset before the appends.
             const u32 wsh = gBits * DK;
-            u32* wb = wbits + ((size_t)((i & 1) * G + g) * 2 + j) * WBW;
-            u32 any = 0;
+            u32* cnt = wcnt + g * 2 + j;
+            unsigned short* lst = wlist + (size_t)(g * 2 + j) * N;
+            if (T == 0)
+                *cnt = 0;
+            __syncwarp();
 #pragma unroll
             for (int r = 0; r < 32; r++) {
                 const int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
                 const u32 Dv = (u32)(dv + (int)A.dig_off);
-                if ((Dv >> wsh) & 1) {
-                    const u32 idx = T + TPN * r;
-                    atomicOr(wb + (idx >> 5), 1u << (idx & 31));
-                    any |= 1u << (idx >> 5);
-                }
+                if ((Dv >> wsh) & 1)
+                    lst[atomicAdd(cnt, 1u)] = (unsigned short)(T + TPN * r);
             }
-            if (any)
-                atomicOr(&wany[((i & 1) * G + g) * 2 + j], any);   // which bitmap words hold flags
         }
         // ---- phase 1: decompose + forward NTT of the DK digit polynomials of component j ---------------------
 #ifdef CGGI32_UNROLL_L
@@ -378,60 +380,6 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             }
         }
         __syncthreads();
-
-        // ---- wrap repair: correct the evaluation-domain accumulator rows of the polynomials with wrapped top digits ---
-        // One warp per flagged polynomial (they are independent); wany[gj] is a summary of which bitmap words are set, so
-        // the common case -- one or two wrapped coefficients -- costs two dependent shared-memory reads before the
-        // slot loop, whose iterations are independent.
-        bool anyflag = false;
-        auto wrap_fix = [&](bool undo) {
-            const u32* fl = wany + (size_t)(i & 1) * G * 2;
-            const int lane = tid & 31;
-#pragma unroll 1
-            for (int gj = tid >> 5; gj < 2 * G; gj += NT / 32) {
-                u32 ws = fl[gj];
-                if (!ws)
-                    continue;
-                const u32* wb = wbits + ((size_t)(i & 1) * G * 2 + gj) * WBW;
-                u32* row = Dsm + (size_t)(gj >> 1) * D * RS + (size_t)(2 * (DK - 1) + (gj & 1)) * RS;
-                while (ws) {
-                    const u32 wd = __ffs(ws) - 1;
-                    ws &= ws - 1;
-                    u32 bits = wb[wd];
-                    while (bits) {
-                        const u32 k0 = 32 * wd + (__ffs(bits) - 1);
-                        bits &= bits - 1;
-#pragma unroll 4
-                        for (int k = lane; k < N; k += 32) {
-                            const u32 br = __brev((u32)k) >> (32 - LOGN);
-                            const u32 x = ((2 * br + 1) * k0) & (2 * N - 1);
-                            const u32 t = psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))];
-                            const u32 pk = pos_of(k);
-                            const u32 y = row[pk];
-                            row[pk] = undo ? cond_sub(y + t, Q) : (y >= t ? y - t : y + Q - t);
-                        }
-                    }
-                }
-            }
-        };
-        if (WRAP) {
-            const u32* fl = wany + (size_t)(i & 1) * G * 2;
-            u32 f = 0;
-#pragma unroll
-            for (int x = 0; x < 2 * G; x++)
-                f |= fl[x];
-            anyflag = f != 0;
-            // the other parity's bitmaps and flags are dead until the next step's detection: clear them now
-            u32* ob = wbits + (size_t)((i + 1) & 1) * G * 2 * WBW;
-            for (int x = tid; x < G * 2 * WBW; x += NT)
-                ob[x] = 0;
-            if (tid < 2 * G)
-                wany[((i + 1) & 1) * G * 2 + tid] = 0;
-            if (anyflag) {
-                wrap_fix(false);
-                __syncthreads();
-            }
-        }
 
         // ---- phase 2: pointwise MAC against the RGSW keys of step i, monomial factors, delta -> regions 0,1 ---
         // The key slice of evaluation slot k is 4*D words, stored as D "planes" of uint4 ([i][x][k][4]) so a warp
@@ -498,12 +446,34 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 #pragma unroll
                 for (int g0 = 0; g0 < G; g0 += GB) {
                     u32 xd[GB][D], m1[GB], m2[GB], dl0[GB], dl1[GB];
+                    u32 xt[WRAP ? GB : 1][2];   // WRAP: the uncorrected accumulator rows
 #pragma unroll
                     for (int b = 0; b < GB; b++) {
                         const u32* dreg = Dsm + (size_t)(g0 + b) * D * RS + pk;
 #pragma unroll
                         for (int l = 0; l < D; l++)
                             xd[b][l] = dreg[(size_t)l * RS];
+                        if (WRAP) {
+                            // the accumulator rows enter the products as NTT(c - B^d e) / N, e = indicator polynomial of
+                            // the wrapped coefficients: subtract (B^d / N) psi^((2 br + 1) k0) per listed k0.  Only the
+                            // operand is corrected; the stored accumulator (xt) keeps accumulating delta.
+#pragma unroll
+                            for (int jj = 0; jj < 2; jj++) {
+                                xt[b][jj] = xd[b][2 * (DK - 1) + jj];
+                                const u32 cw = wcnt[(g0 + b) * 2 + jj];
+                                if (cw) {
+                                    const unsigned short* lst = wlist + (size_t)((g0 + b) * 2 + jj) * N;
+                                    u32 sum = 0;
+#pragma unroll 1
+                                    for (u32 w = 0; w < cw; w++) {
+                                        const u32 x = ((2 * br + 1) * (u32)lst[w]) & (2 * N - 1);
+                                        sum = cond_sub(sum + psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))], Q);
+                                    }
+                                    const u32 y = xt[b][jj];
+                                    xd[b][2 * (DK - 1) + jj] = y >= sum ? y - sum : y + Q - sum;
+                                }
+                            }
+                        }
                         const u32 e = es[(g0 + b) * n + i];
                         const u32 xx = ((2 * br + 1) * e) & (2 * N - 1);
                         const u32 x2 = (2 * N - xx) & (2 * N - 1);
@@ -530,8 +500,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                         dl0[b] = redc_full((u64)r00 * a1 + (u64)r10 * a2);
                         dl1[b] = redc_full((u64)r01 * a1 + (u64)r11 * a2);
                         if (SKIP) {   // acc_eval += delta (kept canonical); its old value is the top row just loaded
-                            m1[b] = cond_sub(xd[b][2 * (DK - 1)] + dl0[b], Q);
-                            m2[b] = cond_sub(xd[b][2 * (DK - 1) + 1] + dl1[b], Q);
+                            m1[b] = cond_sub((WRAP ? xt[b][0] : xd[b][2 * (DK - 1)]) + dl0[b], Q);
+                            m2[b] = cond_sub((WRAP ? xt[b][1] : xd[b][2 * (DK - 1) + 1]) + dl1[b], Q);
                         }
                     }
 #pragma unroll
@@ -564,10 +534,6 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             }
         }
         __syncthreads();
-        if (WRAP && anyflag) {
-            wrap_fix(true);
-            __syncthreads();
-        }
 
         // ---- phase 3: inverse NTT (mirrored block) ------------------------------------------------------------
         // plain path: of delta_j, accumulated into c.  SKIP path: of the evaluation-domain accumulator itself,
@@ -817,8 +783,7 @@ static cudaError_t launch_sweep(const CGGI32Args& a, cudaStream_t s) {
 template <int LOGN, int DK, int G, int SW>
 static cudaError_t launch_wrap(const CGGI32Args& a, cudaStream_t s) {
     using K = KCfg<LOGN, DK, G>;
-    const size_t smem = K::ring_offset((int)a.c.n) + (size_t)2 * K::N * 4 + (size_t)2 * G * 2 * (K::N / 32) * 4 +
-                        (size_t)2 * G * 2 * 4 + 64;
+    const size_t smem = K::ring_offset((int)a.c.n) + (size_t)2 * K::N * 4 + (size_t)2 * G * 4 + (size_t)2 * G * K::N * 2 + 64;
     if (smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G, true, false, false, SW, true>,
