@@ -247,16 +247,17 @@ def test_cggi32_n2048(Q, baseG, rng, monkeypatch):
 
 
 @pytest.mark.parametrize("N,Q,baseG", [(1024, Q27, 1 << 9), (512, Q27, 1 << 9), (1024, Q28, 1 << 7)])
-def test_cggi32_wrapped_top_digit_repair(N, Q, baseG, rng, monkeypatch):
-    """32-bit rings whose top digit can wrap (baseG^digits barely above Q: TOY, the STD128_AP sets, SIGNED_MOD_TEST):
-    top-digit elimination with the on-the-fly repair.  Accumulators are built to hit it -- every coefficient in the wrap
-    zone, a single wrapped coefficient, a mix around the zone's lower edge, the extremes of the centred range -- and
-    compared with the oracle, with the plain path (TFHE_B200_NO_WRAP32) and with the generic kernel."""
+def test_cggi32_wrapping_top_digit_plain_path(N, Q, baseG, rng):
+    """32-bit rings whose top digit can wrap (baseG^digits barely above Q: TOY, the STD128_AP sets, SIGNED_MOD_TEST) stay
+    on the plain path (all digits transformed): the reference truncates the top digit to its window, and the kernel must
+    reproduce exactly that.  Accumulators are built to hit it -- every coefficient in the wrap zone, a single wrapped
+    coefficient, a mix around the zone's lower edge, the extremes of the centred range.  (Top-digit elimination with an
+    on-the-fly repair, as the 64-bit kernel does, was implemented and measured slower here: DESIGN.md section 9.)"""
     p = po.Port.params_custom(10, N, N, Q, 128, baseG, 32, po.GINX)
     port = po.Port(p)
     sk, bk, ksk, g = _ctx(p, port)
     try:
-        assert g.kernel_variant == "cggi_u32_ntt32_skiptop_wrapfix"
+        assert g.kernel_variant == "cggi_u32_ntt32"
         Qm, QH = p.Q, p.Q >> 1
         B, d = baseG, p.digitsG
         off = sum((B // 2) * B**i for i in range(d))
@@ -273,18 +274,7 @@ def test_cggi32_wrapped_top_digit_repair(N, Q, baseG, rng, monkeypatch):
         am = rng.integers(0, p.q, (9, p.n), dtype=np.uint64)
         want = port.eval_acc(bk, am, p.q, acc)
         assert np.array_equal(g.EvalAcc(am, p.q, acc), want)
-        c1 = rng.integers(0, p.q, (13, p.n + 1), dtype=np.uint64)
-        c2 = rng.integers(0, p.q, (13, p.n + 1), dtype=np.uint64)
-        wg = port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, p.q)
-        assert np.array_equal(g.EvalBinGate("NAND", c1, c2), wg)
         g.set_option("force_generic", 1)
-        assert np.array_equal(g.EvalAcc(am, p.q, acc), want)
-    finally:
-        g.GPUClean()
-    monkeypatch.setenv("TFHE_B200_NO_WRAP32", "1")                         # the plain path of the same kernel
-    sk, bk, ksk, g = _ctx(p, port)
-    try:
-        assert g.kernel_variant == "cggi_u32_ntt32"
         assert np.array_equal(g.EvalAcc(am, p.q, acc), want)
     finally:
         g.GPUClean()

@@ -39,8 +39,6 @@ struct CGGI32Args {
     u32 dig_add;         // Q - B/2 (digits are fed to the lazy NTT as r + Q)
     u32 ninvM;           // N^-1 in Montgomery form (SKIP: the evaluation-domain accumulator is kept scaled by N^-1)
     u32 zero;            // always 0: third IADD3 operand that keeps ptxas from turning adds into IMAD.IADD (fma-heavy pipe)
-    u32 kfixM;           // B^digits * N^-1, plain residue (WRAP: times the Montgomery-form psi powers = plain terms); last, so that the
-                         // parameter offsets of the other fields (and with them the SASS of the other variants) stay put
 };
 
 // ---- TMA bulk copies + mbarriers (key streaming of the TMA variant) ----------------------------------------------
@@ -90,38 +88,20 @@ __device__ __forceinline__ void tma_bulk_g2s(u32 dst, const void* src, u32 bytes
 // SWEEP = 2 (29-bit moduli, N = 2048 only): 8 Q is all that fits 32 bits, so a sweep follows every third lazy stage and
 // the transform ends below 2 Q (rows < 2 Q times key words < Q: eight of them stay below 2^63).
 //
-// WRAP = true (with SKIP): top-digit elimination for gadgets whose top digit CAN wrap (baseG = 2^9 on a 27-bit modulus:
-// TOY and the named STD128_AP sets; baseG = 2^7 on the 28-bit modulus: SIGNED_MOD_TEST), with the repair of br_cggi64.cu
-// ported to 32 bits.  The reference truncates the top digit to its gBits window, so for centred values within ~B/2 of
-// Q/2 the digits satisfy c = sum_l d_l B^l + B^d (cggi_skip_top_wrapfix_ok: the only possible discrepancy).  The
-// wrapped coefficients of a step (about one per polynomial for these sets) are listed per (ciphertext, component);
-// in the pointwise stage the accumulator-row OPERAND of a slot is corrected by -(B^d / N) * sum_k0 psi^((2 bitrev(slot)
-// + 1) k0) (the transform of a monomial is a column of the psi-power table, kept pre-multiplied by B^d / N in a second
-// shared-memory table) while the stored accumulator keeps accumulating delta: 2 (DK - 1) + 2 transforms per step
-// instead of 2 DK + 2, no extra pass and no extra barrier, still bit-exact.  (A first version corrected the rows in a
-// separate pass before and after the pointwise stage, as the 64-bit kernel does: two more CTA barriers per step and a
-// serial scan cost more than the two transforms it saved -- 63.9 k against 92.4 k STD128_AP gates/s.)
-//
 // LOGN = 11 (N = 2048: the STD256 family, binfhecontext.cpp:147-148,153-154): 64 threads x 32 coefficients per
 // polynomial, i.e. two warps per (ciphertext, component); the transposes are fenced by a 64-thread named barrier and one
 // cross-lane stage sits between the two in-thread passes (cross_stage in ntt32.cuh).
-template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, int SWEEP = 0, bool WRAP = false>
+template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, int SWEEP = 0>
 __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
     br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
     using K = KCfg<LOGN, DK, G>;
     constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS;
     constexpr int NT = LAT ? 2 * DK * TPN : K::NT;
     static_assert(!LAT || (G == 1 && SKIP && !TMA && DK >= 2), "latency layout: one ciphertext per CTA, skip-top path");
-    static_assert(!WRAP || (SKIP && !TMA && !LAT), "wrap repair belongs to the top-digit-elimination path");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32* Dsm = reinterpret_cast<u32*>(smem_raw);                      // [G][D][RS]
     u32* psiM = Dsm + (size_t)G * D * RS;                             // [2N]
     unsigned short* es = reinterpret_cast<unsigned short*>(psiM + 2 * N);  // [G][n] rotation exponents
-    // WRAP: psi-power table pre-multiplied by B^d / N, per-(ciphertext, component) lists of the wrapped coefficients of the
-    // current step [G][2][N] (u16, full capacity: every coefficient may wrap) and their lengths [G][2]
-    u32* psiK = reinterpret_cast<u32*>(smem_raw + K::ring_offset((int)A.c.n));
-    u32* wcnt = psiK + 2 * N;
-    unsigned short* wlist = reinterpret_cast<unsigned short*>(wcnt + 2 * G);
     // TMA variant: key ring [2][D][NT] uint4 and 4 mbarriers (full[2], empty[2]) behind the exponents, 128-byte aligned
     uint4* ring = reinterpret_cast<uint4*>(smem_raw + K::ring_offset((int)A.c.n));
     const u32 bar0 = smem_u32(ring + 2 * D * NT);
@@ -155,12 +135,6 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     // ---- one-time loads: psi-power table, rotation exponents, per-thread twiddles --------------------------
     for (int x = tid; x < 2 * N; x += NT)
         psiM[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))] = A.psi_pow[x];
-    if (WRAP) {
-        for (int x = tid; x < 2 * N; x += NT)
-            psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))] = A.mod.mont_mul(A.psi_pow[x], A.kfixM);
-        for (int x = tid; x < 2 * G; x += NT)
-            wcnt[x] = 0;
-    }
     {
         // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
         const u32 mod = (u32)C.ct_mod, fac = (2 * N) / mod;
@@ -309,24 +283,6 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 
     // =========================================================================================================
     for (u32 i = 0; i < n; i++) {
-        if (WRAP) {
-            // list the coefficients whose top digit the reference wraps: bit gBits * DK of the offset value.  The list of
-            // the previous step was last read before the barrier that ends its pointwise stage; the threads of a
-            // polynomial share a warp (N <= 1024), so a warp-level fence orders the reset before the appends.
-            const u32 wsh = gBits * DK;
-            u32* cnt = wcnt + g * 2 + j;
-            unsigned short* lst = wlist + (size_t)(g * 2 + j) * N;
-            if (T == 0)
-                *cnt = 0;
-            __syncwarp();
-#pragma unroll
-            for (int r = 0; r < 32; r++) {
-                const int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
-                const u32 Dv = (u32)(dv + (int)A.dig_off);
-                if ((Dv >> wsh) & 1)
-                    lst[atomicAdd(cnt, 1u)] = (unsigned short)(T + TPN * r);
-            }
-        }
         // ---- phase 1: decompose + forward NTT of the DK digit polynomials of component j ---------------------
 #ifdef CGGI32_UNROLL_L
 #pragma unroll
@@ -446,34 +402,12 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 #pragma unroll
                 for (int g0 = 0; g0 < G; g0 += GB) {
                     u32 xd[GB][D], m1[GB], m2[GB], dl0[GB], dl1[GB];
-                    u32 xt[WRAP ? GB : 1][2];   // WRAP: the uncorrected accumulator rows
 #pragma unroll
                     for (int b = 0; b < GB; b++) {
                         const u32* dreg = Dsm + (size_t)(g0 + b) * D * RS + pk;
 #pragma unroll
                         for (int l = 0; l < D; l++)
                             xd[b][l] = dreg[(size_t)l * RS];
-                        if (WRAP) {
-                            // the accumulator rows enter the products as NTT(c - B^d e) / N, e = indicator polynomial of
-                            // the wrapped coefficients: subtract (B^d / N) psi^((2 br + 1) k0) per listed k0.  Only the
-                            // operand is corrected; the stored accumulator (xt) keeps accumulating delta.
-#pragma unroll
-                            for (int jj = 0; jj < 2; jj++) {
-                                xt[b][jj] = xd[b][2 * (DK - 1) + jj];
-                                const u32 cw = wcnt[(g0 + b) * 2 + jj];
-                                if (cw) {
-                                    const unsigned short* lst = wlist + (size_t)((g0 + b) * 2 + jj) * N;
-                                    u32 sum = 0;
-#pragma unroll 1
-                                    for (u32 w = 0; w < cw; w++) {
-                                        const u32 x = ((2 * br + 1) * (u32)lst[w]) & (2 * N - 1);
-                                        sum = cond_sub(sum + psiK[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))], Q);
-                                    }
-                                    const u32 y = xt[b][jj];
-                                    xd[b][2 * (DK - 1) + jj] = y >= sum ? y - sum : y + Q - sum;
-                                }
-                            }
-                        }
                         const u32 e = es[(g0 + b) * n + i];
                         const u32 xx = ((2 * br + 1) * e) & (2 * N - 1);
                         const u32 x2 = (2 * N - xx) & (2 * N - 1);
@@ -500,8 +434,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                         dl0[b] = redc_full((u64)r00 * a1 + (u64)r10 * a2);
                         dl1[b] = redc_full((u64)r01 * a1 + (u64)r11 * a2);
                         if (SKIP) {   // acc_eval += delta (kept canonical); its old value is the top row just loaded
-                            m1[b] = cond_sub((WRAP ? xt[b][0] : xd[b][2 * (DK - 1)]) + dl0[b], Q);
-                            m2[b] = cond_sub((WRAP ? xt[b][1] : xd[b][2 * (DK - 1) + 1]) + dl1[b], Q);
+                            m1[b] = cond_sub(xd[b][2 * (DK - 1)] + dl0[b], Q);
+                            m2[b] = cond_sub(xd[b][2 * (DK - 1) + 1] + dl1[b], Q);
                         }
                     }
 #pragma unroll
@@ -778,35 +712,6 @@ static cudaError_t launch_sweep(const CGGI32Args& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// top-digit elimination with wrap repair (see the kernel header): extra shared memory for the second psi table, the
-// bitmaps and the flags behind the rotation exponents
-template <int LOGN, int DK, int G, int SW>
-static cudaError_t launch_wrap(const CGGI32Args& a, cudaStream_t s) {
-    using K = KCfg<LOGN, DK, G>;
-    const size_t smem = K::ring_offset((int)a.c.n) + (size_t)2 * K::N * 4 + (size_t)2 * G * 4 + (size_t)2 * G * K::N * 2 + 64;
-    if (smem > 227 * 1024)
-        return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G, true, false, false, SW, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess)
-        return e;
-    br_cggi32_kernel<LOGN, DK, G, true, false, false, SW, true><<<(a.c.batch + G - 1) / G, K::NT, smem, s>>>(a);
-    return cudaGetLastError();
-}
-// which parameter sets take that path: top digit not exact but repairable, one of the instantiated shapes
-bool cggi32_wrapfix_shape(const tfhe_b200_params& p) {
-    if (!cggi32_supported(p) || cggi32_skip_top_ok(p) || !cggi_skip_top_wrapfix_ok(p))
-        return false;
-    u32 gbits = 0;
-    while ((1ULL << gbits) < p.baseG)
-        gbits++;
-    if (gbits * p.digitsG >= 32)   // the wrap flag is bit gBits * digits of a 32-bit value
-        return false;
-    const bool sweep = cggi32_needs_sweep(p.Q);
-    return (p.N == 512 && p.digitsG == 3 && !sweep) || (p.N == 1024 && p.digitsG == 3 && !sweep) ||
-           (p.N == 1024 && p.digitsG == 4 && sweep);
-}
-
 // N = 2048 (STD256 family): four digits with top-digit elimination, two ciphertexts per CTA (8 warps)
 template <int SW>
 static cudaError_t launch_n2048(const CGGI32Args& a, cudaStream_t s) {
@@ -867,17 +772,7 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     a.dig_add = t.mod.Q - B / 2;
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
-    a.kfixM = (u32)h_mulmod((u64)(pw % t.mod.Q), h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod.Q);
     const int dk = (int)c.digitsKept;
-    if (t.wrap) {   // top-digit elimination with wrap repair: throughput shapes of the sets that need it
-        if (c.logN == 9 && dk == 3)
-            return launch_wrap<9, 3, 8, 0>(a, s);
-        if (c.logN == 10 && dk == 3 && !cggi32_needs_sweep(t.mod.Q))
-            return launch_wrap<10, 3, 4, 0>(a, s);
-        if (c.logN == 10 && dk == 4 && cggi32_needs_sweep(t.mod.Q))
-            return launch_wrap<10, 4, 4, 1>(a, s);
-        return cudaErrorInvalidConfiguration;
-    }
     if (c.logN == 11) {
         if (dk != 4 || !t.skip_top)
             return cudaErrorInvalidConfiguration;

@@ -176,7 +176,6 @@ struct tfhe_b200_handle {
     bool is64 = false;
     bool have_cggi32 = false;
     bool skip_top = false;
-    bool wrap32 = false;         // 32-bit CGGI kernel eliminates the top digit with wrap repair
     bool have_dm32 = false;
     bool have_dm64w = false;     // AP/DM on the N = 2048 rings (br_dm64w.cu), 64-bit words
     bool have_cggi64 = false;
@@ -679,7 +678,7 @@ extern "C" const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h) {
     if (!h)
         return "";
     if (h->have_cggi32 && !h->force_generic)
-        return h->skip_top ? (h->wrap32 ? "cggi_u32_ntt32_skiptop_wrapfix" : "cggi_u32_ntt32_skiptop") : "cggi_u32_ntt32";
+        return h->skip_top ? "cggi_u32_ntt32_skiptop" : "cggi_u32_ntt32";
     if (h->have_dm32 && !h->force_generic)
         return h->skip_top ? "dm_u32_ntt32_skiptop" : "dm_u32_ntt32";
     if (h->have_dm64w && !h->force_generic)
@@ -825,9 +824,7 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
     h->have_cggi64 = h->is64 && cggi64_supported(p) && !getenv("TFHE_B200_NO_CGGI64");
     h->have_dm32 = !h->is64 && dm32_supported(p) && !getenv("TFHE_B200_NO_DM32");
     h->have_dm64w = h->is64 && dm64w_supported(p) && !getenv("TFHE_B200_NO_DM64");
-    h->wrap32 = h->have_cggi32 && cggi32_wrapfix_shape(p) && !getenv("TFHE_B200_NO_WRAP32") &&
-                !getenv("TFHE_B200_NO_SKIPTOP");
-    h->skip_top = ((h->have_cggi32 && (cggi32_skip_top_ok(p) || h->wrap32)) || (h->have_dm32 && cggi32_skip_top_ok(p)) || (h->have_dm64w && cggi32_skip_top_ok(p)) ||
+    h->skip_top = ((h->have_cggi32 && cggi32_skip_top_ok(p)) || (h->have_dm32 && cggi32_skip_top_ok(p)) || (h->have_dm64w && cggi32_skip_top_ok(p)) ||
                    (h->have_cggi64 && (cggi32_skip_top_ok(p) || cggi_skip_top_wrapfix_ok(p)))) &&
                   !getenv("TFHE_B200_NO_SKIPTOP");
     h->have_cggi64w = h->have_cggi64 && (h->skip_top ? cggi64w_supported(p) : cggi64w_plain_supported(p)) &&
@@ -1160,7 +1157,6 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
     if (h->have_cggi32 && !h->force_generic) {
         CGGI32Tables t;
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB; t.skip_top = h->skip_top;
-        t.wrap = h->wrap32;
         CUDA_TRY(launch_br_cggi32(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_dm32 && !h->force_generic) {

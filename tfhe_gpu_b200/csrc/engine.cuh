@@ -64,14 +64,12 @@ struct CGGI32Tables {
     const u32* psi_pow;   // [2N] Montgomery form
     const u32* twB;       // per-thread pass-B twiddles + Shoup companions, forward
     bool skip_top;        // keys were transformed for top-digit elimination (see br_cggi32.cu)
-    bool wrap = false;    // ... and the top digit can wrap: the kernel repairs it on the fly (WRAP variants)
     const u32* twA;       // HOST pointer: uniform pass-A twiddles + companions [fwd|inv][32][2] (kernel params)
 };
 bool cggi32_supported(const tfhe_b200_params& p);
 // moduli between 2^32/22 and 2^28 run the cggi32 variant with a mid-transform reduction sweep (ntt32.cuh)
 inline bool cggi32_needs_sweep(u64 Q) { return Q >= (1ULL << 32) / 22; }
 bool cggi32_skip_top_ok(const tfhe_b200_params& p);
-bool cggi32_wrapfix_shape(const tfhe_b200_params& p);   // elimination with wrap repair on the 32-bit CGGI kernel
 bool cggi_skip_top_wrapfix_ok(const tfhe_b200_params& p);   // top digit may wrap but the 64-bit kernel can repair it
 cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStream_t s, int sm_count, int group);
 bool dm32_supported(const tfhe_b200_params& p);
