@@ -31,7 +31,6 @@ struct DM32Args {
     u32 twA_f[32][2];
     u32 twA_i[32][2];
     u32 Q2, dig_off, dig_add, ninvM, zero;
-    u32 l2_prefetch;     // pull every step's key row towards L2 ahead of the pointwise stage (TFHE_B200_DM_PREFETCH=0: off)
 };
 
 // LAT = true: latency layout for batches of at most one ciphertext per SM (same idea as br_cggi32.cu): G = 1, 2*DK
@@ -202,14 +201,6 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
         const int row = kidx[g * steps + s];        // uniform over the ciphertext's threads
         if (row < 0)
             continue;
-        // The step's whole key row (P * N * 16 B) is pulled towards L2 now: with the large DM keys (2-46 GB) most rows come
-        // from HBM, and the forward transforms that follow cover that latency; the pointwise loads then hit L2.
-        if (A.l2_prefetch) {
-            const uint4* rowp = reinterpret_cast<const uint4*>(A.bk) + (size_t)row * P * N;
-#pragma unroll 1
-            for (int ln = lt; ln < P * N / 8; ln += CT_THREADS)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + 8 * ln));
-        }
         // key words of the first pointwise iteration: requested now, consumed after the forward transforms
         const uint4* kp = reinterpret_cast<const uint4*>(A.bk) + (size_t)row * P * N + lt;
         uint4 cur[P];
@@ -413,10 +404,6 @@ cudaError_t launch_br_dm32(const BRCommon& c, const CGGI32Tables& t, cudaStream_
     a.dig_add = t.mod.Q - B / 2;
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
-    {
-        const char* pf = getenv("TFHE_B200_DM_PREFETCH");
-        a.l2_prefetch = pf ? (u32)atoi(pf) : 1;
-    }
     {
         const bool sweep = cggi32_needs_sweep(t.mod.Q), plain = !t.skip_top;
         const int dk = (int)c.digitsKept;

@@ -39,7 +39,6 @@ struct DM64WArgs {
     const u64* twB;
     const u64* twU;
     u64 Q2, dig_off, dig_add, ninvM, zero64;
-    u32 l2_prefetch;     // TFHE_B200_DM_PREFETCH=0 switches the per-step key-row prefetch off
 };
 
 // PLAIN = true: no top-digit elimination (two digits whose top digit can wrap: STD128Q / STD128Q_OPT): all DK digits of
@@ -163,14 +162,6 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_dm64w_kernel(const __grid
             if (a0 == 0)
                 continue;
             const size_t row = ((size_t)i * baseR + a0) * digitsR + k;
-            // pull the step's key row (D * N * 16 B, mostly HBM-resident: the DM keys are 4-46 GB) towards L2 now; the
-            // forward transforms cover the latency and the pointwise loads hit L2
-            if (A.l2_prefetch) {
-                const ulonglong2* rowp = reinterpret_cast<const ulonglong2*>(A.bk) + row * (size_t)D * N;
-#pragma unroll 1
-                for (int ln = lt; ln < D * N / 8; ln += CT_THREADS)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + 8 * ln));
-            }
             // ---- phase 1: digits 0..DK-2 of component j -> forward transforms -------------------------------------
             if (NF > 1) {
                 u64* park = myD + (size_t)j * N;
@@ -338,10 +329,6 @@ cudaError_t launch_br_dm64w(const BRCommon& c, const CGGI64WTables& t, cudaStrea
     a.dig_add = t.mod.Q - B / 2;
     a.zero64 = 0;
     a.ninvM = to_mont<u64>(h_powmod((u64)w64::N, t.mod.Q - 2, t.mod.Q), t.mod);
-    {
-        const char* pf = getenv("TFHE_B200_DM_PREFETCH");
-        a.l2_prefetch = pf ? (u32)atoi(pf) : 1;
-    }
     const bool one = group == 1 || (group == 0 && sm_count > 0 && c.batch <= sm_count);
     if (c.digitsKept == 2) {
         if (!t.plain)
