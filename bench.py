@@ -556,7 +556,8 @@ def main():
         h2d, d2h = wl.io_bytes(count)
         line = {
             "metric": wl.metric, "value": value, "unit": wl.unit,
-            "n_gpus": n_gpus, "steps": args.steps, "warmup": warmup, "ms_per_step": dt / args.steps * 1e3,
+            "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup, "warmup_done": warmup,
+            "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32" if p.Q < (1 << 32) else "u64", "data": "synthetic",
             "config": {"workload": f"{wl.desc}{'(' + args.gate + ')' if wl.kind == 'gate' else ''}, batch "
