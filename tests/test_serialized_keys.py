@@ -61,6 +61,45 @@ def test_malformed_streams_are_refused():
         serialized_info(bytes(bad), ksks)
 
 
+@pytest.mark.parametrize("name", ["ginx", "ap"])
+def test_corrupted_streams_never_crash_the_reader(name):
+    """Key files come from outside: random truncations, byte flips and hostile length fields (huge vector sizes) must
+    end in a TfheB200Error or in a successful parse -- never in a crash, a hang or an absurd allocation."""
+    from tfhe_gpu_b200 import TfheB200Error, flatten_serialized, serialized_info
+
+    _, bks, ksks, _ = _fixture(name)
+    rng = np.random.default_rng(7)
+
+    def attempt(b, k):
+        try:
+            info = serialized_info(b, k)
+            assert info.bk_words < (1 << 32) and info.ksk_words < (1 << 32)
+            if info.bk_words * 8 <= 4 * len(b) and info.ksk_words * 8 <= 4 * len(k):
+                flatten_serialized(b, k)
+        except TfheB200Error:
+            pass
+
+    for _ in range(60):
+        for which in (0, 1):
+            src = bytearray(bks if which == 0 else ksks)
+            kind = rng.integers(0, 4)
+            if kind == 0:                                   # truncate
+                src = src[:int(rng.integers(0, len(src)))]
+            elif kind == 1:                                 # flip a few bytes in the structural head of the stream
+                for pos in rng.integers(0, min(len(src), 400), 3):
+                    src[int(pos)] ^= int(rng.integers(1, 256))
+            elif kind == 2:                                 # flip bytes anywhere
+                for pos in rng.integers(0, len(src), 4):
+                    src[int(pos)] ^= int(rng.integers(1, 256))
+            else:                                           # hostile 64-bit length field somewhere in the head
+                pos = int(rng.integers(1, min(len(src), 300) - 8))
+                src[pos:pos + 8] = int(rng.integers(1 << 40, 1 << 63)).to_bytes(8, "little")
+            if which == 0:
+                attempt(bytes(src), ksks)
+            else:
+                attempt(bks, bytes(src))
+
+
 @pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libtfhe_ref.so not built")
 @pytest.mark.parametrize("method", [po.GINX, po.AP])
 def test_fresh_reference_streams_round_trip(method, tmp_path):

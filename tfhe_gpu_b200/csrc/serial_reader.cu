@@ -49,7 +49,9 @@ struct Cursor {
         }
         return false;
     }
-    bool need(size_t k) { return (ok && pos + k <= n) ? true : fail("serialized stream is truncated"); }
+    bool need(size_t k) { return (ok && k <= n - pos) ? true : fail("serialized stream is truncated"); }
+    // `count` 8-byte words (no overflow for hostile counts)
+    bool need_words(u64 count) { return (ok && count <= (n - pos) / 8) ? true : fail("serialized stream is truncated"); }
     u32 get_u8() {
         if (!need(1))
             return 0;
@@ -156,7 +158,7 @@ int index_serialized_acc_key(const void* data, size_t bytes, SerializedAccKey* o
                             k.N = len;
                         else if (len != k.N)
                             c.fail("polynomials of different length");
-                        if (!c.need(len * 8))
+                        if (!c.need_words(len))
                             break;
                         offs.push_back(c.pos);
                         c.pos += len * 8;
@@ -230,7 +232,7 @@ int index_serialized_switch_key(const void* data, size_t bytes, SerializedSwitch
             const u64 dks = c.get_u64();
             if (i == 0 && a == 0) {
                 k.dKS = dks;
-                if (c.ok && dks <= 64)
+                if (c.ok && dks <= 64 && k.N * k.baseKS * dks <= bytes / 8)   // a row takes at least 8 bytes of stream
                     k.rowA_off.reserve((size_t)(k.N * k.baseKS * dks));
             }
             else if (dks != k.dKS)
@@ -244,7 +246,7 @@ int index_serialized_switch_key(const void* data, size_t bytes, SerializedSwitch
                     k.n = len;
                 else if (len != k.n)
                     c.fail("key switching rows of different length");
-                if (!c.need(len * 8))
+                if (!c.need_words(len))
                     break;
                 k.rowA_off.push_back(c.pos);
                 c.pos += len * 8;
@@ -266,7 +268,7 @@ int index_serialized_switch_key(const void* data, size_t bytes, SerializedSwitch
         for (u64 a = 0; c.ok && a < k.baseKS; a++) {
             if (c.get_u64() != k.dKS)
                 c.fail("switching key: A and B disagree");
-            if (!c.need(k.dKS * 8))
+            if (!c.need_words(k.dKS))
                 break;
             k.rowB_off.push_back(c.pos);
             c.pos += k.dKS * 8;
