@@ -355,3 +355,36 @@ def test_cggi32_tma_key_ring_variant(rng, monkeypatch):
         assert np.array_equal(tma, want)
     finally:
         g.GPUClean()
+
+
+@pytest.mark.parametrize("N,baseG", [(1024, 1 << 7), (512, 1 << 9)])        # headline shape (top digit eliminated) / TOY shape
+def test_cggi32_persistent_variant(N, baseG, rng):
+    """Persistent blind rotation (br_cggi32_kernel<..., PERS>): the groups x n rotation steps of a launch are cut into
+    equal ranges, one per CTA, so groups are split between neighbouring CTAs at arbitrary steps and handed over through
+    the accumulator image.  Forced here with few CTAs on a short LWE dimension: every split position, ragged last
+    group, gate / per-ciphertext LUT / explicit accumulators -- all bit-exact against the oracle and the plain launch."""
+    p = po.Port.params_custom(13, N, N, Q27, 128, baseG, 32, po.GINX)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant.startswith("cggi_u32_ntt32")
+        q, n = p.q, p.n
+        per_cta = 4 if N == 1024 else 8
+        batch = 7 * per_cta - 3                                             # seven groups, the last one ragged
+        c1 = rng.integers(0, q, (batch, n + 1), dtype=np.uint64)
+        c2 = rng.integers(0, q, (batch, n + 1), dtype=np.uint64)
+        want = port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, q)
+        tab = rng.integers(0, q, (batch, q), dtype=np.uint64)
+        want_f = port.bootstrap_func(bk, ksk, c1, q, tab, q)
+        acc = rng.integers(0, p.Q, (batch, 2, N), dtype=np.uint64)
+        want_a = port.eval_acc(bk, c1[:, :n].copy(), q, acc)
+        for ctas in (2, 3, 4, 5, 6, 7):                                     # 7 x 13 steps over `ctas` ranges
+            g.set_option("persistent_ctas", ctas)
+            assert np.array_equal(g.EvalBinGate("NAND", c1, c2), want), ctas
+            assert np.array_equal(g.BootstrapFunc(c1, q, tab, q), want_f), ctas
+            assert np.array_equal(g.EvalAcc(c1[:, :n].copy(), q, acc), want_a), ctas
+        g.set_option("persistent_ctas", 0)
+        g.set_option("persistent", 0)
+        assert np.array_equal(g.EvalBinGate("NAND", c1, c2), want)
+    finally:
+        g.GPUClean()

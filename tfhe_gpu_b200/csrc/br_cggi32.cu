@@ -24,6 +24,15 @@
 
 #include "ntt32.cuh"
 
+// Words per entry of the monomial-factor table in shared memory (phase 2):
+//   1: psi^x (Montgomery form); the two factors psi^x - 1 and psi^-x - 1 are two lookups plus a modular subtraction each
+//   2: (psi^x - 1, psi^-x - 1): one index computation, one 64-bit lookup, no subtraction
+//   4: (a1 R, a1, a2 R, a2) with a = psi^(+-x) - 1: the four 64-bit sums of a slot are folded straight into the two outputs
+//      as hi(s) * (a R) + lo(s) * a (s = hi 2^32 + lo, R = 2^32) with ONE reduction per output instead of three
+#ifndef CGGI32_TABW
+#define CGGI32_TABW 1
+#endif
+
 namespace tfhe_b200 {
 
 struct CGGI32Args {
@@ -39,6 +48,11 @@ struct CGGI32Args {
     u32 dig_add;         // Q - B/2 (digits are fed to the lazy NTT as r + Q)
     u32 ninvM;           // N^-1 in Montgomery form (SKIP: the evaluation-domain accumulator is kept scaled by N^-1)
     u32 zero;            // always 0: third IADD3 operand that keeps ptxas from turning adds into IMAD.IADD (fma-heavy pipe)
+    // persistent variant (PERS): hand-over slots of the groups that are split between two CTAs, see the kernel header
+    u32* pers_state;     // [slot][2][G][2][N] accumulator image: coefficient registers, evaluation-domain rows (SKIP path)
+    u32* pers_flags;     // [slot] launch epoch once the slot's image is complete
+    u32 pers_epoch;
+    u32 pers_groups;     // ceil(batch / G)
 };
 
 // ---- TMA bulk copies + mbarriers (key streaming of the TMA variant) ----------------------------------------------
@@ -91,17 +105,30 @@ __device__ __forceinline__ void tma_bulk_g2s(u32 dst, const void* src, u32 bytes
 // LOGN = 11 (N = 2048: the STD256 family, binfhecontext.cpp:147-148,153-154): 64 threads x 32 coefficients per
 // polynomial, i.e. two warps per (ciphertext, component); the transposes are fenced by a 64-thread named barrier and one
 // cross-lane stage sits between the two in-thread passes (cross_stage in ntt32.cuh).
-template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, int SWEEP = 0>
+//
+// PERS = true (persistent variant, no wave quantisation): CTAs walk the n steps of a group in lock-step, so a plain
+// launch costs ceil(groups / SMs) wave times whatever the remainder.  Here the grid is ONE CTA per SM and the
+// groups * n rotation steps of the launch are cut into gridDim.x equal contiguous ranges (McNaughton's wrap-around rule
+// for preemptive scheduling): a CTA's range is the last steps of group gA, whole groups, and the first sB steps of group
+// gB.  It runs the head of gB FIRST (and leaves the accumulator image in its hand-over slot), then its whole groups,
+// then the rest of gA LAST, whose head the previous CTA ran at the very start of the launch -- a range is at least n
+// steps long, so that image has been waiting since long before it is needed (the flag wait is a formality) and the two
+// parts of a group never overlap in time.  Every CTA finishes at the same moment: groups * n / SMs step times instead
+// of ceil(groups / SMs) * n.  The image is the coefficient registers plus, on the SKIP path, the evaluation-domain rows:
+// the very words the next step would have read, so the results are bit-exact by construction.
+template <int LOGN, int DK, int G, bool SKIP, bool TMA = false, bool LAT = false, int SWEEP = 0, bool PERS = false>
 __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN, DK, G>::NT, 1)
     br_cggi32_kernel(const __grid_constant__ CGGI32Args A) {
     using K = KCfg<LOGN, DK, G>;
     constexpr int N = K::N, TPN = K::TPN, PB = K::PB, NTW = K::NTW, D = K::D, RS = K::RS;
     constexpr int NT = LAT ? 2 * DK * TPN : K::NT;
     static_assert(!LAT || (G == 1 && SKIP && !TMA && DK >= 2), "latency layout: one ciphertext per CTA, skip-top path");
+    static_assert(!PERS || (!LAT && !TMA), "persistent variant: throughput shapes with register-staged key loads");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u32* Dsm = reinterpret_cast<u32*>(smem_raw);                      // [G][D][RS]
-    u32* psiM = Dsm + (size_t)G * D * RS;                             // [2N]
-    unsigned short* es = reinterpret_cast<unsigned short*>(psiM + 2 * N);  // [G][n] rotation exponents
+    constexpr int TABW = TMA ? 1 : CGGI32_TABW;                       // words per monomial-factor entry (see the top of the file)
+    u32* psiM = Dsm + (size_t)G * D * RS;                             // [2N][TABW]
+    unsigned short* es = reinterpret_cast<unsigned short*>(psiM + 2 * N * TABW);  // [G][n] rotation exponents
     // TMA variant: key ring [2][D][NT] uint4 and 4 mbarriers (full[2], empty[2]) behind the exponents, 128-byte aligned
     uint4* ring = reinterpret_cast<uint4*>(smem_raw + K::ring_offset((int)A.c.n));
     const u32 bar0 = smem_u32(ring + 2 * D * NT);
@@ -128,21 +155,35 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     const int T = tid % TPN;               // thread index within the NTT
     const int pbar = 1 + 2 * g + j;        // named barrier of this polynomial's threads (N = 2048 only)
     const bool odd_lane = tid & 1;
-    const int ct = blockIdx.x * G + g;
-    const bool live = ct < C.batch;
-    const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
 
-    // ---- one-time loads: psi-power table, rotation exponents, per-thread twiddles --------------------------
-    for (int x = tid; x < 2 * N; x += NT)
-        psiM[((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4))] = A.psi_pow[x];
-    {
-        // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
-        const u32 mod = (u32)C.ct_mod, fac = (2 * N) / mod;
-        const int lt = tid % (2 * TPN);
-        for (u32 i = lt; i < n; i += 2 * TPN) {
-            u32 ai = (u32)(lwe[i] % mod);
-            u32 e = ((mod - ai) % mod) * fac;
-            es[g * n + i] = live ? (unsigned short)e : 0;
+    // ---- persistent variant: this CTA's range of the launch's groups * n rotation steps ----------------------------
+    u32 gA = 0, sA = 0, gB = 0, sB = 0, first_full = 0;
+    int n_full = 0, n_items = 1;
+    if (PERS) {
+        const u64 Wt = (u64)A.pers_groups * n;
+        const u64 lo = Wt * blockIdx.x / gridDim.x, hi = Wt * (blockIdx.x + 1) / gridDim.x;
+        gA = (u32)(lo / n); sA = (u32)(lo % n); gB = (u32)(hi / n); sB = (u32)(hi % n);
+        first_full = gA + (sA ? 1 : 0);
+        n_full = (int)gB - (int)first_full;
+        n_items = (sB ? 1 : 0) + n_full + (sA ? 1 : 0);
+    }
+
+    // ---- one-time loads: psi-power table, per-thread twiddles ------------------------------------------------
+    // bit-rotated index: the distinct exponents a warp touches differ in their top bits only, which become the low
+    // index bits so that they fall into distinct banks (16 x 4 B, 16 x 8 B per half-warp, 8 x 16 B per quarter-warp)
+    constexpr int TB = TABW == 4 ? 3 : 4;
+    auto tab_index = [&](u32 x) -> u32 { return ((x & (2 * N / (1 << TB) - 1)) << TB) | (x >> (LOGN + 1 - TB)); };
+    for (int x = tid; x < 2 * N; x += NT) {
+        if (TABW == 1)
+            psiM[tab_index(x)] = A.psi_pow[x];
+        else {
+            u32 a1 = A.psi_pow[x], a2 = A.psi_pow[(2 * N - x) & (2 * N - 1)];
+            a1 = a1 >= oneM ? a1 - oneM : a1 + Q - oneM;
+            a2 = a2 >= oneM ? a2 - oneM : a2 + Q - oneM;
+            if (TABW == 2)
+                reinterpret_cast<uint2*>(psiM)[tab_index(x)] = make_uint2(a1, a2);
+            else
+                reinterpret_cast<uint4*>(psiM)[tab_index(x)] = make_uint4(a1, A.mod.mont_mul(a1, 1), a2, A.mod.mont_mul(a2, 1));
         }
     }
     u32 tw[32], twp[32];
@@ -155,10 +196,41 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             twp[x] = w.y;
         }
     }
+    u32* const myD = Dsm + (size_t)g * D * RS;
+    const u32 QHalf = Q >> 1;
+    const u32 gBits = C.gBits, gmask = (1u << gBits) - 1;
+    u32 c[32];
+    u32 bk_pre[TMA ? 1 : 4 * D];   // key slice of (step, slot tid), requested one step ahead (register-staged variant)
+
+    for (int item = 0; item < n_items; item++) {
+    // this item: rotation steps [sb, se) of group grp (the whole rotation unless PERS)
+    u32 grp = blockIdx.x, sb = 0, se = n;
+    if (PERS) {
+        const int u = item - (sB ? 1 : 0);
+        if (u < 0) { grp = gB; se = sB; }
+        else if (u < n_full) grp = first_full + (u32)u;
+        else { grp = gA; sb = sA; }
+        __syncthreads();   // the previous item is done with the exponents and the digit regions
+    }
+    const int ct = (int)grp * G + g;
+    const bool live = ct < C.batch;
+    const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
+    {
+        // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
+        const u32 mod = (u32)C.ct_mod, fac = (2 * N) / mod;
+        const int lt = tid % (2 * TPN);
+        for (u32 i = lt; i < n; i += 2 * TPN) {
+            u32 ai = (u32)(lwe[i] % mod);
+            u32 e = ((mod - ai) % mod) * fac;
+            es[g * n + i] = live ? (unsigned short)e : 0;
+        }
+    }
 
     // ---- accumulator initialisation in A layout (coefficient idx = T + TPN*r) --------------------------------
-    u32 c[32];
-    if (C.acc_init == ACC_EXPLICIT) {
+    if (PERS && sb > 0) {
+        // resumed group: the accumulator comes from the hand-over slot (below)
+    }
+    else if (C.acc_init == ACC_EXPLICIT) {
         const u64* src = C.acc_io + ((size_t)(live ? ct : 0) * 2 + j) * N;
 #pragma unroll
         for (int r = 0; r < 32; r++)
@@ -202,9 +274,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     }
     __syncthreads();
 
-    u32 bk_pre[TMA ? 1 : 4 * D];   // key slice of (step, slot tid), requested one step ahead (register-staged variant)
     if (!TMA) {
-        const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + tid;
+        const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (PERS ? (size_t)sb * D * N : (size_t)0) + tid;
 #pragma unroll
         for (int x = 0; x < D; x++) {
             uint4 w = __ldg(p4 + (size_t)x * N);
@@ -216,11 +287,38 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
         if (total_fills > 1)
             issue_fill(1);
     }
-    u32* myD = Dsm + (size_t)g * D * RS;
-    const u32 QHalf = Q >> 1;
-    const u32 gBits = C.gBits, gmask = (1u << gBits) - 1;
 
-    if (SKIP) {
+    if (PERS && sb > 0) {
+        // the head of this group was run by the previous CTA at the start of the launch: wait for its image
+        const u32 slot = blockIdx.x - 1;
+        if (tid == 0) {
+            u32 f, spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(A.pers_flags + slot) : "memory");
+                if (f == A.pers_epoch)
+                    break;
+                __nanosleep(200);
+                if (++spins > (1u << 26))   // ~20 s: cannot happen (CTA k-1 is dispatched before CTA k and fills the slot
+                    __trap();               // first thing); fail the launch loudly rather than hang or return garbage
+            }
+        }
+        __syncthreads();
+        // image: [slot][2][G][2][N] words -- the coefficient registers, then (SKIP path) the evaluation-domain rows
+        const uint4* src4 = reinterpret_cast<const uint4*>(A.pers_state) + (((size_t)slot * 2 * G + g) * 2 + j) * (N / 4) + T * 8;
+#pragma unroll
+        for (int x = 0; x < 8; x++) {
+            const uint4 w = __ldcg(src4 + x);
+            c[4 * x] = w.x; c[4 * x + 1] = w.y; c[4 * x + 2] = w.z; c[4 * x + 3] = w.w;
+        }
+        if (SKIP) {
+            uint4* p4 = reinterpret_cast<uint4*>(myD + (size_t)(2 * (DK - 1) + j) * RS + 36 * T);
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+                p4[x] = __ldcg(src4 + (size_t)G * 2 * (N / 4) + x);
+            __syncthreads();
+        }
+    }
+    else if (SKIP) {
         // Top-digit elimination.  With no digits thrown and B^(DK-1) * (B/2 - 1) > Q/2 the signed digits satisfy
         // c = sum_l d_l B^l EXACTLY (the top digit never wraps), hence NTT(d_top) = B^-(DK-1) (NTT(c) - sum_{l<top}
         // B^l NTT(d_l)).  Substituting into sum_l NTT(d_l) BK_l gives sum_{l<top} NTT(d_l) BK'_l + NTT(c) BK'_top
@@ -282,7 +380,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     }
 
     // =========================================================================================================
-    for (u32 i = 0; i < n; i++) {
+    for (u32 i = sb; i < se; i++) {
         // ---- phase 1: decompose + forward NTT of the DK digit polynomials of component j ---------------------
 #ifdef CGGI32_UNROLL_L
 #pragma unroll
@@ -402,6 +500,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 #pragma unroll
                 for (int g0 = 0; g0 < G; g0 += GB) {
                     u32 xd[GB][D], m1[GB], m2[GB], dl0[GB], dl1[GB];
+                    u32 n1[TABW == 4 ? GB : 1], n2[TABW == 4 ? GB : 1];   // TABW = 4: the plain-form factors
 #pragma unroll
                     for (int b = 0; b < GB; b++) {
                         const u32* dreg = Dsm + (size_t)(g0 + b) * D * RS + pk;
@@ -410,11 +509,21 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                             xd[b][l] = dreg[(size_t)l * RS];
                         const u32 e = es[(g0 + b) * n + i];
                         const u32 xx = ((2 * br + 1) * e) & (2 * N - 1);
-                        const u32 x2 = (2 * N - xx) & (2 * N - 1);
-                        // psi-power table is stored bit-rotated (low LOGN-3 bits <-> high 4 bits) so that the 16 distinct
-                        // exponents a warp touches (they differ by multiples of 2N/16) fall into distinct banks
-                        m1[b] = psiM[((xx & (2 * N / 16 - 1)) << 4) | (xx >> (LOGN + 1 - 4))];
-                        m2[b] = psiM[((x2 & (2 * N / 16 - 1)) << 4) | (x2 >> (LOGN + 1 - 4))];
+                        // the table is stored bit-rotated (see tab_index) so that the distinct exponents a warp touches
+                        // (they differ by multiples of 2N/16) fall into distinct banks
+                        if (TABW == 1) {
+                            const u32 x2 = (2 * N - xx) & (2 * N - 1);
+                            m1[b] = psiM[tab_index(xx)];
+                            m2[b] = psiM[tab_index(x2)];
+                        }
+                        else if (TABW == 2) {
+                            const uint2 w = reinterpret_cast<const uint2*>(psiM)[tab_index(xx)];
+                            m1[b] = w.x; m2[b] = w.y;
+                        }
+                        else {
+                            const uint4 w = reinterpret_cast<const uint4*>(psiM)[tab_index(xx)];
+                            m1[b] = w.x; n1[b] = w.y; m2[b] = w.z; n2[b] = w.w;
+                        }
                     }
 #pragma unroll
                     for (int b = 0; b < GB; b++) {
@@ -427,12 +536,27 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                             s10 += (u64)x * bkv[(1 * D + l) * 2 + 0];
                             s11 += (u64)x * bkv[(1 * D + l) * 2 + 1];
                         }
+                        if (TABW == 4) {
+                            // s = hi R + lo, so s a R^-1 = (hi (a R) + lo a) R^-1: fold the monomial factors into the sums
+                            // before the one reduction.  Bounds: s < 8 * 24 Q * Q < 2^62, hi < 2^30, the four products
+                            // stay below 2 (2^31 + 2^32) Q = 3 Q 2^32 < 2^63 for any s < 2^63; REDC leaves less than 3 Q + Q.
+                            const u32 A1 = m1[b], B1 = n1[b], A2 = m2[b], B2 = n2[b];
+                            const u64 t0 = (u64)(u32)(s00 >> 32) * A1 + (u64)(u32)s00 * B1 + (u64)(u32)(s10 >> 32) * A2 + (u64)(u32)s10 * B2;
+                            const u64 t1 = (u64)(u32)(s01 >> 32) * A1 + (u64)(u32)s01 * B1 + (u64)(u32)(s11 >> 32) * A2 + (u64)(u32)s11 * B2;
+                            u32 d0 = redc_lazy(t0), d1 = redc_lazy(t1);
+                            dl0[b] = cond_sub(cond_sub(d0, Q2), Q);
+                            dl1[b] = cond_sub(cond_sub(d1, Q2), Q);
+                        }
+                        else {
                         const u32 r00 = redc_lazy(s00), r01 = redc_lazy(s01), r10 = redc_lazy(s10), r11 = redc_lazy(s11);
                         u32 a1 = m1[b], a2 = m2[b];
-                        a1 = a1 >= oneM ? a1 - oneM : a1 + Q - oneM;
-                        a2 = a2 >= oneM ? a2 - oneM : a2 + Q - oneM;
+                        if (TABW == 1) {
+                            a1 = a1 >= oneM ? a1 - oneM : a1 + Q - oneM;
+                            a2 = a2 >= oneM ? a2 - oneM : a2 + Q - oneM;
+                        }
                         dl0[b] = redc_full((u64)r00 * a1 + (u64)r10 * a2);
                         dl1[b] = redc_full((u64)r01 * a1 + (u64)r11 * a2);
+                        }
                         if (SKIP) {   // acc_eval += delta (kept canonical); its old value is the top row just loaded
                             m1[b] = cond_sub(xd[b][2 * (DK - 1)] + dl0[b], Q);
                             m2[b] = cond_sub(xd[b][2 * (DK - 1) + 1] + dl1[b], Q);
@@ -458,7 +582,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 }
             }
             // request the first slot of the next step now
-            if (!TMA && i + 1 < n) {
+            if (!TMA && i + 1 < se) {
                 const uint4* p4 = reinterpret_cast<const uint4*>(A.bk) + (size_t)(i + 1) * D * N + tid;
 #pragma unroll
                 for (int x = 0; x < D; x++) {
@@ -474,6 +598,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
         // c = INTT(acc_eval) (identical mod Q because the transform is linear), read from its own region and
         // transposed through the free digit region j, so acc_eval survives for the next step and c is dead between
         // the digit extraction and this point (32 registers less through phases 1 and 2).
+        // (the last step of a head part runs it as well: the hand-over image holds both forms of the accumulator)
         if (!helper) {
             u32 v[32];
             u32* reg = myD + (size_t)(LAT ? j + 2 * lw : j) * RS;   // scratch: this warp's own digit region
@@ -510,6 +635,26 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
         // (barrier above) and region j, which only this thread group read in phase 3 (__syncwarp above).
     }
 
+    if (PERS && se < n) {
+        // head part of a split group: leave the accumulator image for the next CTA
+        const u32 slot = blockIdx.x;
+        uint4* dst4 = reinterpret_cast<uint4*>(A.pers_state) + (((size_t)slot * 2 * G + g) * 2 + j) * (N / 4) + T * 8;
+#pragma unroll
+        for (int x = 0; x < 8; x++)
+            __stcg(dst4 + x, make_uint4(c[4 * x], c[4 * x + 1], c[4 * x + 2], c[4 * x + 3]));
+        if (SKIP) {
+            // phase 3 only read the evaluation-domain rows: they are as phase 2 left them
+            const uint4* p4 = reinterpret_cast<const uint4*>(myD + (size_t)(2 * (DK - 1) + j) * RS + 36 * T);
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+                __stcg(dst4 + (size_t)G * 2 * (N / 4) + x, p4[x]);
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.pers_flags + slot), "r"(A.pers_epoch) : "memory");
+        continue;
+    }
     // ---- extraction: a'(X) = a(X^-1), b = acc_b[0] (+ Q8 for gates) ---------------------------------------------
     if (live && (!LAT || lw == 0)) {
         if (C.write_acc) {
@@ -541,6 +686,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             }
         }
     }
+    }   // items
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -582,7 +728,7 @@ bool cggi32_supported(const tfhe_b200_params& p) {
     // shared memory of the throughput shape: G * D digit regions + psi table + G * n rotation exponents
     const u32 G = p.N == 2048 ? 2 : (p.N == 1024 ? (dk <= 4 ? 4 : 2) : (dk <= 4 ? 8 : 4));
     const size_t RS = p.N + p.N / 8 + (p.N == 512 ? 16 : 0);
-    const size_t smem = (size_t)G * 2 * dk * RS * 4 + (size_t)2 * p.N * 4 + (size_t)G * ((p.n + 1) / 2 * 2) * 2 + 64;
+    const size_t smem = (size_t)G * 2 * dk * RS * 4 + (size_t)2 * p.N * 4 * CGGI32_TABW + (size_t)G * ((p.n + 1) / 2 * 2) * 2 + 64;
     if (smem > 227 * 1024)
         return false;
     return true;
@@ -682,10 +828,36 @@ void cggi32_build_tables(const tfhe_b200_params& p, std::vector<u32>& twA, std::
         }
 }
 
+// Persistent variant: one CTA per SM, the launch's groups * n steps cut into equal ranges (see the kernel header).
+// Instantiated for the shapes the named sets run at large batches.
+template <int LOGN, int DK, int G, bool SKIP>
+static cudaError_t launch_pers(CGGI32Args a, cudaStream_t s, int ctas) {
+    using K = KCfg<LOGN, DK, G>;
+    const size_t smem = (K::smem_bytes((int)a.c.n) + (size_t)(CGGI32_TABW - 1) * 2 * K::N * 4);
+    if (smem > 227 * 1024)
+        return cudaErrorInvalidConfiguration;
+    cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G, SKIP, false, false, 0, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
+    a.pers_groups = (a.c.batch + G - 1) / G;
+    br_cggi32_kernel<LOGN, DK, G, SKIP, false, false, 0, true><<<ctas, K::NT, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+// Does the throughput shape of this parameter set have a persistent instantiation?  (group = ciphertexts per CTA)
+bool cggi32_pers_shape(u32 logN, u32 dk, bool skip_top, u64 Q, int* group) {
+    if (cggi32_needs_sweep(Q))
+        return false;
+    if (logN == 10 && dk == 4 && skip_top) { *group = 4; return true; }
+    if (logN == 9 && dk == 3 && !skip_top) { *group = 8; return true; }
+    return false;
+}
+
 template <int LOGN, int DK, int G, bool SKIP, bool TMA>
 static cudaError_t launch_t2(const CGGI32Args& a, cudaStream_t s) {
     using K = KCfg<LOGN, DK, G>;
-    const size_t smem = TMA ? K::ring_offset((int)a.c.n) + (size_t)2 * K::D * K::NT * 16 + 64 : K::smem_bytes((int)a.c.n);
+    const size_t smem = TMA ? K::ring_offset((int)a.c.n) + (size_t)2 * K::D * K::NT * 16 + 64 : (K::smem_bytes((int)a.c.n) + (size_t)(CGGI32_TABW - 1) * 2 * K::N * 4);
     if (smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, G, SKIP, TMA>,
@@ -701,7 +873,7 @@ static cudaError_t launch_t2(const CGGI32Args& a, cudaStream_t s) {
 template <int DK, bool SKIP>
 static cudaError_t launch_sweep(const CGGI32Args& a, cudaStream_t s) {
     using K = KCfg<10, DK, 4>;
-    const size_t smem = K::smem_bytes((int)a.c.n);
+    const size_t smem = (K::smem_bytes((int)a.c.n) + (size_t)(CGGI32_TABW - 1) * 2 * K::N * 4);
     if (smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<10, DK, 4, SKIP, false, false, 1>,
@@ -716,7 +888,7 @@ static cudaError_t launch_sweep(const CGGI32Args& a, cudaStream_t s) {
 template <int SW>
 static cudaError_t launch_n2048(const CGGI32Args& a, cudaStream_t s) {
     using K = KCfg<11, 4, 2>;
-    const size_t smem = K::smem_bytes((int)a.c.n);
+    const size_t smem = (K::smem_bytes((int)a.c.n) + (size_t)(CGGI32_TABW - 1) * 2 * K::N * 4);
     if (smem > 227 * 1024)
         return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<11, 4, 2, true, false, false, SW>,
@@ -731,7 +903,7 @@ static cudaError_t launch_n2048(const CGGI32Args& a, cudaStream_t s) {
 template <int LOGN, int DK>
 static cudaError_t launch_lat(const CGGI32Args& a, cudaStream_t s) {
     using K = KCfg<LOGN, DK, 1>;
-    const size_t smem = K::smem_bytes((int)a.c.n);
+    const size_t smem = (K::smem_bytes((int)a.c.n) + (size_t)(CGGI32_TABW - 1) * 2 * K::N * 4);
     cudaError_t e = cudaFuncSetAttribute(br_cggi32_kernel<LOGN, DK, 1, true, false, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
@@ -773,6 +945,27 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     a.zero = 0;
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
     const int dk = (int)c.digitsKept;
+    a.pers_state = nullptr; a.pers_flags = nullptr; a.pers_epoch = 0; a.pers_groups = 0;
+    {
+        // Persistent variant: whenever the plain launch would end on a partial wave (t.pers_ctas > 0 forces a CTA count,
+        // tests).  The caller owns the hand-over slots and bumps the epoch per launch.
+        int pg = 0;
+        if (group == 0 && t.pers_state && t.pers_mode != 0 && cggi32_pers_shape(c.logN, dk, t.skip_top, t.mod.Q, &pg)) {
+            const int groups = (c.batch + pg - 1) / pg;
+            int ctas = std::min(sm_count, groups);
+            bool use = groups > sm_count && groups % sm_count != 0;
+            if (t.pers_ctas > 0) {
+                ctas = std::min(std::min(t.pers_ctas, groups), sm_count);
+                use = true;
+            }
+            if (use && ctas <= t.pers_slots) {
+                a.pers_state = t.pers_state; a.pers_flags = t.pers_flags; a.pers_epoch = t.pers_epoch;
+                if (c.logN == 10)
+                    return launch_pers<10, 4, 4, true>(a, s, ctas);
+                return launch_pers<9, 3, 8, false>(a, s, ctas);
+            }
+        }
+    }
     if (c.logN == 11) {
         if (dk != 4 || !t.skip_top)
             return cudaErrorInvalidConfiguration;

@@ -144,6 +144,9 @@ struct Dev {
     u64* twUw = nullptr;
     void* ksk = nullptr;
     u64* ks_partial = nullptr;   // column-sum accumulator of split key switches (batches below one ciphertext per SM)
+    u32* pers_state = nullptr;   // persistent blind rotation: hand-over slots of split groups, one per SM (br_cggi32.cu)
+    u32* pers_flags = nullptr;   // ... and their completion flags (hold the epoch of the launch that filled the slot)
+    u32 pers_epoch = 0;
     Arena ws;
     Pinned pin;                         // pinned host staging (inputs and outputs of the current call)
     std::vector<PendingOut> pending;    // staged outputs to hand to the caller after the stream has drained
@@ -184,6 +187,8 @@ struct tfhe_b200_handle {
     int force_generic = 0;
     bool keep_generic = false;   // generic key layout retained beside the specialised one (cross-check kernel)
     int group = 0;  // ciphertexts per CTA of the cggi32 kernel (0 = default)
+    int pers_mode = 1;   // persistent blind rotation: 0 = never, 1 = whenever a plain launch would end on a partial wave
+    int pers_ctas = 0;   // > 0: force the persistent variant with this many CTAs (tests: splits at arbitrary steps)
     u32 logN = 0, d = 0, gBits = 0;
     ModCtx<u32> m32;
     ModCtx<u64> m64;
@@ -701,6 +706,10 @@ extern "C" int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_
     }
     else if (k == "group")
         h->group = (int)value;
+    else if (k == "persistent")
+        h->pers_mode = (int)value;
+    else if (k == "persistent_ctas")
+        h->pers_ctas = (int)value;
     else
         FAIL(TFHE_B200_EINVAL, "set_option: unknown key " + k);
     for (auto& kv : h->key_map)
@@ -715,7 +724,7 @@ static int free_dev(Dev& d, bool borrowed_streams = false) {
         d.stream = d.xfer_in = d.xfer_out = nullptr;
     if (d.stream)
         cudaStreamSynchronize(d.stream);
-    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twU64, d.twCw, d.twBw, d.twUw, d.twB, d.ksk, d.ks_partial, d.ws.base};
+    void* ptrs[] = {d.bk_generic, d.bk_cggi32, d.tw_fwd, d.tw_inv, d.psi_pow, d.sh_fwd, d.sh_inv, d.bk_cggi64, d.twB64, d.tw32_64, d.twU64, d.twCw, d.twBw, d.twUw, d.twB, d.ksk, d.ks_partial, d.pers_state, d.pers_flags, d.ws.base};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -845,6 +854,9 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
             CUDA_TRY(cudaGetDeviceProperties(&prop, d.id));
             d.sm_count = prop.multiProcessorCount;
             CUDA_TRY(cudaMalloc((void**)&d.ks_partial, mkmswitch_partial_bytes(h->row_stride, 2 * d.sm_count)));
+            CUDA_TRY(cudaMalloc((void**)&d.pers_state, (size_t)d.sm_count * PERS_SLOT_WORDS * 4));
+            CUDA_TRY(cudaMalloc((void**)&d.pers_flags, (size_t)d.sm_count * 4));
+            CUDA_TRY(cudaMemset(d.pers_flags, 0, (size_t)d.sm_count * 4));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_in, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_out, cudaStreamNonBlocking));
@@ -1157,6 +1169,12 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
     if (h->have_cggi32 && !h->force_generic) {
         CGGI32Tables t;
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB; t.skip_top = h->skip_top;
+        if (++d.pers_epoch == 0) {   // the flags hold the epoch of the launch that filled them: start over after a wrap
+            CUDA_TRY(cudaMemsetAsync(d.pers_flags, 0, (size_t)d.sm_count * 4, d.stream));
+            d.pers_epoch = 1;
+        }
+        t.pers_state = d.pers_state; t.pers_flags = d.pers_flags; t.pers_epoch = d.pers_epoch; t.pers_slots = d.sm_count;
+        t.pers_mode = getenv("TFHE_B200_NO_PERSISTENT") ? 0 : h->pers_mode; t.pers_ctas = h->pers_ctas;
         CUDA_TRY(launch_br_cggi32(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_dm32 && !h->force_generic) {
@@ -1222,9 +1240,16 @@ static int throughput_group(const tfhe_b200_handle* h) {
     return 1;
 }
 // ... and the largest remainder (in ciphertexts per SM) for which the kernel has a latency shape; 0 = none.
+// Does the active kernel have a persistent variant (no wave quantisation: any batch above one wave costs
+// groups / SMs wave times)?  Then neither the tail launch nor wave-aligned chunks are needed.
+static bool persistent_shape(const tfhe_b200_handle* h) {
+    int g = 0;
+    return h->have_cggi32 && !h->force_generic && h->group == 0 && h->pers_mode != 0 && !getenv("TFHE_B200_NO_PERSISTENT") &&
+           cggi32_pers_shape(h->logN, h->d / 2, h->skip_top, h->p.Q, &g);
+}
 static void tail_shapes(const tfhe_b200_handle* h, int* per_cta, int* tail_per_sm) {
     *per_cta = *tail_per_sm = 0;
-    if (h->force_generic || h->group != 0)
+    if (h->force_generic || h->group != 0 || persistent_shape(h))
         return;
     const u32 dk = h->d / 2;
     if (h->have_cggi32) {
@@ -1790,7 +1815,8 @@ static int eval_bin_gate_impl(tfhe_b200_handle* h, int gate, int batch, const Ga
             // is exposed before the first launch and one wave's worth of output after the last.  Pageable buffers (and
             // per-object ciphertexts) are staged through the handle's pinned memory: the host memcpy / gather of chunk
             // k+1 and the hand-back of chunk k-1 run while the GPU works on chunk k.
-            const int waves = (count + unit - 1) / unit;
+            // (with a persistent blind rotation the remainder costs only its share of a wave: it joins the last chunk)
+            const int waves = persistent_shape(h) ? count / unit : (count + unit - 1) / unit;
             int wsz[MAX_CHUNKS], nch = 0;
             {
                 const int mid = waves - 2, nmid = std::min(MAX_CHUNKS - 2, (mid + 5) / 6);   // middle chunks of <= ~6 waves

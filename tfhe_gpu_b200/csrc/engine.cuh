@@ -65,7 +65,16 @@ struct CGGI32Tables {
     const u32* twB;       // per-thread pass-B twiddles + Shoup companions, forward
     bool skip_top;        // keys were transformed for top-digit elimination (see br_cggi32.cu)
     const u32* twA;       // HOST pointer: uniform pass-A twiddles + companions [fwd|inv][32][2] (kernel params)
+    // persistent variant (br_cggi32.cu): hand-over slots of split groups, owned by the device record
+    u32* pers_state = nullptr;   // [pers_slots][PERS_SLOT_WORDS]
+    u32* pers_flags = nullptr;   // [pers_slots], zero at allocation
+    u32 pers_epoch = 0;          // unique per launch on this device (never 0)
+    int pers_slots = 0;
+    int pers_mode = 1;           // 0 = never, 1 = automatic
+    int pers_ctas = 0;           // > 0: force the persistent variant with this many CTAs (tests)
 };
+constexpr size_t PERS_SLOT_WORDS = 16384;   // G * 2 * N words of the largest persistent shape (4 x 2 x 1024, 8 x 2 x 512)
+bool cggi32_pers_shape(u32 logN, u32 dk, bool skip_top, u64 Q, int* group);
 bool cggi32_supported(const tfhe_b200_params& p);
 // moduli between 2^32/22 and 2^28 run the cggi32 variant with a mid-transform reduction sweep (ntt32.cuh)
 inline bool cggi32_needs_sweep(u64 Q) { return Q >= (1ULL << 32) / 22; }
