@@ -388,3 +388,36 @@ def test_cggi32_persistent_variant(N, baseG, rng):
         assert np.array_equal(g.EvalBinGate("NAND", c1, c2), want)
     finally:
         g.GPUClean()
+
+
+@pytest.mark.parametrize("baseG", [1 << 27, 1 << 18])                        # digitsG = 2 (EvalFunc sets), 3 (EvalSign sets)
+def test_cggi64w_persistent_variant(baseG, rng):
+    """Persistent variant of the wide 54-bit kernel (two ciphertexts per CTA): groups split between neighbouring CTAs
+    at arbitrary steps, wrap-zone accumulators included (the wrap bitmaps are rebuilt after a hand-over)."""
+    p = po.Port.params_custom(7, 2048, 4096, Q54, 64, baseG, 32, po.GINX)
+    port = po.Port(p)
+    sk, bk, ksk, g = _ctx(p, port)
+    try:
+        assert g.kernel_variant.startswith("cggi_u64") and g.kernel_variant.endswith("skiptop")
+        Q, QH, N, n, q = p.Q, p.Q >> 1, 2048, p.n, p.q
+        batch = 11                                                          # six groups of two, the last one ragged
+        off = sum((baseG // 2) * baseG**i for i in range(p.digitsG))
+        lo = max(baseG**p.digitsG - off, 0)
+        acc = rng.integers(0, Q, (batch, 2, N), dtype=np.uint64)
+        if lo < QH:
+            acc[0] = rng.integers(lo, QH, (2, N), dtype=np.uint64)          # every coefficient in the wrap zone
+            acc[5, 1, 3] = QH - 1
+        am = rng.integers(0, q, (batch, n), dtype=np.uint64)
+        want_a = port.eval_acc(bk, am, q, acc)
+        c1 = rng.integers(0, q, (batch, n + 1), dtype=np.uint64)
+        tab = rng.integers(0, q, q, dtype=np.uint64)
+        want_f = port.bootstrap_func(bk, ksk, c1, q, tab, q)
+        for ctas in (2, 3, 4, 5, 6):                                        # 6 x 7 steps over `ctas` ranges
+            g.set_option("persistent_ctas", ctas)
+            assert np.array_equal(g.EvalAcc(am, q, acc), want_a), ctas
+            assert np.array_equal(g.BootstrapFunc(c1, q, tab, q), want_f), ctas
+        g.set_option("persistent_ctas", 0)
+        g.set_option("persistent", 0)
+        assert np.array_equal(g.EvalAcc(am, q, acc), want_a)
+    finally:
+        g.GPUClean()

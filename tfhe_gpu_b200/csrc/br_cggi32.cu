@@ -26,11 +26,12 @@
 
 // Words per entry of the monomial-factor table in shared memory (phase 2):
 //   1: psi^x (Montgomery form); the two factors psi^x - 1 and psi^-x - 1 are two lookups plus a modular subtraction each
-//   2: (psi^x - 1, psi^-x - 1): one index computation, one 64-bit lookup, no subtraction
-//   4: (a1 R, a1, a2 R, a2) with a = psi^(+-x) - 1: the four 64-bit sums of a slot are folded straight into the two outputs
-//      as hi(s) * (a R) + lo(s) * a (s = hi 2^32 + lo, R = 2^32) with ONE reduction per output instead of three
+//      (kept for the TMA variant, whose shared-memory ring is laid out behind the 8 KB table)
+//   2: (psi^x - 1, psi^-x - 1): one index computation, one 64-bit lookup, no subtraction -- 160.8 -> 156.0 ms per 16384
+//      STD128 bootstraps.  (A four-word entry (a R, a) that folds the factors into the 64-bit sums as hi(s) (a R) + lo(s) a
+//      with one reduction per output saves four more multiplier slots per slot but measured 157.2 ms: not kept.)
 #ifndef CGGI32_TABW
-#define CGGI32_TABW 1
+#define CGGI32_TABW 2
 #endif
 
 namespace tfhe_b200 {
@@ -170,9 +171,8 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 
     // ---- one-time loads: psi-power table, per-thread twiddles ------------------------------------------------
     // bit-rotated index: the distinct exponents a warp touches differ in their top bits only, which become the low
-    // index bits so that they fall into distinct banks (16 x 4 B, 16 x 8 B per half-warp, 8 x 16 B per quarter-warp)
-    constexpr int TB = TABW == 4 ? 3 : 4;
-    auto tab_index = [&](u32 x) -> u32 { return ((x & (2 * N / (1 << TB) - 1)) << TB) | (x >> (LOGN + 1 - TB)); };
+    // index bits so that they fall into distinct banks (16 x 4 B per warp, 16 x 8 B per half-warp)
+    auto tab_index = [&](u32 x) -> u32 { return ((x & (2 * N / 16 - 1)) << 4) | (x >> (LOGN + 1 - 4)); };
     for (int x = tid; x < 2 * N; x += NT) {
         if (TABW == 1)
             psiM[tab_index(x)] = A.psi_pow[x];
@@ -180,10 +180,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
             u32 a1 = A.psi_pow[x], a2 = A.psi_pow[(2 * N - x) & (2 * N - 1)];
             a1 = a1 >= oneM ? a1 - oneM : a1 + Q - oneM;
             a2 = a2 >= oneM ? a2 - oneM : a2 + Q - oneM;
-            if (TABW == 2)
-                reinterpret_cast<uint2*>(psiM)[tab_index(x)] = make_uint2(a1, a2);
-            else
-                reinterpret_cast<uint4*>(psiM)[tab_index(x)] = make_uint4(a1, A.mod.mont_mul(a1, 1), a2, A.mod.mont_mul(a2, 1));
+            reinterpret_cast<uint2*>(psiM)[tab_index(x)] = make_uint2(a1, a2);
         }
     }
     u32 tw[32], twp[32];
@@ -395,12 +392,13 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                 // centred representative, closed-form signed digit, fed to the lazy NTT as digit + Q
                 int dv = (c[r] < QHalf) ? (int)c[r] : (int)c[r] - (int)Q;
                 u32 Dv = (u32)(dv + (int)A.dig_off);
-                v[r] = ((u32)((int)Dv >> sh) & gmask) + A.dig_add;
+                // (the offset of the first sixteen coefficients is added inside the first butterfly stage)
+                v[r] = ((u32)((int)Dv >> sh) & gmask) + ((SWEEP == 2 || r >= 16) ? A.dig_add : 0u);
             }
             if (SWEEP == 2)
                 fwd_passA_sw(v, A, Q, Q2);
             else
-                fwd_passA(v, A, Q, Q2);
+                fwd_passA(v, A, Q, Q2, A.dig_add);
             if (SWEEP == 1)
                 sweep_below_2q(v, Q2);
             if (SWEEP == 2)
@@ -500,7 +498,6 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 #pragma unroll
                 for (int g0 = 0; g0 < G; g0 += GB) {
                     u32 xd[GB][D], m1[GB], m2[GB], dl0[GB], dl1[GB];
-                    u32 n1[TABW == 4 ? GB : 1], n2[TABW == 4 ? GB : 1];   // TABW = 4: the plain-form factors
 #pragma unroll
                     for (int b = 0; b < GB; b++) {
                         const u32* dreg = Dsm + (size_t)(g0 + b) * D * RS + pk;
@@ -516,13 +513,9 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                             m1[b] = psiM[tab_index(xx)];
                             m2[b] = psiM[tab_index(x2)];
                         }
-                        else if (TABW == 2) {
+                        else {
                             const uint2 w = reinterpret_cast<const uint2*>(psiM)[tab_index(xx)];
                             m1[b] = w.x; m2[b] = w.y;
-                        }
-                        else {
-                            const uint4 w = reinterpret_cast<const uint4*>(psiM)[tab_index(xx)];
-                            m1[b] = w.x; n1[b] = w.y; m2[b] = w.z; n2[b] = w.w;
                         }
                     }
 #pragma unroll
@@ -536,30 +529,31 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                             s10 += (u64)x * bkv[(1 * D + l) * 2 + 0];
                             s11 += (u64)x * bkv[(1 * D + l) * 2 + 1];
                         }
-                        if (TABW == 4) {
-                            // s = hi R + lo, so s a R^-1 = (hi (a R) + lo a) R^-1: fold the monomial factors into the sums
-                            // before the one reduction.  Bounds: s < 8 * 24 Q * Q < 2^62, hi < 2^30, the four products
-                            // stay below 2 (2^31 + 2^32) Q = 3 Q 2^32 < 2^63 for any s < 2^63; REDC leaves less than 3 Q + Q.
-                            const u32 A1 = m1[b], B1 = n1[b], A2 = m2[b], B2 = n2[b];
-                            const u64 t0 = (u64)(u32)(s00 >> 32) * A1 + (u64)(u32)s00 * B1 + (u64)(u32)(s10 >> 32) * A2 + (u64)(u32)s10 * B2;
-                            const u64 t1 = (u64)(u32)(s01 >> 32) * A1 + (u64)(u32)s01 * B1 + (u64)(u32)(s11 >> 32) * A2 + (u64)(u32)s11 * B2;
-                            u32 d0 = redc_lazy(t0), d1 = redc_lazy(t1);
-                            dl0[b] = cond_sub(cond_sub(d0, Q2), Q);
-                            dl1[b] = cond_sub(cond_sub(d1, Q2), Q);
-                        }
-                        else {
+                        {
                         const u32 r00 = redc_lazy(s00), r01 = redc_lazy(s01), r10 = redc_lazy(s10), r11 = redc_lazy(s11);
                         u32 a1 = m1[b], a2 = m2[b];
                         if (TABW == 1) {
                             a1 = a1 >= oneM ? a1 - oneM : a1 + Q - oneM;
                             a2 = a2 >= oneM ? a2 - oneM : a2 + Q - oneM;
                         }
+                        if (SKIP) {
+                            // acc_eval += delta in one go: y = top + hi - t lies in (-Q, 2Q) (mod 2^32), and the canonical
+                            // residue is whichever of y, y + Q, y - Q is below Q -- the unsigned minimum of the three
+                            // (two VIADDMNMX instead of compare / select / add / add / min: 153.7 -> 152.5 ms per 16384)
+                            auto redc_acc = [&](u64 x, u32 top) -> u32 {
+                                u32 lo = (u32)x, hi = (u32)(x >> 32);
+                                u32 t = mulhi_w(lo * qinv, Q);
+                                u32 y = hi - t + top;
+                                return min(min(y, y + Q), y - Q);
+                            };
+                            m1[b] = redc_acc((u64)r00 * a1 + (u64)r10 * a2, xd[b][2 * (DK - 1)]);
+                            m2[b] = redc_acc((u64)r01 * a1 + (u64)r11 * a2, xd[b][2 * (DK - 1) + 1]);
+                        }
+                        else
+                        {
                         dl0[b] = redc_full((u64)r00 * a1 + (u64)r10 * a2);
                         dl1[b] = redc_full((u64)r01 * a1 + (u64)r11 * a2);
                         }
-                        if (SKIP) {   // acc_eval += delta (kept canonical); its old value is the top row just loaded
-                            m1[b] = cond_sub(xd[b][2 * (DK - 1)] + dl0[b], Q);
-                            m2[b] = cond_sub(xd[b][2 * (DK - 1) + 1] + dl1[b], Q);
                         }
                     }
 #pragma unroll
@@ -611,7 +605,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
                     v[4 * x] = w.x; v[4 * x + 1] = w.y; v[4 * x + 2] = w.z; v[4 * x + 3] = w.w;
                 }
             }
-            inv_passB<PB>(v, tw, twp, Q, Q2, A.zero);
+            inv_passB<PB, true>(v, tw, twp, Q, Q2, A.zero);   // both paths transform canonical rows
             if (K::XS)
                 cross_stage<false>(v, tw[31], twp[31], Q, Q2, A.zero, odd_lane);
             poly_sync<TPN>(pbar);

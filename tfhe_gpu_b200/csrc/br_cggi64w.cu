@@ -33,13 +33,23 @@ struct CGGI64WArgs {
     const u64* twB;      // [16][8][2]   pass-B twiddles: entry (blk, cnt-1+x) = W[16 cnt + cnt blk + x] (slot 7 unused)
     const u64* twU;      // [2][15][2]   uniform pass-A twiddles: forward W[e+1], then NEGATED inverse
     u64 Q2, dig_off, dig_add, ninvM, zero64, kfix;
+    // persistent variant (PERS, see br_cggi32.cu): hand-over slots of the groups split between two CTAs
+    u64* pers_state;     // [slot][2][G][2][N]: coefficient registers, then the evaluation-domain accumulator rows
+    u32* pers_flags;     // [slot] launch epoch once the slot's image is complete
+    u32 pers_epoch;
+    u32 pers_groups;     // ceil(batch / G)
 };
 
 // PLAIN = true: no top-digit elimination (thrown digits, or a top digit that is neither exact nor repairable).  The
 // region layout stays the same -- DK - 1 digit rows per component plus the evaluation-domain accumulator rows, which
 // are still maintained (acc_eval += delta) and inverse-transformed, only no longer multiplied by a key row: DK - 1 is
 // then the number of KEPT digits, the key has 2 (DK - 1) rows per secret-key half, and there is no wrap repair.
-template <int DK, int G, bool PLAIN = false>
+//
+// PERS = true: persistent variant without wave quantisation -- one CTA per SM, the launch's groups x n rotation steps cut
+// into equal ranges, split groups handed over through an accumulator image; the scheme and its argument are in the
+// header of br_cggi32_kernel.  The wrap bitmaps are rebuilt from the coefficients in every phase 1, so the image is the
+// coefficient registers plus the evaluation-domain rows here as well.
+template <int DK, int G, bool PLAIN = false, bool PERS = false>
 __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __grid_constant__ CGGI64WArgs A) {
     using K = KW<DK, G>;
     constexpr int D = K::D, NT = K::NT, NF = DK - 1;
@@ -60,10 +70,19 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
     const int tid = threadIdx.x;
     const int g = tid / (2 * TPN), j = (tid / TPN) & 1, T = tid % TPN;
     const int bar_id = 1 + g * 2 + j;
-    const int ct = blockIdx.x * G + g;
-    const bool live = ct < C.batch;
-    const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
     const int blk = T >> 3, u8 = T & 7;
+
+    // persistent variant: this CTA's range of the launch's groups * n rotation steps (br_cggi32.cu)
+    u32 gA = 0, sA = 0, gB = 0, sB = 0, first_full = 0;
+    int n_full = 0, n_items = 1;
+    if (PERS) {
+        const u64 Wt = (u64)A.pers_groups * n;
+        const u64 lo = Wt * blockIdx.x / gridDim.x, hi = Wt * (blockIdx.x + 1) / gridDim.x;
+        gA = (u32)(lo / n); sA = (u32)(lo % n); gB = (u32)(hi / n); sB = (u32)(hi % n);
+        first_full = gA + (sA ? 1 : 0);
+        n_full = (int)gB - (int)first_full;
+        n_items = (sB ? 1 : 0) + n_full + (sA ? 1 : 0);
+    }
 
     for (int x = tid; x < 15 * TPN; x += NT)
         twC[x] = reinterpret_cast<const ulonglong2*>(A.twC)[x];
@@ -72,9 +91,71 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
     for (int x = tid; x < 2 * 15; x += NT)
         twUf[x] = reinterpret_cast<const ulonglong2*>(A.twU)[x];
 
-    // ---- accumulator initialisation in A layout (coefficient idx = T + 128 r) -----------------------------------
     u64 c[CPT];
-    if (C.acc_init == ACC_EXPLICIT) {
+    u64* const myD = Dsm + (size_t)g * D * N;
+    u64* const top = myD + (size_t)(j + 2 * (DK - 1)) * N;   // evaluation-domain accumulator row of this component
+    const u64 QHalf = Q >> 1;
+    const u32 gBits = C.gBits;
+    const u64 gmask = ((u64)1 << gBits) - 1;
+
+    // forward transform of v (A layout in) through region `reg`; result in registers in C layout of block T, < 29 Q
+    auto forward = [&](u64 (&v)[CPT], u64* reg) {
+        fwd_pass4(v, twUf, 1, 0, nQ, QO, Z);
+#pragma unroll
+        for (int r = 0; r < CPT; r++)
+            reg[posw(T + TPN * r)] = v[r];
+        group_sync128(bar_id);
+        load_Bw(v, reg, blk, u8);
+        fwd_pass3(v, twB + 8 * blk, nQ, QO, Z);
+        store_Bw(v, reg, blk, u8);
+        __syncwarp();
+        load_C(v, reg, T);
+        fwd_pass4(v, twC, TPN, T, nQ, QO, Z);
+        const u64 Q16 = 4 * QO;
+#pragma unroll
+        for (int r = 0; r < CPT; r++)
+            v[r] = csub(v[r], Q16);   // 11 lazy stages: < 45 Q -> < 29 Q (27-bit limb split of the pointwise stage)
+    };
+
+    for (int item = 0; item < n_items; item++) {
+    // this item: rotation steps [sb, se) of group grp (the whole rotation unless PERS)
+    u32 grp = blockIdx.x, sb = 0, se = n;
+    if (PERS) {
+        const int u = item - (sB ? 1 : 0);
+        if (u < 0) { grp = gB; se = sB; }
+        else if (u < n_full) grp = first_full + (u32)u;
+        else { grp = gA; sb = sA; }
+        __syncthreads();   // the previous item is done with the digit regions and the wrap bitmaps
+    }
+    const int ct = (int)grp * G + g;
+    const bool live = ct < C.batch;
+    const u64* lwe = C.ct + (size_t)(live ? ct : 0) * (n + 1);
+
+    // ---- accumulator initialisation in A layout (coefficient idx = T + 128 r) -----------------------------------
+    if (PERS && sb > 0) {
+        // the head of this group was run by the previous CTA at the start of the launch: wait for its image
+        const u32 slot = blockIdx.x - 1;
+        if (tid == 0) {
+            u32 f, spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(A.pers_flags + slot) : "memory");
+                if (f == A.pers_epoch)
+                    break;
+                __nanosleep(200);
+                if (++spins > (1u << 26))   // cannot happen: fail the launch loudly rather than hang (br_cggi32.cu)
+                    __trap();
+            }
+        }
+        __syncthreads();
+        const u64* src = A.pers_state + (((size_t)slot * 2 * G + g) * 2 + j) * N;
+#pragma unroll
+        for (int r = 0; r < CPT; r++)
+            c[r] = __ldcg(src + T + TPN * r);
+#pragma unroll
+        for (int r = 0; r < CPT; r++)
+            top[T + TPN * r] = __ldcg(src + (size_t)G * 2 * N + T + TPN * r);
+    }
+    else if (C.acc_init == ACC_EXPLICIT) {
         const u64* src = C.acc_io + ((size_t)(live ? ct : 0) * 2 + j) * N;
 #pragma unroll
         for (int r = 0; r < CPT; r++)
@@ -107,32 +188,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
     }
     __syncthreads();
 
-    u64* myD = Dsm + (size_t)g * D * N;
-    u64* top = myD + (size_t)(j + 2 * (DK - 1)) * N;   // evaluation-domain accumulator row of this component
-    const u64 QHalf = Q >> 1;
-    const u32 gBits = C.gBits;
-    const u64 gmask = ((u64)1 << gBits) - 1;
-
-    // forward transform of v (A layout in) through region `reg`; result in registers in C layout of block T, < 29 Q
-    auto forward = [&](u64 (&v)[CPT], u64* reg) {
-        fwd_pass4(v, twUf, 1, 0, nQ, QO, Z);
-#pragma unroll
-        for (int r = 0; r < CPT; r++)
-            reg[posw(T + TPN * r)] = v[r];
-        group_sync128(bar_id);
-        load_Bw(v, reg, blk, u8);
-        fwd_pass3(v, twB + 8 * blk, nQ, QO, Z);
-        store_Bw(v, reg, blk, u8);
-        __syncwarp();
-        load_C(v, reg, T);
-        fwd_pass4(v, twC, TPN, T, nQ, QO, Z);
-        const u64 Q16 = 4 * QO;
-#pragma unroll
-        for (int r = 0; r < CPT; r++)
-            v[r] = csub(v[r], Q16);   // 11 lazy stages: < 45 Q -> < 29 Q (27-bit limb split of the pointwise stage)
-    };
-
-    {
+    if (!PERS || sb == 0) {
         // evaluation-domain accumulator (scaled by N^-1), see br_cggi32.cu
         u64 v[CPT];
 #pragma unroll
@@ -144,10 +200,10 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
             v[r] = A.mod.mont_mul(v[r], A.ninvM);
         __syncwarp();
         store_C(v, top, T);
-        __syncthreads();
     }
+    __syncthreads();
 
-    for (u32 i = 0; i < n; i++) {
+    for (u32 i = sb; i < se; i++) {
         // ---- phase 1: wrapped-top-digit detection, digits 0..DK-2 -> forward transforms ----------------------------
         if (!PLAIN) {
             u32 wm = 0;
@@ -255,7 +311,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
 #pragma unroll
             for (int gg = 0; gg < G; gg++) {
                 // rgsw-acc-cggi.cpp:146-153: e_i = ((mod - a_i) mod mod) * (2N / mod); 0 for dead slots
-                const int cg = blockIdx.x * G + gg;
+                const int cg = (int)grp * G + gg;
                 u64 e = 0;
                 if (cg < C.batch) {
                     u64 ai = C.ct[(size_t)cg * (n + 1) + i] % C.ct_mod;
@@ -342,6 +398,22 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
         }
     }
 
+    if (PERS && se < n) {
+        // head part of a split group: leave the accumulator image for the next CTA (phase 3 only read the top rows)
+        const u32 slot = blockIdx.x;
+        u64* dst = A.pers_state + (((size_t)slot * 2 * G + g) * 2 + j) * N;
+#pragma unroll
+        for (int r = 0; r < CPT; r++)
+            __stcg(dst + T + TPN * r, c[r]);
+#pragma unroll
+        for (int r = 0; r < CPT; r++)
+            __stcg(dst + (size_t)G * 2 * N + T + TPN * r, top[T + TPN * r]);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.pers_flags + slot), "r"(A.pers_epoch) : "memory");
+        continue;
+    }
     if (live) {
         if (C.write_acc) {
             u64* dst = C.acc_io + (size_t)ct * 2 * N;
@@ -372,6 +444,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
             }
         }
     }
+    }   // items
 }
 
 u32 bitrev_w(u32 x, u32 bits) {
@@ -384,6 +457,18 @@ u32 bitrev_w(u32 x, u32 bits) {
 }
 u64 shoup_w(u64 w, u64 Q) {
     return (u64)((((unsigned __int128)w) << 64) / Q);
+}
+
+template <int DK, int G, bool PLAIN = false>
+cudaError_t launch_w_pers(CGGI64WArgs a, cudaStream_t s, int ctas) {
+    using K = KW<DK, G>;
+    cudaError_t e = cudaFuncSetAttribute(br_cggi64w_kernel<DK, G, PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)K::smem);
+    if (e != cudaSuccess)
+        return e;
+    a.pers_groups = (a.c.batch + G - 1) / G;
+    br_cggi64w_kernel<DK, G, PLAIN, true><<<ctas, K::NT, K::smem, s>>>(a);
+    return cudaGetLastError();
 }
 
 template <int DK, int G, bool PLAIN = false>
@@ -481,6 +566,22 @@ cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStr
     // a batch of at most one ciphertext per SM is latency-bound: one ciphertext per CTA (8 warps instead of 16 competing
     // for the SM) finishes a rotation step sooner; `group` = 1 / 2 forces a shape (tests, measurements)
     const bool one = group == 1 || (group == 0 && sm_count > 0 && c.batch <= sm_count);
+    a.pers_state = nullptr; a.pers_flags = nullptr; a.pers_epoch = 0; a.pers_groups = 0;
+    if (!t.plain && group == 0 && t.pers_state && t.pers_mode != 0 && (c.digitsKept == 2 || c.digitsKept == 3)) {
+        // persistent variant of the two-ciphertext shapes: whenever the plain launch would end on a partial wave
+        // (t.pers_ctas > 0 forces a CTA count, tests)
+        const int groups = (c.batch + 1) / 2;
+        int ctas = std::min(sm_count, groups);
+        bool use = groups > sm_count && groups % sm_count != 0;
+        if (t.pers_ctas > 0) {
+            ctas = std::min(std::min(t.pers_ctas, groups), sm_count);
+            use = true;
+        }
+        if (use && ctas <= t.pers_slots) {
+            a.pers_state = t.pers_state; a.pers_flags = t.pers_flags; a.pers_epoch = t.pers_epoch;
+            return c.digitsKept == 2 ? launch_w_pers<2, 2>(a, s, ctas) : launch_w_pers<3, 2>(a, s, ctas);
+        }
+    }
     if (t.plain) {   // DK template = kept digits + 1 (the accumulator rows take the place of the eliminated digit)
         if (c.digitsKept == 1)
             return one ? launch_w<2, 1, true>(a, s) : launch_w<2, 2, true>(a, s);

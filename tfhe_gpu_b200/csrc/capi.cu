@@ -144,7 +144,8 @@ struct Dev {
     u64* twUw = nullptr;
     void* ksk = nullptr;
     u64* ks_partial = nullptr;   // column-sum accumulator of split key switches (batches below one ciphertext per SM)
-    u32* pers_state = nullptr;   // persistent blind rotation: hand-over slots of split groups, one per SM (br_cggi32.cu)
+    void* pers_state = nullptr;  // persistent blind rotation: hand-over slots of split groups, one per SM (br_cggi32.cu)
+    size_t pers_slot_bytes = 0;
     u32* pers_flags = nullptr;   // ... and their completion flags (hold the epoch of the launch that filled the slot)
     u32 pers_epoch = 0;
     Arena ws;
@@ -854,9 +855,6 @@ static int setup_impl(const tfhe_b200_params* params, const KeySource* src, cons
             CUDA_TRY(cudaGetDeviceProperties(&prop, d.id));
             d.sm_count = prop.multiProcessorCount;
             CUDA_TRY(cudaMalloc((void**)&d.ks_partial, mkmswitch_partial_bytes(h->row_stride, 2 * d.sm_count)));
-            CUDA_TRY(cudaMalloc((void**)&d.pers_state, (size_t)d.sm_count * PERS_SLOT_WORDS * 4));
-            CUDA_TRY(cudaMalloc((void**)&d.pers_flags, (size_t)d.sm_count * 4));
-            CUDA_TRY(cudaMemset(d.pers_flags, 0, (size_t)d.sm_count * 4));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_in, cudaStreamNonBlocking));
             CUDA_TRY(cudaStreamCreateWithFlags(&d.xfer_out, cudaStreamNonBlocking));
@@ -1162,19 +1160,43 @@ struct AccDesc {
     u64 ext_add_b = 0;
 };
 
-static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, int* launches) {
+// Hand-over slots of the persistent blind rotation (one per SM, allocated on first use) and a fresh epoch: the flags
+// hold the epoch of the launch that filled them, so they never need clearing between launches.
+static int pers_prepare(Dev& d, size_t slot_bytes) {
+    if (!d.pers_flags) {
+        CUDA_TRY(cudaMalloc((void**)&d.pers_flags, (size_t)d.sm_count * 4));
+        CUDA_TRY(cudaMemsetAsync(d.pers_flags, 0, (size_t)d.sm_count * 4, d.stream));
+    }
+    if (d.pers_slot_bytes < slot_bytes) {
+        if (d.pers_state) {
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+            CUDA_TRY(cudaFree(d.pers_state));
+            d.pers_state = nullptr;
+            d.pers_slot_bytes = 0;
+        }
+        CUDA_TRY(cudaMalloc(&d.pers_state, (size_t)d.sm_count * slot_bytes));
+        d.pers_slot_bytes = slot_bytes;
+    }
+    if (++d.pers_epoch == 0) {   // wrapped: start over
+        CUDA_TRY(cudaMemsetAsync(d.pers_flags, 0, (size_t)d.sm_count * 4, d.stream));
+        d.pers_epoch = 1;
+    }
+    return 0;
+}
+
+static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, int* launches, bool allow_pers = true) {
     if (c.batch <= 0)
         return 0;
     NvtxRange nvtx("tfhe_b200:blind_rotate");
     if (h->have_cggi32 && !h->force_generic) {
         CGGI32Tables t;
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB; t.skip_top = h->skip_top;
-        if (++d.pers_epoch == 0) {   // the flags hold the epoch of the launch that filled them: start over after a wrap
-            CUDA_TRY(cudaMemsetAsync(d.pers_flags, 0, (size_t)d.sm_count * 4, d.stream));
-            d.pers_epoch = 1;
+        t.pers_mode = (getenv("TFHE_B200_NO_PERSISTENT") || !allow_pers) ? 0 : h->pers_mode; t.pers_ctas = h->pers_ctas;
+        if (t.pers_mode) {
+            int rc = pers_prepare(d, PERS_SLOT_WORDS * 4);
+            if (rc) return rc;
+            t.pers_state = (u32*)d.pers_state; t.pers_flags = d.pers_flags; t.pers_epoch = d.pers_epoch; t.pers_slots = d.sm_count;
         }
-        t.pers_state = d.pers_state; t.pers_flags = d.pers_flags; t.pers_epoch = d.pers_epoch; t.pers_slots = d.sm_count;
-        t.pers_mode = getenv("TFHE_B200_NO_PERSISTENT") ? 0 : h->pers_mode; t.pers_ctas = h->pers_ctas;
         CUDA_TRY(launch_br_cggi32(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_dm32 && !h->force_generic) {
@@ -1193,6 +1215,12 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
         CGGI64WTables t;
         t.mod = h->m64; t.bk = d.bk_cggi64; t.psi_pow = (const u64*)d.psi_pow; t.twC = d.twCw; t.twB = d.twBw; t.twU = d.twUw;
         t.plain = !h->skip_top;
+        t.pers_mode = (getenv("TFHE_B200_NO_PERSISTENT") || !allow_pers) ? 0 : h->pers_mode; t.pers_ctas = h->pers_ctas;
+        if (t.pers_mode && !t.plain) {
+            int rc = pers_prepare(d, PERS_SLOT_WORDS64 * 8);
+            if (rc) return rc;
+            t.pers_state = (u64*)d.pers_state; t.pers_flags = d.pers_flags; t.pers_epoch = d.pers_epoch; t.pers_slots = d.sm_count;
+        }
         CUDA_TRY(launch_br_cggi64w(c, t, d.stream, d.sm_count, h->group));
     }
     else if (h->have_cggi64 && !h->force_generic) {
@@ -1244,8 +1272,15 @@ static int throughput_group(const tfhe_b200_handle* h) {
 // groups / SMs wave times)?  Then neither the tail launch nor wave-aligned chunks are needed.
 static bool persistent_shape(const tfhe_b200_handle* h) {
     int g = 0;
-    return h->have_cggi32 && !h->force_generic && h->group == 0 && h->pers_mode != 0 && !getenv("TFHE_B200_NO_PERSISTENT") &&
-           cggi32_pers_shape(h->logN, h->d / 2, h->skip_top, h->p.Q, &g);
+    if (h->force_generic || h->group != 0 || h->pers_mode == 0 || getenv("TFHE_B200_NO_PERSISTENT"))
+        return false;
+    if (h->have_cggi32)
+        return cggi32_pers_shape(h->logN, h->d / 2, h->skip_top, h->p.Q, &g);
+    if (h->have_dm32 || h->have_dm64w)
+        return false;
+    if (h->have_cggi64w && !getenv("TFHE_B200_C64_NARROW"))   // the two-ciphertext shapes with top-digit elimination
+        return h->skip_top && (h->d / 2 == 2 || h->d / 2 == 3);
+    return false;
 }
 static void tail_shapes(const tfhe_b200_handle* h, int* per_cta, int* tail_per_sm) {
     *per_cta = *tail_per_sm = 0;
@@ -1292,14 +1327,28 @@ static int blind_rotate(tfhe_b200_handle* h, Dev& d, int batch, const u64* ct, u
     // STD128 at 2048 ciphertexts per GPU (16384 over 8 GPUs): 3 waves of 5.7 ms + one of 4.4 ms instead of 4 x 5.7 ms.
     int per_cta, tail_per_sm;
     tail_shapes(h, &per_cta, &tail_per_sm);
-    const int wave = per_cta * d.sm_count;
-    const int rem = wave ? batch % wave : 0;
-    if (wave && batch > wave && rem > 0 && rem <= tail_per_sm * d.sm_count && !getenv("TFHE_B200_NO_TAIL")) {
-        const int head = batch - rem;
+    int wave = per_cta * d.sm_count;
+    int rem = wave ? batch % wave : 0;
+    bool split = wave && batch > wave && rem > 0 && rem <= tail_per_sm * d.sm_count && !getenv("TFHE_B200_NO_TAIL");
+    int head = batch - rem;
+    bool head_pers = true;
+    if (persistent_shape(h) && h->have_cggi64w && !h->have_cggi32 && h->pers_ctas == 0) {
+        // The persistent variant staggers its CTAs over the rotation steps.  The 32-bit kernels do not care (their key
+        // lives in L2); the 54-bit keys (342 / 513 MB) are streamed from HBM once per wave by CTAs in lock-step, and once
+        // per CTA when staggered: measured 2-3 % per step.  So only the end of a launch -- the last whole wave plus the
+        // remainder -- runs persistently; everything before it runs as plain lock-step waves.
+        wave = throughput_group(h) * d.sm_count;
+        rem = batch % wave;
+        head = (batch / wave - 1) * wave;
+        split = rem > 0 && head > 0;
+        head_pers = false;
+    }
+    if (split) {
         c.batch = head;
-        int r = blind_rotate_launch(h, d, c, launches);
+        int r = blind_rotate_launch(h, d, c, launches, head_pers);
         if (r)
             return r;
+        rem = batch - head;
         c.batch = rem;
         c.ct = ct + (size_t)head * (p.n + 1);
         if (c.table && a.mode == ACC_TABLE_PER)

@@ -108,7 +108,13 @@ struct CGGI64WTables {
     const u64* twB;       // device [16][8][2]
     const u64* twU;       // device [2][15][2]
     bool plain = false;   // no top-digit elimination (untransformed key, thrown digits honoured)
+    // persistent variant (see CGGI32Tables): slots of PERS_SLOT_WORDS64 u64
+    u64* pers_state = nullptr;
+    u32* pers_flags = nullptr;
+    u32 pers_epoch = 0;
+    int pers_slots = 0, pers_mode = 1, pers_ctas = 0;
 };
+constexpr size_t PERS_SLOT_WORDS64 = 16384;   // 2 images x 2 ciphertexts x 2 components x 2048 coefficients
 bool cggi64w_supported(const tfhe_b200_params& p);
 bool cggi64w_plain_supported(const tfhe_b200_params& p);
 void cggi64w_build_tables(const tfhe_b200_params& p, std::vector<u64>& twU, std::vector<u64>& twB, std::vector<u64>& twC);

@@ -50,8 +50,10 @@ struct KCfg {
 
 // ---- register-resident NTT passes -----------------------------------------------------------------------------
 // forward pass A: Cooley-Tukey stages with stride TPN*2^s, s = 4..0 (uniform twiddles from the parameter bank)
+// `add0`: a constant still to be added to v[0..15] (the lower operands of the first stage): it rides in the third operand
+// of that stage's additions (digit polynomials: the offset Q - B/2 of the first sixteen coefficients, br_cggi32.cu)
 template <typename A>
-__device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
+__device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2, u32 add0) {
     const u32 Z = args.zero;
 #pragma unroll
     for (int s = 4; s >= 0; s--) {
@@ -62,10 +64,14 @@ __device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u3
             const int ti = (16 >> s) + (r >> (s + 1));
             u32 t = shoup_mul(v[r + (1 << s)], args.twA_f[ti][0], args.twA_f[ti][1], Q);
             u32 x = v[r];
-            v[r] = x + t + Z;
-            v[r + (1 << s)] = x - t + Q2;
+            v[r] = x + t + (s == 4 ? add0 : Z);
+            v[r + (1 << s)] = x - t + (s == 4 ? Q2 + add0 : Q2);
         }
     }
+}
+template <typename A>
+__device__ __forceinline__ void fwd_passA(u32 (&v)[32], const A& args, u32 Q, u32 Q2) {
+    fwd_passA(v, args, Q, Q2, args.zero);
 }
 // Mid-transform sweep for 28-bit moduli: the lazy forward transform lets values grow by 2Q per stage, (2 + 2 s) Q after
 // s stages, and 22 Q must fit 32 bits -- true for the 27-bit primes only.  Bringing the values back below 2Q between the
@@ -191,7 +197,8 @@ __device__ __forceinline__ void fwd_passB(u32 (&v)[32], const u32 (&tw)[32], con
 }
 // inverse pass B' on the MIRRORED block (virtual thread TPN-1-T): Gentleman-Sande stages 2^s, s = 0..PB-1, with
 // (U - V) * psi^-x == (V - U) * psi^{mirror}; all values kept below 2Q
-template <int PB>
+// CANON: the inputs are canonical (< Q), so the sums of the first stage are below 2Q without a correction
+template <int PB, bool CANON = false>
 __device__ __forceinline__ void inv_passB(u32 (&v)[32], const u32 (&tw)[32], const u32 (&twp)[32], u32 Q, u32 Q2,
                                           u32 Z) {
 #pragma unroll
@@ -204,7 +211,7 @@ __device__ __forceinline__ void inv_passB(u32 (&v)[32], const u32 (&tw)[32], con
                 continue;
             const int ti = off + (cnt - 1 - (r >> (s + 1)));
             u32 U = v[r], V = v[r + (1 << s)];
-            v[r] = cond_sub(U + V + Z, Q2);
+            v[r] = (CANON && s == 0) ? U + V + Z : cond_sub(U + V + Z, Q2);
             v[r + (1 << s)] = shoup_mul(V - U + Q2, tw[ti], twp[ti], Q);
         }
     }

@@ -3,7 +3,7 @@
 // No Python, no torch: start-up is a second, so a GPU call spends its time on the kernels.
 //
 //   g++ -O2 -o build/abbench tools/abbench.cpp -I include -I /usr/local/cuda/include -L /usr/local/cuda/lib64 -lcudart -ldl
-//   abbench [--set std128|toy|ap] [--batch B[,B..]] [--reps R] SPEC [SPEC ...]
+//   abbench [--set std128|ap|func12|sign17] [--batch B[,B..]] [--reps R] SPEC [SPEC ...]
 //   SPEC = path/to/libtfhe_b200.so[:option=value[:option=value]]     (options of tfhe_b200_set_option)
 //
 // Keys come from tfhe_b200_keygen_test_seed of the FIRST library (deterministic), inputs are uniform random words.
@@ -29,6 +29,7 @@ struct Lib {
     decltype(&tfhe_b200_last_error) last_error;
     decltype(&tfhe_b200_set_option) set_option;
     decltype(&tfhe_b200_eval_bin_gate) eval_bin_gate;
+    decltype(&tfhe_b200_bootstrap_func) bootstrap_func;
     decltype(&tfhe_b200_keygen_test_seed) keygen;
     decltype(&tfhe_b200_bk_words) bk_words;
     decltype(&tfhe_b200_ksk_words) ksk_words;
@@ -58,6 +59,7 @@ int main(int argc, char** argv) {
     std::string set = "std128";
     std::vector<int> batches = {16384};
     int reps = 5, gate = TFHE_B200_NAND;
+    bool func = false;   // time ONE BootstrapFunc (blind rotation + MS/KS/MS) instead of a gate
     std::vector<Lib> libs;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -96,6 +98,12 @@ int main(int argc, char** argv) {
         P.method = set == "ap" ? TFHE_B200_METHOD_AP : TFHE_B200_METHOD_GINX;
         P.digitsR = set == "ap" ? 2 : 0;
     }
+    else if (set == "func12" || set == "sign17") {   // the STD128 functional sets (logQ = 12 arbitrary LUT, logQ = 17)
+        P.n = 1305; P.N = 2048; P.q = set == "func12" ? 2048 : 4096; P.Q = 18014398509404161ULL; P.qKS = 34359738368ULL;
+        P.baseKS = 32; P.dKS = 7; P.baseG = set == "func12" ? 134217728u : 262144u; P.digitsG = set == "func12" ? 2 : 3;
+        P.baseR = 23; P.psi = 2604308523238ULL; P.beta = 128; P.method = TFHE_B200_METHOD_GINX;
+        func = true;
+    }
     else {
         fprintf(stderr, "unknown set %s\n", set.c_str());
         return 1;
@@ -109,6 +117,7 @@ int main(int argc, char** argv) {
 #define SYM(f, name) L.f = (decltype(L.f))dlsym(L.dl, name); if (!L.f) { fprintf(stderr, "missing %s\n", name); return 2; }
         SYM(setup, "tfhe_b200_setup") SYM(clean, "tfhe_b200_clean") SYM(last_error, "tfhe_b200_last_error")
         SYM(set_option, "tfhe_b200_set_option") SYM(eval_bin_gate, "tfhe_b200_eval_bin_gate")
+        SYM(bootstrap_func, "tfhe_b200_bootstrap_func")
         SYM(keygen, "tfhe_b200_keygen_test_seed") SYM(bk_words, "tfhe_b200_bk_words") SYM(ksk_words, "tfhe_b200_ksk_words")
         SYM(variant, "tfhe_b200_kernel_variant")
     }
@@ -143,7 +152,12 @@ int main(int argc, char** argv) {
     CK(cudaFree(ksk));
     const size_t W = P.n + 1;
     for (int batch : batches) {
-        std::vector<uint64_t> hin(2 * (size_t)batch * W), hout((size_t)batch * W);
+        std::vector<uint64_t> hin(2 * (size_t)batch * W), hout((size_t)batch * W), htab(P.q);
+        for (size_t i = 0; i < htab.size(); i++)
+            htab[i] = (i * 2654435761ULL) % P.q;
+        uint64_t* tab;
+        CK(cudaMalloc(&tab, P.q * 8));
+        CK(cudaMemcpy(tab, htab.data(), P.q * 8, cudaMemcpyHostToDevice));
         unsigned long long x = 0x9E3779B97F4A7C15ULL + batch;
         for (auto& v : hin) {
             x ^= x << 13; x ^= x >> 7; x ^= x << 17;
@@ -162,7 +176,8 @@ int main(int argc, char** argv) {
                 Lib& L = libs[k];
                 tfhe_b200_stats st;
                 CK(cudaMemset(out, 0, (size_t)batch * W * 8));
-                if (L.eval_bin_gate(L.h, gate, batch, c1, c2, P.q, out, TFHE_B200_DEVICE, &st)) {
+                if (func ? L.bootstrap_func(L.h, batch, c1, P.q, tab, 0, P.q, out, TFHE_B200_DEVICE, &st)
+                         : L.eval_bin_gate(L.h, gate, batch, c1, c2, P.q, out, TFHE_B200_DEVICE, &st)) {
                     fprintf(stderr, "eval %s: %s\n", L.spec.c_str(), L.last_error());
                     return 2;
                 }
@@ -186,6 +201,7 @@ int main(int argc, char** argv) {
                    sum[k] == sum[0] ? "true" : "false");
             fflush(stdout);
         }
+        CK(cudaFree(tab));
         CK(cudaFree(c1));
         CK(cudaFree(c2));
         CK(cudaFree(out));
