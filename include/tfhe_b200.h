@@ -119,7 +119,10 @@ const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h);
  *   "force_generic" = 1  run the generic kernel instead of the specialised one (cross-check of the two implementations)
  *   "group"              ciphertexts per CTA of the specialised CGGI kernels: 0 = automatic (throughput shape for large
  *                        batches, latency shapes for batches that cannot fill the SMs), 4 / 2 = fixed, 1 = one
- *                        ciphertext per CTA (32-bit rings: the latency layout, one warp per digit polynomial) */
+ *                        ciphertext per CTA (32-bit rings: the latency layout, one warp per digit polynomial)
+ *   "persistent"         1 (default) = launches that would end on a partial wave of CTAs run the persistent variant of the
+ *                        blind rotation (one CTA per SM, the launch's rotation steps cut into equal ranges); 0 = never
+ *   "persistent_ctas"    > 0 forces the persistent variant with this many CTAs (tests: splits at arbitrary steps) */
 int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value);
 
 /* --------------------------------------------------------------------------------------------------------

@@ -65,9 +65,10 @@ def test_pageable_pinned_and_device_buffers_agree(rng):
 
 @pytest.mark.parametrize("tail", [100, 272])
 def test_cggi32_tail_launch(tail, rng, monkeypatch):
-    """STD128-shaped ring: a batch of one full wave of 4-ciphertext CTAs plus a remainder of <= 1 (latency layout) or
-    <= 2 (CTAs of two) ciphertexts per SM runs as two launches; the bits equal the single-launch result and the oracle,
-    in particular across the seam, for gate, per-ciphertext LUT and explicit accumulators."""
+    """STD128-shaped ring: a batch of one full wave of 4-ciphertext CTAs plus a remainder.  By default it is ONE launch of
+    the persistent variant (no wave quantisation); with that switched off the remainder of <= 1 (latency layout) or <= 2
+    (CTAs of two) ciphertexts per SM runs as a second launch.  The bits equal the single-launch result and the oracle
+    every way, in particular across the seam, for gate, per-ciphertext LUT and explicit accumulators."""
     p = po.Port.params_custom(12, 1024, 1024, Q27, 128, 1 << 7, 32, po.GINX)
     port = po.Port(p)
     sk, bk, ksk, g = _ctx(p, port)
@@ -78,6 +79,10 @@ def test_cggi32_tail_launch(tail, rng, monkeypatch):
         c1 = rng.integers(0, q, (batch, n + 1), dtype=np.uint64)
         c2 = rng.integers(0, q, (batch, n + 1), dtype=np.uint64)
         want = port.eval_bin_gate(bk, ksk, po.GATES["NAND"], c1, c2, q)
+        got = g.EvalBinGate("NAND", c1, c2)
+        assert g.last_stats.kernel_launches == 3              # affine, ONE persistent blind rotation, key switch
+        assert np.array_equal(got, want)
+        g.set_option("persistent", 0)
         got = g.EvalBinGate("NAND", c1, c2)
         assert g.last_stats.kernel_launches == 4              # affine, two blind rotations, key switch
         assert np.array_equal(got, want)
@@ -96,6 +101,10 @@ def test_cggi32_tail_launch(tail, rng, monkeypatch):
         got = g.EvalAcc(am, q, acc)
         assert np.array_equal(got[seam], port.eval_acc(bk, am[seam], q, acc[seam]))
         assert np.array_equal(got[-2:], port.eval_acc(bk, am[-2:], q, acc[-2:]))
+        got_f = g.BootstrapFunc(c1, q, tab, q)
+        g.set_option("persistent", 1)                          # one CTA per SM, every group boundary a potential split
+        assert np.array_equal(g.EvalAcc(am, q, acc), got)
+        assert np.array_equal(g.BootstrapFunc(c1, q, tab, q), got_f)
     finally:
         g.GPUClean()
 
@@ -126,9 +135,14 @@ def test_dm32_and_cggi64w_tail_launch(rng):
         batch = 2 * sm + sm - 7
         ct = rng.integers(0, q, (batch, n + 1), dtype=np.uint64)
         tab = rng.integers(0, q, q, dtype=np.uint64)
+        want = port.bootstrap_func(bk, ksk, ct, q, tab, q)
         got = g.BootstrapFunc(ct, q, tab, q)
-        assert g.last_stats.kernel_launches == 3
-        assert np.array_equal(got, port.bootstrap_func(bk, ksk, ct, q, tab, q))
+        assert g.last_stats.kernel_launches == 2              # one persistent blind rotation, key switch
+        assert np.array_equal(got, want)
+        g.set_option("persistent", 0)
+        got = g.BootstrapFunc(ct, q, tab, q)
+        assert g.last_stats.kernel_launches == 3              # throughput shape + latency-shaped tail, key switch
+        assert np.array_equal(got, want)
     finally:
         g.GPUClean()
 
