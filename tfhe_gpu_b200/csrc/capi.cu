@@ -1879,6 +1879,16 @@ static int eval_bin_gate_impl(tfhe_b200_handle* h, int gate, int batch, const Ga
             for (int k = 0; k < nch; k++)
                 coff[k + 1] = std::min(count, coff[k] + wsz[k] * unit);
             coff[nch] = count;
+            if (persistent_shape(h) && nch > 2) {
+                // A persistent blind rotation costs groups / SMs wave times whatever the chunk size, and its staggered
+                // CTAs run a step 1.7 % faster than lock-step waves (all SMs asking L2 for the same key lines at the same
+                // moment), so the middle chunks share everything between the first and the last wave EVENLY instead of
+                // in whole waves: 16384 gates = 1 + 5 x 5.13 + 1 waves.
+                const int g = throughput_group(h), nmid = nch - 2;
+                const int each = (count - 2 * unit) / nmid / g * g;
+                for (int k = 1; k < nch - 1; k++)
+                    coff[k + 1] = coff[k] + each;   // the last chunk (one wave + the rounding) ends at count
+            }
             cudaEvent_t* ev_in = d.pev;
             cudaEvent_t* ev_done = d.pev + MAX_CHUNKS;
             cudaEvent_t* ev_out = d.pev + 2 * MAX_CHUNKS;
