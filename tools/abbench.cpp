@@ -3,7 +3,7 @@
 // No Python, no torch: start-up is a second, so a GPU call spends its time on the kernels.
 //
 //   g++ -O2 -o build/abbench tools/abbench.cpp -I include -I /usr/local/cuda/include -L /usr/local/cuda/lib64 -lcudart -ldl
-//   abbench [--set std128|ap|func12|sign17] [--batch B[,B..]] [--reps R] SPEC [SPEC ...]
+//   abbench [--set std128|ap|toy|medium|std128_ap_set|std256|std256q|func12|sign17] [--batch B[,B..]] [--reps R] SPEC [SPEC ...]
 //   SPEC = path/to/libtfhe_b200.so[:option=value[:option=value]]     (options of tfhe_b200_set_option)
 //
 // Keys come from tfhe_b200_keygen_test_seed of the FIRST library (deterministic), inputs are uniform random words.
@@ -97,6 +97,26 @@ int main(int argc, char** argv) {
         P.baseG = 128; P.digitsG = 4; P.baseR = 32; P.psi = 282116; P.beta = 128;
         P.method = set == "ap" ? TFHE_B200_METHOD_AP : TFHE_B200_METHOD_GINX;
         P.digitsR = set == "ap" ? 2 : 0;
+    }
+    else if (set == "toy") {            // binfhecontext.cpp:139
+        P.n = 64; P.N = 512; P.q = 512; P.Q = 134215681ULL; P.qKS = 134215681ULL; P.baseKS = 25; P.dKS = 6;
+        P.baseG = 512; P.digitsG = 3; P.baseR = 23; P.psi = 78074; P.beta = 128; P.method = TFHE_B200_METHOD_GINX;
+    }
+    else if (set == "medium") {         // binfhecontext.cpp:140 (28-bit modulus: reduction sweep)
+        P.n = 422; P.N = 1024; P.q = 1024; P.Q = 268369921ULL; P.qKS = 16384; P.baseKS = 128; P.dKS = 2;
+        P.baseG = 1024; P.digitsG = 3; P.baseR = 32; P.psi = 326097; P.beta = 128; P.method = TFHE_B200_METHOD_GINX;
+    }
+    else if (set == "std128_ap_set") {  // binfhecontext.cpp:141 under GINX (three digits, top digit may wrap: plain path)
+        P.n = 512; P.N = 1024; P.q = 1024; P.Q = 134215681ULL; P.qKS = 16384; P.baseKS = 128; P.dKS = 2;
+        P.baseG = 512; P.digitsG = 3; P.baseR = 32; P.psi = 282116; P.beta = 128; P.method = TFHE_B200_METHOD_GINX;
+    }
+    else if (set == "std256") {         // binfhecontext.cpp:147 (N = 2048, 29-bit modulus)
+        P.n = 1024; P.N = 2048; P.q = 2048; P.Q = 536813569ULL; P.qKS = 16384; P.baseKS = 128; P.dKS = 2;
+        P.baseG = 256; P.digitsG = 4; P.baseR = 46; P.psi = 145054; P.beta = 128; P.method = TFHE_B200_METHOD_GINX;
+    }
+    else if (set == "std256q") {        // binfhecontext.cpp:153 (N = 2048, 27-bit modulus)
+        P.n = 2048; P.N = 2048; P.q = 2048; P.Q = 134176769ULL; P.qKS = 65536; P.baseKS = 16; P.dKS = 4;
+        P.baseG = 128; P.digitsG = 4; P.baseR = 46; P.psi = 100530; P.beta = 128; P.method = TFHE_B200_METHOD_GINX;
     }
     else if (set == "func12" || set == "sign17") {   // the STD128 functional sets (logQ = 12 arbitrary LUT, logQ = 17)
         P.n = 1305; P.N = 2048; P.q = set == "func12" ? 2048 : 4096; P.Q = 18014398509404161ULL; P.qKS = 34359738368ULL;
