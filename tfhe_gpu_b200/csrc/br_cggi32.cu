@@ -54,6 +54,8 @@ struct CGGI32Args {
     u32* pers_flags;     // [slot] launch epoch once the slot's image is complete
     u32 pers_epoch;
     u32 pers_groups;     // ceil(batch / G)
+    u32* pers_ticket;    // running count of persistent CTAs started on this device (never reset)
+    u32 pers_ticket_base;   // ... its value when this launch starts
 };
 
 // ---- TMA bulk copies + mbarriers (key streaming of the TMA variant) ----------------------------------------------
@@ -160,9 +162,20 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     // ---- persistent variant: this CTA's range of the launch's groups * n rotation steps ----------------------------
     u32 gA = 0, sA = 0, gB = 0, sB = 0, first_full = 0;
     int n_full = 0, n_items = 1;
+    // The ranges are handed out in the order the CTAs START (a ticket, as in decoupled look-back scans), not by
+    // blockIdx: range k only ever waits for range k - 1, whose CTA is then running or done whatever order the hardware
+    // dispatches blocks in.
+    u32 bid = blockIdx.x;
+    if (PERS) {
+        __shared__ u32 s_bid;
+        if (tid == 0)
+            s_bid = atomicAdd(A.pers_ticket, 1u) - A.pers_ticket_base;
+        __syncthreads();
+        bid = s_bid;
+    }
     if (PERS) {
         const u64 Wt = (u64)A.pers_groups * n;
-        const u64 lo = Wt * blockIdx.x / gridDim.x, hi = Wt * (blockIdx.x + 1) / gridDim.x;
+        const u64 lo = Wt * bid / gridDim.x, hi = Wt * (bid + 1) / gridDim.x;
         gA = (u32)(lo / n); sA = (u32)(lo % n); gB = (u32)(hi / n); sB = (u32)(hi % n);
         first_full = gA + (sA ? 1 : 0);
         n_full = (int)gB - (int)first_full;
@@ -201,7 +214,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 
     for (int item = 0; item < n_items; item++) {
     // this item: rotation steps [sb, se) of group grp (the whole rotation unless PERS)
-    u32 grp = blockIdx.x, sb = 0, se = n;
+    u32 grp = bid, sb = 0, se = n;
     if (PERS) {
         const int u = item - (sB ? 1 : 0);
         if (u < 0) { grp = gB; se = sB; }
@@ -287,7 +300,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 
     if (PERS && sb > 0) {
         // the head of this group was run by the previous CTA at the start of the launch: wait for its image
-        const u32 slot = blockIdx.x - 1;
+        const u32 slot = bid - 1;
         if (tid == 0) {
             u32 f, spins = 0;
             for (;;) {
@@ -631,7 +644,7 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
 
     if (PERS && se < n) {
         // head part of a split group: leave the accumulator image for the next CTA
-        const u32 slot = blockIdx.x;
+        const u32 slot = bid;
         uint4* dst4 = reinterpret_cast<uint4*>(A.pers_state) + (((size_t)slot * 2 * G + g) * 2 + j) * (N / 4) + T * 8;
 #pragma unroll
         for (int x = 0; x < 8; x++)
@@ -940,6 +953,7 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
     a.ninvM = to_mont<u32>(h_powmod((u64)1 << c.logN, t.mod.Q - 2, t.mod.Q), t.mod);
     const int dk = (int)c.digitsKept;
     a.pers_state = nullptr; a.pers_flags = nullptr; a.pers_epoch = 0; a.pers_groups = 0;
+    a.pers_ticket = nullptr; a.pers_ticket_base = 0;
     {
         // Persistent variant: whenever the plain launch would end on a partial wave (t.pers_ctas > 0 forces a CTA count,
         // tests).  The caller owns the hand-over slots and bumps the epoch per launch.
@@ -954,6 +968,9 @@ cudaError_t launch_br_cggi32(const BRCommon& c, const CGGI32Tables& t, cudaStrea
             }
             if (use && ctas <= t.pers_slots) {
                 a.pers_state = t.pers_state; a.pers_flags = t.pers_flags; a.pers_epoch = t.pers_epoch;
+                a.pers_ticket = t.pers_ticket; a.pers_ticket_base = t.pers_ticket_base;
+                if (t.pers_launched)
+                    *t.pers_launched = ctas;
                 if (c.logN == 10)
                     return launch_pers<10, 4, 4, true>(a, s, ctas);
                 return launch_pers<9, 3, 8, false>(a, s, ctas);

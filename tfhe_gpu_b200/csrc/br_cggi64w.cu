@@ -38,6 +38,8 @@ struct CGGI64WArgs {
     u32* pers_flags;     // [slot] launch epoch once the slot's image is complete
     u32 pers_epoch;
     u32 pers_groups;     // ceil(batch / G)
+    u32* pers_ticket;    // running count of persistent CTAs started on this device (never reset)
+    u32 pers_ticket_base;   // ... its value when this launch starts
 };
 
 // PLAIN = true: no top-digit elimination (thrown digits, or a top digit that is neither exact nor repairable).  The
@@ -75,9 +77,20 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
     // persistent variant: this CTA's range of the launch's groups * n rotation steps (br_cggi32.cu)
     u32 gA = 0, sA = 0, gB = 0, sB = 0, first_full = 0;
     int n_full = 0, n_items = 1;
+    // The ranges are handed out in the order the CTAs START (a ticket, as in decoupled look-back scans), not by
+    // blockIdx: range k only ever waits for range k - 1, whose CTA is then running or done whatever order the hardware
+    // dispatches blocks in.
+    u32 bid = blockIdx.x;
+    if (PERS) {
+        __shared__ u32 s_bid;
+        if (tid == 0)
+            s_bid = atomicAdd(A.pers_ticket, 1u) - A.pers_ticket_base;
+        __syncthreads();
+        bid = s_bid;
+    }
     if (PERS) {
         const u64 Wt = (u64)A.pers_groups * n;
-        const u64 lo = Wt * blockIdx.x / gridDim.x, hi = Wt * (blockIdx.x + 1) / gridDim.x;
+        const u64 lo = Wt * bid / gridDim.x, hi = Wt * (bid + 1) / gridDim.x;
         gA = (u32)(lo / n); sA = (u32)(lo % n); gB = (u32)(hi / n); sB = (u32)(hi % n);
         first_full = gA + (sA ? 1 : 0);
         n_full = (int)gB - (int)first_full;
@@ -119,7 +132,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
 
     for (int item = 0; item < n_items; item++) {
     // this item: rotation steps [sb, se) of group grp (the whole rotation unless PERS)
-    u32 grp = blockIdx.x, sb = 0, se = n;
+    u32 grp = bid, sb = 0, se = n;
     if (PERS) {
         const int u = item - (sB ? 1 : 0);
         if (u < 0) { grp = gB; se = sB; }
@@ -134,7 +147,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
     // ---- accumulator initialisation in A layout (coefficient idx = T + 128 r) -----------------------------------
     if (PERS && sb > 0) {
         // the head of this group was run by the previous CTA at the start of the launch: wait for its image
-        const u32 slot = blockIdx.x - 1;
+        const u32 slot = bid - 1;
         if (tid == 0) {
             u32 f, spins = 0;
             for (;;) {
@@ -400,7 +413,7 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
 
     if (PERS && se < n) {
         // head part of a split group: leave the accumulator image for the next CTA (phase 3 only read the top rows)
-        const u32 slot = blockIdx.x;
+        const u32 slot = bid;
         u64* dst = A.pers_state + (((size_t)slot * 2 * G + g) * 2 + j) * N;
 #pragma unroll
         for (int r = 0; r < CPT; r++)
@@ -567,6 +580,7 @@ cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStr
     // for the SM) finishes a rotation step sooner; `group` = 1 / 2 forces a shape (tests, measurements)
     const bool one = group == 1 || (group == 0 && sm_count > 0 && c.batch <= sm_count);
     a.pers_state = nullptr; a.pers_flags = nullptr; a.pers_epoch = 0; a.pers_groups = 0;
+    a.pers_ticket = nullptr; a.pers_ticket_base = 0;
     if (!t.plain && group == 0 && t.pers_state && t.pers_mode != 0 && (c.digitsKept == 2 || c.digitsKept == 3)) {
         // persistent variant of the two-ciphertext shapes: whenever the plain launch would end on a partial wave
         // (t.pers_ctas > 0 forces a CTA count, tests)
@@ -579,6 +593,9 @@ cudaError_t launch_br_cggi64w(const BRCommon& c, const CGGI64WTables& t, cudaStr
         }
         if (use && ctas <= t.pers_slots) {
             a.pers_state = t.pers_state; a.pers_flags = t.pers_flags; a.pers_epoch = t.pers_epoch;
+            a.pers_ticket = t.pers_ticket; a.pers_ticket_base = t.pers_ticket_base;
+            if (t.pers_launched)
+                *t.pers_launched = ctas;
             return c.digitsKept == 2 ? launch_w_pers<2, 2>(a, s, ctas) : launch_w_pers<3, 2>(a, s, ctas);
         }
     }

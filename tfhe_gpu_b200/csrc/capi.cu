@@ -146,8 +146,10 @@ struct Dev {
     u64* ks_partial = nullptr;   // column-sum accumulator of split key switches (batches below one ciphertext per SM)
     void* pers_state = nullptr;  // persistent blind rotation: hand-over slots of split groups, one per SM (br_cggi32.cu)
     size_t pers_slot_bytes = 0;
-    u32* pers_flags = nullptr;   // ... and their completion flags (hold the epoch of the launch that filled the slot)
+    u32* pers_flags = nullptr;   // ... and their completion flags (hold the epoch of the launch that filled the slot);
+                                 // word [sm_count] counts the persistent CTAs started so far (range tickets)
     u32 pers_epoch = 0;
+    u32 pers_tickets = 0;        // host shadow of that counter: its value when the next launch starts
     Arena ws;
     Pinned pin;                         // pinned host staging (inputs and outputs of the current call)
     std::vector<PendingOut> pending;    // staged outputs to hand to the caller after the stream has drained
@@ -1164,8 +1166,9 @@ struct AccDesc {
 // hold the epoch of the launch that filled them, so they never need clearing between launches.
 static int pers_prepare(Dev& d, size_t slot_bytes) {
     if (!d.pers_flags) {
-        CUDA_TRY(cudaMalloc((void**)&d.pers_flags, (size_t)d.sm_count * 4));
-        CUDA_TRY(cudaMemsetAsync(d.pers_flags, 0, (size_t)d.sm_count * 4, d.stream));
+        CUDA_TRY(cudaMalloc((void**)&d.pers_flags, (size_t)(d.sm_count + 1) * 4));
+        CUDA_TRY(cudaMemsetAsync(d.pers_flags, 0, (size_t)(d.sm_count + 1) * 4, d.stream));
+        d.pers_tickets = 0;
     }
     if (d.pers_slot_bytes < slot_bytes) {
         if (d.pers_state) {
@@ -1188,6 +1191,7 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
     if (c.batch <= 0)
         return 0;
     NvtxRange nvtx("tfhe_b200:blind_rotate");
+    int pers_launched = 0;
     if (h->have_cggi32 && !h->force_generic) {
         CGGI32Tables t;
         t.mod = h->m32; t.bk = d.bk_cggi32; t.psi_pow = (const u32*)d.psi_pow; t.twA = h->twA_host.data(); t.twB = d.twB; t.skip_top = h->skip_top;
@@ -1196,8 +1200,10 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
             int rc = pers_prepare(d, PERS_SLOT_WORDS * 4);
             if (rc) return rc;
             t.pers_state = (u32*)d.pers_state; t.pers_flags = d.pers_flags; t.pers_epoch = d.pers_epoch; t.pers_slots = d.sm_count;
+            t.pers_ticket = d.pers_flags + d.sm_count; t.pers_ticket_base = d.pers_tickets; t.pers_launched = &pers_launched;
         }
         CUDA_TRY(launch_br_cggi32(c, t, d.stream, d.sm_count, h->group));
+        d.pers_tickets += (u32)pers_launched;
     }
     else if (h->have_dm32 && !h->force_generic) {
         CGGI32Tables t;
@@ -1220,8 +1226,10 @@ static int blind_rotate_launch(tfhe_b200_handle* h, Dev& d, const BRCommon& c, i
             int rc = pers_prepare(d, PERS_SLOT_WORDS64 * 8);
             if (rc) return rc;
             t.pers_state = (u64*)d.pers_state; t.pers_flags = d.pers_flags; t.pers_epoch = d.pers_epoch; t.pers_slots = d.sm_count;
+            t.pers_ticket = d.pers_flags + d.sm_count; t.pers_ticket_base = d.pers_tickets; t.pers_launched = &pers_launched;
         }
         CUDA_TRY(launch_br_cggi64w(c, t, d.stream, d.sm_count, h->group));
+        d.pers_tickets += (u32)pers_launched;
     }
     else if (h->have_cggi64 && !h->force_generic) {
         CGGI64Tables t;

@@ -69,6 +69,9 @@ struct CGGI32Tables {
     u32* pers_state = nullptr;   // [pers_slots][PERS_SLOT_WORDS]
     u32* pers_flags = nullptr;   // [pers_slots], zero at allocation
     u32 pers_epoch = 0;          // unique per launch on this device (never 0)
+    u32* pers_ticket = nullptr;  // device counter of persistent CTAs started so far (ranges are handed out in start order)
+    u32 pers_ticket_base = 0;    // its value at the start of this launch (host shadow)
+    int* pers_launched = nullptr;   // HOST out: persistent CTAs launched by this call (0 = a plain launch)
     int pers_slots = 0;
     int pers_mode = 1;           // 0 = never, 1 = automatic
     int pers_ctas = 0;           // > 0: force the persistent variant with this many CTAs (tests)
@@ -112,6 +115,9 @@ struct CGGI64WTables {
     u64* pers_state = nullptr;
     u32* pers_flags = nullptr;
     u32 pers_epoch = 0;
+    u32* pers_ticket = nullptr;
+    u32 pers_ticket_base = 0;
+    int* pers_launched = nullptr;
     int pers_slots = 0, pers_mode = 1, pers_ctas = 0;
 };
 constexpr size_t PERS_SLOT_WORDS64 = 16384;   // 2 images x 2 ciphertexts x 2 components x 2048 coefficients
