@@ -125,6 +125,14 @@ const char* tfhe_b200_kernel_variant(const tfhe_b200_handle* h);
  *   "persistent_ctas"    > 0 forces the persistent variant with this many CTAs (tests: splits at arbitrary steps) */
 int tfhe_b200_set_option(tfhe_b200_handle* h, const char* key, int64_t value);
 
+/* Persistent blind rotation, host view of the schedule (no GPU needed; tests and capacity planning).  A launch of
+ * `groups` CTA groups x `n` rotation steps on `ctas` persistent CTAs cuts the groups * n steps into `ctas` equal ranges;
+ * range `cta` is worked off as items in the order the kernel runs them (head of the group shared with the next range,
+ * whole groups, tail of the group shared with the previous range).  Returns the number of items of range `cta` (or a
+ * negative status); if item >= 0, out[0..2] = (group, first step, end step) of that item.  The same code runs on the
+ * device (csrc/engine.cuh: PersRange). */
+int tfhe_b200_persistent_plan(uint32_t groups, uint32_t n, uint32_t ctas, uint32_t cta, int item, uint32_t out[3]);
+
 /* --------------------------------------------------------------------------------------------------------
  * SURVEY.md section 8(f) rank 4 -- dynamic gadget base ("timeOptimization") for EvalSign / EvalDecomp.
  * BinFHEContext::BTKeyGen with timeOptimization fills m_BTKey_map with one RingGSWBTKey (BK and KSK) per gadget base

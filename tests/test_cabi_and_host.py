@@ -132,3 +132,53 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "toy"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("groups,n,ctas", [(4096, 503, 148), (512, 503, 148), (175, 503, 148), (7, 13, 3), (7, 13, 7),
+                                           (2048, 64, 148), (149, 1305, 148), (5, 1, 5), (1000, 2048, 132)])
+def test_persistent_schedule_properties(groups, n, ctas):
+    """The schedule of the persistent blind rotation (csrc/engine.cuh PersRange, the code the kernels run, through its
+    host entry point): every (group, step) is covered exactly once; the ranges differ by at most one step; a group is
+    split between at most two neighbouring ranges; the head of a split group is the FIRST item of its range and the tail
+    the LAST item of the next one, and the head ends (in steps since the launch began) no later than the tail starts --
+    McNaughton's wrap-around rule, so a CTA never actually waits for its predecessor."""
+    lib = tg.load_library()
+    lib.tfhe_b200_persistent_plan.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                              C.POINTER(C.c_uint32)]
+    out = (C.c_uint32 * 3)()
+    covered = np.zeros((groups, n), dtype=np.int32)
+    head_end, tail_start, sizes = {}, {}, []
+    for k in range(ctas):
+        items = lib.tfhe_b200_persistent_plan(groups, n, ctas, k, -1, None)
+        assert items >= 1
+        t = 0                                                   # steps this CTA has run so far
+        for it in range(items):
+            assert lib.tfhe_b200_persistent_plan(groups, n, ctas, k, it, out) == items
+            g, sb, se = out[0], out[1], out[2]
+            assert g < groups and sb < se <= n
+            covered[g, sb:se] += 1
+            if se < n:                                          # head part: first item, starts at step 0 of the group
+                assert it == 0 and sb == 0
+                head_end[g] = t + (se - sb)
+            if sb > 0:                                          # tail part: last item, runs to the end of the group
+                assert it == items - 1 and se == n
+                tail_start[g] = t
+            t += se - sb
+        sizes.append(t)
+    assert (covered == 1).all()
+    assert max(sizes) - min(sizes) <= 1 and min(sizes) >= n
+    assert set(head_end) == set(tail_start)
+    for g in head_end:
+        assert head_end[g] <= tail_start[g], (g, head_end[g], tail_start[g])
+    assert len(head_end) <= ctas - 1
+
+
+def test_persistent_plan_rejects_bad_arguments():
+    lib = tg.load_library()
+    lib.tfhe_b200_persistent_plan.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                              C.POINTER(C.c_uint32)]
+    out = (C.c_uint32 * 3)()
+    assert lib.tfhe_b200_persistent_plan(0, 10, 1, 0, -1, None) < 0
+    assert lib.tfhe_b200_persistent_plan(4, 10, 5, 0, -1, None) < 0        # a range would be shorter than n steps
+    assert lib.tfhe_b200_persistent_plan(8, 10, 4, 4, -1, None) < 0
+    assert lib.tfhe_b200_persistent_plan(8, 10, 4, 1, 99, out) < 0

@@ -90,6 +90,7 @@ EXPORTS = [
     "tfhe_b200_eval_func", "tfhe_b200_eval_floor", "tfhe_b200_eval_sign", "tfhe_b200_eval_decomp",
     "tfhe_b200_eval_bin_gate_v", "tfhe_b200_eval_circuit", "tfhe_b200_keygen", "tfhe_b200_keygen_test_seed", "tfhe_b200_setup_from_serialized",
     "tfhe_b200_serialized_info", "tfhe_b200_flatten_serialized", "tfhe_b200_add_key_set", "tfhe_b200_num_key_sets",
+    "tfhe_b200_persistent_plan",
 ]
 
 

@@ -160,8 +160,6 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     const bool odd_lane = tid & 1;
 
     // ---- persistent variant: this CTA's range of the launch's groups * n rotation steps ----------------------------
-    u32 gA = 0, sA = 0, gB = 0, sB = 0, first_full = 0;
-    int n_full = 0, n_items = 1;
     // The ranges are handed out in the order the CTAs START (a ticket, as in decoupled look-back scans), not by
     // blockIdx: range k only ever waits for range k - 1, whose CTA is then running or done whatever order the hardware
     // dispatches blocks in.
@@ -173,14 +171,10 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
         __syncthreads();
         bid = s_bid;
     }
-    if (PERS) {
-        const u64 Wt = (u64)A.pers_groups * n;
-        const u64 lo = Wt * bid / gridDim.x, hi = Wt * (bid + 1) / gridDim.x;
-        gA = (u32)(lo / n); sA = (u32)(lo % n); gB = (u32)(hi / n); sB = (u32)(hi % n);
-        first_full = gA + (sA ? 1 : 0);
-        n_full = (int)gB - (int)first_full;
-        n_items = (sB ? 1 : 0) + n_full + (sA ? 1 : 0);
-    }
+    PersRange range;
+    range.n_items = 1;
+    if (PERS)
+        range = PersRange::of(A.pers_groups, n, gridDim.x, bid);
 
     // ---- one-time loads: psi-power table, per-thread twiddles ------------------------------------------------
     // bit-rotated index: the distinct exponents a warp touches differ in their top bits only, which become the low
@@ -212,14 +206,11 @@ __global__ void __launch_bounds__(LAT ? 2 * DK * ((1 << LOGN) / 32) : KCfg<LOGN,
     u32 c[32];
     u32 bk_pre[TMA ? 1 : 4 * D];   // key slice of (step, slot tid), requested one step ahead (register-staged variant)
 
-    for (int item = 0; item < n_items; item++) {
+    for (int item = 0; item < range.n_items; item++) {
     // this item: rotation steps [sb, se) of group grp (the whole rotation unless PERS)
     u32 grp = bid, sb = 0, se = n;
     if (PERS) {
-        const int u = item - (sB ? 1 : 0);
-        if (u < 0) { grp = gB; se = sB; }
-        else if (u < n_full) grp = first_full + (u32)u;
-        else { grp = gA; sb = sA; }
+        range.item(item, n, grp, sb, se);
         __syncthreads();   // the previous item is done with the exponents and the digit regions
     }
     const int ct = (int)grp * G + g;

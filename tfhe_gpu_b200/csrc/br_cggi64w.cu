@@ -75,8 +75,6 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
     const int blk = T >> 3, u8 = T & 7;
 
     // persistent variant: this CTA's range of the launch's groups * n rotation steps (br_cggi32.cu)
-    u32 gA = 0, sA = 0, gB = 0, sB = 0, first_full = 0;
-    int n_full = 0, n_items = 1;
     // The ranges are handed out in the order the CTAs START (a ticket, as in decoupled look-back scans), not by
     // blockIdx: range k only ever waits for range k - 1, whose CTA is then running or done whatever order the hardware
     // dispatches blocks in.
@@ -88,14 +86,10 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
         __syncthreads();
         bid = s_bid;
     }
-    if (PERS) {
-        const u64 Wt = (u64)A.pers_groups * n;
-        const u64 lo = Wt * bid / gridDim.x, hi = Wt * (bid + 1) / gridDim.x;
-        gA = (u32)(lo / n); sA = (u32)(lo % n); gB = (u32)(hi / n); sB = (u32)(hi % n);
-        first_full = gA + (sA ? 1 : 0);
-        n_full = (int)gB - (int)first_full;
-        n_items = (sB ? 1 : 0) + n_full + (sA ? 1 : 0);
-    }
+    PersRange range;
+    range.n_items = 1;
+    if (PERS)
+        range = PersRange::of(A.pers_groups, n, gridDim.x, bid);
 
     for (int x = tid; x < 15 * TPN; x += NT)
         twC[x] = reinterpret_cast<const ulonglong2*>(A.twC)[x];
@@ -130,14 +124,11 @@ __global__ void __launch_bounds__(KW<DK, G>::NT, 1) br_cggi64w_kernel(const __gr
             v[r] = csub(v[r], Q16);   // 11 lazy stages: < 45 Q -> < 29 Q (27-bit limb split of the pointwise stage)
     };
 
-    for (int item = 0; item < n_items; item++) {
+    for (int item = 0; item < range.n_items; item++) {
     // this item: rotation steps [sb, se) of group grp (the whole rotation unless PERS)
     u32 grp = bid, sb = 0, se = n;
     if (PERS) {
-        const int u = item - (sB ? 1 : 0);
-        if (u < 0) { grp = gB; se = sB; }
-        else if (u < n_full) grp = first_full + (u32)u;
-        else { grp = gA; sb = sA; }
+        range.item(item, n, grp, sb, se);
         __syncthreads();   // the previous item is done with the digit regions and the wrap bitmaps
     }
     const int ct = (int)grp * G + g;

@@ -1145,6 +1145,21 @@ extern "C" int tfhe_b200_add_key_set(tfhe_b200_handle* h, uint32_t baseG, const 
     h->key_map[baseG] = c;
     return 0;
 }
+extern "C" int tfhe_b200_persistent_plan(uint32_t groups, uint32_t n, uint32_t ctas, uint32_t cta, int item,
+                                         uint32_t out[3]) {
+    if (groups == 0 || n == 0 || ctas == 0 || cta >= ctas)
+        FAIL(TFHE_B200_EINVAL, "persistent_plan: empty launch or range index out of bounds");
+    if (ctas > groups)
+        FAIL(TFHE_B200_EINVAL, "persistent_plan: more CTAs than groups (a range must hold at least n steps)");
+    const PersRange r = PersRange::of(groups, n, ctas, cta);
+    if (item >= 0) {
+        if (item >= r.n_items || !out)
+            FAIL(TFHE_B200_EINVAL, "persistent_plan: item out of range");
+        r.item(item, n, out[0], out[1], out[2]);
+    }
+    return r.n_items;
+}
+
 extern "C" int tfhe_b200_num_key_sets(const tfhe_b200_handle* h) {
     return h ? 1 + (int)h->key_map.size() : 0;
 }

@@ -42,6 +42,33 @@ struct BRCommon {
     u64 ext_add_b;              // constant added to b on extraction (Q8 for gates, 0 for functions)
 };
 
+// Persistent blind rotation (br_cggi32.cu, br_cggi64w.cu): the groups * n rotation steps of a launch are cut into
+// `ctas` equal contiguous ranges (McNaughton's wrap-around rule).  Range k is the last steps of group gA (from step sA),
+// n_full whole groups starting at first_full, and the first sB steps of group gB; it is worked off as items in the order
+// head of gB, whole groups, tail of gA, so that the two parts of a split group never run at the same time.
+struct PersRange {
+    u32 gA, sA, gB, sB, first_full;
+    int n_full, n_items;
+    __host__ __device__ static inline PersRange of(u32 groups, u32 n, u32 ctas, u32 k) {
+        PersRange r;
+        const u64 Wt = (u64)groups * n;
+        const u64 lo = Wt * k / ctas, hi = Wt * (k + 1) / ctas;
+        r.gA = (u32)(lo / n); r.sA = (u32)(lo % n); r.gB = (u32)(hi / n); r.sB = (u32)(hi % n);
+        r.first_full = r.gA + (r.sA ? 1 : 0);
+        r.n_full = (int)r.gB - (int)r.first_full;
+        r.n_items = (r.sB ? 1 : 0) + r.n_full + (r.sA ? 1 : 0);
+        return r;
+    }
+    // item t of the range: rotation steps [sb, se) of group grp
+    __host__ __device__ inline void item(int t, u32 n, u32& grp, u32& sb, u32& se) const {
+        const int u = t - (sB ? 1 : 0);
+        sb = 0; se = n;
+        if (u < 0) { grp = gB; se = sB; }
+        else if (u < n_full) grp = first_full + (u32)u;
+        else { grp = gA; sb = sA; }
+    }
+};
+
 template <typename T>
 struct BRTables {
     ModCtx<T> mod;
