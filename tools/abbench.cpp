@@ -87,7 +87,7 @@ int main(int argc, char** argv) {
         }
     }
     if (libs.empty()) {
-        fprintf(stderr, "usage: abbench [--set std128|toy|ap] [--batch B,..] [--reps R] LIB[:opt=val] ...\n");
+        fprintf(stderr, "usage: abbench [--set std128|ap|toy|medium|std128_ap_set|std256|std256q|func12|sign17] [--batch B,..] [--reps R] LIB[:opt=val] ...\n");
         return 1;
     }
     tfhe_b200_params P;
